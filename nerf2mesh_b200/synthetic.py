@@ -1,0 +1,155 @@
+"""Synthetic, seeded stand-ins for the datasets the reference trains on (no datasets or network
+are available): Lego-like orbit cameras, ray sampling exactly as the reference's collate does it,
+an analytic "bricks" scene (axis-aligned coloured boxes) with its occupancy grid in the
+reference's Morton/bitfield layout, and analytic ground-truth colours for those rays.
+
+Shapes / conventions follow SURVEY.md section 8(d): 100 poses on the upper hemisphere at radius
+4.031 * 0.8, 800x800, fl = 400 / tan(0.5 * 0.6911), rays exactly as nerf/utils.py:282-290
+(unnormalised directions, -z forward, y flipped), pixel ids via randint as provider.py:303 and
+utils.py:271.  Pure torch/numpy host code; no kernels.
+"""
+import math
+
+import numpy as np
+import torch
+
+LEGO_RADIUS = 4.031 * 0.8
+LEGO_FOVX = 0.6911
+LEGO_HW = 800
+
+
+def look_at_pose(cam_pos):
+    """camera-to-world, OpenGL convention (camera looks down -z, y up), looking at the origin."""
+    c = np.asarray(cam_pos, np.float64)
+    fwd = -c / np.linalg.norm(c)                 # viewing direction
+    up = np.array([0.0, 0.0, 1.0])
+    if abs(np.dot(fwd, up)) > 0.999:
+        up = np.array([0.0, 1.0, 0.0])
+    right = np.cross(fwd, up); right /= np.linalg.norm(right)
+    true_up = np.cross(right, fwd)
+    pose = np.eye(4)
+    pose[:3, 0] = right
+    pose[:3, 1] = true_up
+    pose[:3, 2] = -fwd
+    pose[:3, 3] = c
+    return pose
+
+
+def orbit_cameras(n=100, radius=LEGO_RADIUS, seed=0, min_elev=0.05, max_elev=1.3):
+    """n camera-to-world poses on the upper hemisphere (seeded)."""
+    rng = np.random.default_rng(seed)
+    az = rng.uniform(0, 2 * math.pi, n)
+    el = rng.uniform(min_elev, max_elev, n)
+    pos = np.stack([radius * np.cos(el) * np.cos(az), radius * np.cos(el) * np.sin(az), radius * np.sin(el)], -1)
+    return torch.from_numpy(np.stack([look_at_pose(p) for p in pos]).astype(np.float32))
+
+
+def lego_intrinsics(H=LEGO_HW, W=LEGO_HW, fovx=LEGO_FOVX):
+    fl = 0.5 * W / math.tan(0.5 * fovx)
+    return np.array([fl, fl, W / 2, H / 2], np.float32)
+
+
+def sample_rays(poses, intrinsics, H, W, N, generator=None):
+    """Random (image, pixel) pairs -> rays_o, rays_d [N,3] float32 (host tensors).
+    Mirrors provider.py:303 (image index per ray) + utils.py:242-290 (pixel centre +0.5,
+    directions ((i-cx)/fx, -(j-cy)/fy, -1) rotated by the pose, unnormalised)."""
+    fx, fy, cx, cy = [float(v) for v in intrinsics]
+    img = torch.randint(0, poses.shape[0], (N,), generator=generator)
+    pix = torch.randint(0, H * W, (N,), generator=generator)
+    i = (pix % W).float() + 0.5
+    j = (pix // W).float() + 0.5
+    dirs = torch.stack([(i - cx) / fx, -(j - cy) / fy, -torch.ones_like(i)], -1)        # [N,3]
+    R = poses[img, :3, :3]
+    rays_d = torch.einsum("nij,nj->ni", R, dirs).contiguous()
+    rays_o = poses[img, :3, 3].contiguous()
+    return rays_o, rays_d, img, pix
+
+
+# ---- analytic bricks scene ------------------------------------------------------------------
+def make_bricks(n_boxes=40, extent=0.7, seed=1, min_size=0.08, max_size=0.25):
+    """Seeded axis-aligned boxes inside [-extent, extent]^3: (lo [K,3], hi [K,3], rgb [K,3])."""
+    rng = np.random.default_rng(seed)
+    size = rng.uniform(min_size, max_size, (n_boxes, 3))
+    ctr = rng.uniform(-extent, extent, (n_boxes, 3))
+    lo = np.clip(ctr - size, -extent, extent)
+    hi = np.clip(ctr + size, -extent, extent)
+    rgb = rng.uniform(0.1, 0.95, (n_boxes, 3))
+    return (torch.from_numpy(lo.astype(np.float32)), torch.from_numpy(hi.astype(np.float32)),
+            torch.from_numpy(rgb.astype(np.float32)))
+
+
+def render_bricks(rays_o, rays_d, bricks):
+    """Analytic first-hit render: returns rgba [N,4] (alpha 1 on hit, 0 on miss)."""
+    lo, hi, rgb = bricks
+    o = rays_o[:, None, :]; d = rays_d[:, None, :]
+    inv = 1.0 / torch.where(d.abs() < 1e-9, torch.full_like(d, 1e-9), d)
+    t0 = (lo[None] - o) * inv
+    t1 = (hi[None] - o) * inv
+    tmin = torch.minimum(t0, t1).amax(-1)
+    tmax = torch.maximum(t0, t1).amin(-1)
+    hit = (tmax >= tmin) & (tmax > 0)
+    tmin = torch.where(hit, tmin.clamp(min=0), torch.full_like(tmin, float("inf")))
+    t_first, k = tmin.min(-1)
+    any_hit = torch.isfinite(t_first)
+    col = rgb[k] * any_hit[:, None]
+    return torch.cat([col, any_hit[:, None].float()], -1)
+
+
+def _morton_np(c):
+    def spread(v):
+        v = v.astype(np.uint64)
+        v = (v | (v << 16)) & 0x030000FF
+        v = (v | (v << 8)) & 0x0300F00F
+        v = (v | (v << 4)) & 0x030C30C3
+        v = (v | (v << 2)) & 0x09249249
+        return v
+    return (spread(c[..., 0]) | (spread(c[..., 1]) << 1) | (spread(c[..., 2]) << 2)).astype(np.int64)
+
+
+def occupancy_from_bricks(bricks, H=128, bound=1.0, cascades=1, dilate=1):
+    """density_grid float32 [cascades, H^3] in the reference's layout (cascade-major, Morton-ordered
+    cells, renderer.py:1100-1118) with 1.0 inside (dilated) bricks, 0 elsewhere."""
+    lo, hi, _ = bricks
+    lo = lo.numpy(); hi = hi.numpy()
+    ax = np.arange(H)
+    coords = np.stack(np.meshgrid(ax, ax, ax, indexing="ij"), -1).reshape(-1, 3)
+    mort = _morton_np(coords)
+    grid = np.zeros((cascades, H ** 3), np.float32)
+    for cas in range(cascades):
+        b = min(2 ** cas, bound)
+        cell = 2 * b / H
+        ctr = (coords + 0.5) * cell - b
+        pad = dilate * cell
+        inside = np.zeros(len(coords), bool)
+        for k in range(len(lo)):
+            inside |= ((ctr >= lo[k] - pad) & (ctr <= hi[k] + pad)).all(-1)
+        grid[cas, mort] = inside.astype(np.float32)
+    return torch.from_numpy(grid)
+
+
+def packbits_host(grid, thresh=0.5):
+    """host-side packbits (bit i of byte n <-> cell 8n+i), for building synthetic inputs only."""
+    g = grid.reshape(-1, 8).numpy() > thresh
+    return torch.from_numpy((g.astype(np.uint8) << np.arange(8, dtype=np.uint8)).sum(-1).astype(np.uint8))
+
+
+def occupancy_regime(regime, H=128, cascades=1, bound=1.0, seed=1):
+    """'cold' (everything occupied), 'mid' (~30 % cells), 'converged' (bricks; ~16 % of cells, ~70 samples/ray => M ~ 2^18 at 4096 rays).
+    Returns (density_grid [cas, H^3] float32, bitfield uint8 [cas*H^3/8], bricks)."""
+    bricks = make_bricks(seed=seed)
+    if regime == "cold":
+        grid = torch.ones(cascades, H ** 3)
+    elif regime == "mid":
+        g = torch.Generator().manual_seed(seed)
+        # blocky 30 %: occupancy decided per 8^3 super-cell so rays see coherent runs
+        sc = (torch.rand((H // 8) ** 3, generator=g) < 0.30)
+        ax = np.arange(H)
+        coords = np.stack(np.meshgrid(ax, ax, ax, indexing="ij"), -1).reshape(-1, 3)
+        sidx = (coords[:, 0] // 8) * (H // 8) ** 2 + (coords[:, 1] // 8) * (H // 8) + coords[:, 2] // 8
+        grid = torch.zeros(cascades, H ** 3)
+        grid[:, torch.from_numpy(_morton_np(coords))] = sc[torch.from_numpy(sidx)].float()
+    elif regime == "converged":
+        grid = occupancy_from_bricks(bricks, H, bound, cascades)
+    else:
+        raise ValueError(regime)
+    return grid, packbits_host(grid), bricks
