@@ -1,0 +1,127 @@
+/* n2m_b200_fused.h -- C ABI of the FUSED stage-0 train path of libn2m_b200.so.
+ *
+ * The operator-level entry points in n2m_b200.h are the drop-in replacements for the reference's
+ * pybind functions.  The entry points here implement the same arithmetic as ONE pipeline with a
+ * B200-native data layout, no host synchronisation and no per-step allocation, so the whole train
+ * step can be captured in a CUDA graph.  What each stage replaces in the reference:
+ *
+ *   n2m_s0_march          raymarching.near_far_from_aabb + march_rays_train (raymarching.py:19-49,181-245;
+ *                          raymarching.cu:92-145,338-475) without the .item() sync (raymarching.py:232)
+ *   n2m_s0_encode_fwd     GridEncoder.forward x2 (grid.py:151-168; gridencoder.cu:88-196) + cat + safe_normalize
+ *   n2m_s0_mlp_fwd        sigma_net / color_net / specular_net + trunc_exp / sigmoid / clamp
+ *                          (nerf/network.py:81-108,159-189) on tcgen05 tensor cores
+ *   n2m_s0_composite_loss composite_rays_train fwd+bwd (raymarching.cu:501-694), background mix
+ *                          (renderer.py:804) and the MSE(+mask, +specular) loss (utils.py:660-738)
+ *   n2m_s0_mlp_bwd        autograd of the three MLPs (dgrad + wgrad) on tcgen05
+ *   n2m_s0_encode_bwd     grid_encode backward x2 (gridencoder.cu:248-339) + grad_total_variation
+ *                          (gridencoder.cu:506-609; utils.py:801-823)
+ *   n2m_s0_adam           GradScaler.unscale_/step/update + Adam(eps 1e-15) + the per-step fp32->fp16
+ *                          table cast (grid.py:45-46) + zero_grad  (utils.py:549,1163,1176-1177)
+ *
+ * Data layout (all buffers allocated by the caller, see nerf2mesh_b200/stage0.py):
+ *   table      [rows]  8-byte entries {float density_feature; half2 colour_features}: the density table
+ *              (fp32, C=1) and the fp16 working copy of the colour table (C=2) interleaved so that one
+ *              64-bit access serves both encoders.  fp32 colour masters live in `color_master [rows] float2`.
+ *   gtable     [rows]  float4 {g_density, g_colour0, g_colour1, 0}, loss-scaled, reduced with one
+ *              red.global.add.v4.f32 per lattice corner.
+ *   enc_tiles  one 16 KiB image per 128 samples: fp16 [128 x 64] in the UMMA no-swizzle core-matrix layout
+ *              (chunk-major, tc05.cuh): cols 0-2 xyz, 3-18 density features, 19-50 colour features,
+ *              51-53 unit view direction, 54-63 zero.  It is the A operand of every first-layer GEMM and is
+ *              staged global->shared with a single bulk async copy.
+ *   recs       [Mcap] float4 {t_before, dt, t_after, ray_id (bits)} per sample, ray order.
+ *   counters   int32 [4]: [0] M (total samples marched), [1] min(M, Mcap), [2] overflow flag, [3] unused.
+ *   wpack      packed fp16 MLP weights in tensor-core tile layout (n2m_s0_pack_weights).
+ */
+#ifndef N2M_B200_FUSED_H
+#define N2M_B200_FUSED_H
+
+#include "n2m_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct {
+    float bound;            /* marching bound (renderer.real_bound) */
+    float grid_bound;       /* bound that normalises positions for the hash grid (renderer.bound) */
+    float inv_2gb;          /* float32(1) / float32(2 * grid_bound) -- torch divides by a scalar this way */
+    float dt_gamma;
+    float min_near;
+    float T_thresh;
+    float S;                /* log2(per_level_scale) as float32 (grid.py:38) */
+    float lambda_mask;
+    float lambda_specular;
+    float lambda_tv;
+    uint32_t contract;
+    uint32_t max_steps;
+    uint32_t cascades;
+    uint32_t grid_size;
+    uint32_t num_levels;    /* must be 16 */
+    uint32_t base_res;
+    uint32_t shading_full;  /* 0 = 'diffuse' (first diffuse_step iterations), 1 = 'full' */
+    uint32_t gt_has_alpha;  /* gt is rgba: blend with bg and add the mask loss (utils.py:662-667,681-683) */
+} n2m_s0_params;
+
+/* sizes of the packed weight blob (bytes) and of the flat fp32 MLP parameter / gradient vector (floats) */
+uint32_t n2m_s0_wpack_bytes(void);
+uint32_t n2m_s0_mlp_param_count(void);      /* 7648 = 608+32 + 2240+4096+384 + 192+96 */
+
+/* fp32 masters (reference nn.Linear layouts [out,in], concatenated: sigma0, sigma1, color0, color1, color2,
+ * spec0, spec1) -> packed fp16 tiles */
+int n2m_s0_pack_weights(const float* mlp_params, void* wpack, n2m_stream_t stream);
+
+/* interleave / de-interleave the hash tables (import / export of reference-format tensors) */
+int n2m_s0_pack_tables(const float* emb_density, const float* emb_color, uint32_t rows,
+                       void* table, void* color_master, n2m_stream_t stream);
+int n2m_s0_unpack_tables(const void* table, const void* color_master, uint32_t rows,
+                         float* emb_density, float* emb_color, n2m_stream_t stream);
+/* gtable (loss-scaled float4) -> reference-format gradients, divided by *loss_scale */
+int n2m_s0_unpack_grads(const void* gtable, uint32_t rows, const float* loss_scale,
+                        float* g_density, float* g_color, n2m_stream_t stream);
+
+/* march: near/far + count + scan + sample records.  cam_near_far [N,2] nullable (renderer.py:689-691). */
+int n2m_s0_march(const n2m_s0_params* p, const float* rays_o, const float* rays_d, const float* aabb,
+                 const float* cam_near_far, const uint8_t* bitfield, const float* noises, uint32_t N,
+                 int32_t* rays, int32_t* counters, float* tbuf, void* recs, uint32_t Mcap,
+                 n2m_stream_t stream);
+
+int n2m_s0_encode_fwd(const n2m_s0_params* p, const void* recs, const int32_t* counters, uint32_t Mcap,
+                      const float* rays_o, const float* rays_d, const void* table, const int32_t* offsets,
+                      void* enc_tiles, n2m_stream_t stream);
+
+/* out [Mcap] float4 {sigma, r, g, b}; spec_sq_sum: += sum over samples of |specular|^2 (for the loss value) */
+int n2m_s0_mlp_fwd(const n2m_s0_params* p, const void* enc_tiles, const int32_t* counters, uint32_t Mcap,
+                   const void* wpack, void* out, float* spec_sq_sum, n2m_stream_t stream);
+
+/* per ray: composite, loss, composite backward.  gt [N,4] (rgba) or [N,3]; bg [N,3].
+ * dout [Mcap] float4 {dL/dsigma, dL/dr, dL/dg, dL/db} * loss_scale (zero beyond each ray's break).
+ * loss_out float[4]: [0] += sum_rays per-ray loss / N, [1] += mask term; image/ws/depth [N] outputs. */
+int n2m_s0_composite_loss(const n2m_s0_params* p, const void* out, const void* recs, const int32_t* rays,
+                          const int32_t* counters, uint32_t N, uint32_t Mcap, const float* gt, const float* bg,
+                          const float* loss_scale, void* dout, float* image, float* weights_sum, float* depth,
+                          float* loss_out, n2m_stream_t stream);
+
+/* MLP backward: denc_tiles (same tile layout as enc_tiles, fp16, loss-scaled), g_mlp flat fp32 [7648] += */
+int n2m_s0_mlp_bwd(const n2m_s0_params* p, const void* enc_tiles, const void* dout, const int32_t* counters,
+                   uint32_t Mcap, const void* wpack, void* denc_tiles, float* g_mlp, const float* loss_scale,
+                   n2m_stream_t stream);
+
+/* scatter denc into gtable (+ TV gradient of the density features, scaled by *loss_scale) */
+int n2m_s0_encode_bwd(const n2m_s0_params* p, const void* recs, const int32_t* counters, uint32_t Mcap,
+                      const float* rays_o, const float* rays_d, const void* denc_tiles, const void* table,
+                      const int32_t* offsets, void* gtable, const float* loss_scale, n2m_stream_t stream);
+
+/* optimizer state block (device, float[8]): [0] loss_scale, [1] growth_tracker, [2] adam step t,
+ * [3] found_inf (set by n2m_s0_check_grads), [4] lr (host-written each step), [5..7] reserved */
+int n2m_s0_check_grads(const void* gtable, uint32_t rows, const float* g_mlp, float* opt_state, n2m_stream_t stream);
+
+/* Adam (betas 0.9/0.999, eps) on tables + MLP; unscales by loss_scale, skips everything when found_inf,
+ * refreshes the fp16 working copies (table, wpack), zeroes gtable / g_mlp, then updates the scaler. */
+int n2m_s0_adam(void* table, void* color_master, void* gtable, float* m_table, float* v_table, uint32_t rows,
+                float* mlp_params, float* g_mlp, float* m_mlp, float* v_mlp, void* wpack,
+                float* opt_state, float eps, n2m_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* N2M_B200_FUSED_H */

@@ -1,0 +1,558 @@
+// stage0.cu -- fused stage-0 train path, the non-tensor-core stages (see include/n2m_b200_fused.h):
+//   march (near/far + count + scan + sample records), hash-grid encode forward into tensor-core
+//   tile images, composite + loss + composite-backward per ray, hash-grid scatter (+TV) backward,
+//   table (de)interleave helpers.  The MLP stages live in mlp_tc.cu, the optimizer in optim.cu.
+#include "march_core.cuh"
+#include "tc05.cuh"
+#include "../../include/n2m_b200_fused.h"
+
+namespace n2m {
+namespace {
+
+using namespace march;
+
+constexpr uint32_t kTile = 128;            // samples per tile image
+constexpr uint32_t kTileCols = 64;         // fp16 features per sample
+constexpr uint32_t kTileBytes = kTile * kTileCols * 2;
+constexpr uint32_t kChunkBytes = kTile * 16;   // one 8-column chunk of a 128-row tile
+constexpr uint32_t kColXyz = 0, kColDens = 3, kColColor = 19, kColDir = 51;
+constexpr uint32_t kLevels = 16;
+
+struct __align__(8) TableEntry { float d; __half2 c; };
+
+// ------------------------------------------------------------------------------------------------
+// march
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_s0_count(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ aabb,
+           const float* __restrict__ cam_nf, const uint8_t* __restrict__ bits, const float* __restrict__ noises,
+           n2m_s0_params p, uint32_t N, int32_t* __restrict__ rays, float2* __restrict__ tbuf) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const MarchCfg c = make_cfg(p.bound, p.contract != 0, p.dt_gamma, p.max_steps, p.cascades, p.grid_size, bits);
+    float near, far;
+    near_far_aabb(rays_o + 3 * n, rays_d + 3 * n, aabb, p.min_near, near, far);
+    if (cam_nf) {                      // renderer.py:689-691
+        near = fmaxf(near, cam_nf[2 * n]);
+        far = fminf(far, cam_nf[2 * n + 1]);
+    }
+    const float ox = rays_o[3 * n], oy = rays_o[3 * n + 1], oz = rays_o[3 * n + 2];
+    const float dx = rays_d[3 * n], dy = rays_d[3 * n + 1], dz = rays_d[3 * n + 2];
+    const float rdx = 1 / dx, rdy = 1 / dy, rdz = 1 / dz;
+    float t0 = near;
+    t0 += clampf(t0 * c.dt_gamma, c.dt_min, c.dt_max) * noises[n];
+    CountSink sink{tbuf + (size_t)n * p.max_steps};
+    const uint32_t cnt = march_one(c, t0, far, p.max_steps, ox, oy, oz, dx, dy, dz, rdx, rdy, rdz, sink);
+    rays[2 * n + 1] = (int32_t)cnt;
+}
+
+// single-block exclusive scan (N is a few thousand rays) -> offsets + counters
+__global__ void __launch_bounds__(1024)
+k_s0_scan(int32_t* __restrict__ rays, uint32_t N, uint32_t Mcap, int32_t* __restrict__ counters) {
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t carry_s;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < N; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < N ? (uint32_t)rays[2 * i + 1] : 0u;
+        uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        if (lane == 31) warp_tot[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t w = warp_tot[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += u;
+            }
+            warp_tot[lane] = w;
+        }
+        __syncthreads();
+        const uint32_t carry = carry_s;
+        if (i < N) rays[2 * i] = (int32_t)(carry + (wid ? warp_tot[wid - 1] : 0u) + inc - v);
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + warp_tot[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const uint32_t M = carry_s;
+        counters[0] = (int32_t)M;
+        counters[1] = (int32_t)min(M, Mcap);
+        counters[2] = M > Mcap ? 1 : 0;
+        counters[3] = 0;
+    }
+}
+
+// one warp per ray: sample records {t_before, dt, t_after, ray}
+__global__ void __launch_bounds__(256)
+k_s0_records(const int32_t* __restrict__ rays, const float2* __restrict__ tbuf, uint32_t N, uint32_t max_steps,
+             uint32_t Mcap, float4* __restrict__ recs) {
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const uint32_t off = (uint32_t)rays[2 * n], cnt = (uint32_t)rays[2 * n + 1];
+    const float2* slab = tbuf + (size_t)n * max_steps;
+    for (uint32_t k = lane; k < cnt; k += 32) {
+        const uint32_t j = off + k;
+        if (j >= Mcap) break;
+        const float2 td = slab[k];
+        recs[j] = make_float4(td.x, td.y, td.x + td.y, __int_as_float((int)n));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared sample geometry
+// ------------------------------------------------------------------------------------------------
+struct Sample {
+    float x, y, z;        // (contracted) position handed to the network
+    float u, v, w;        // position mapped to [0,1]^3 for the grid
+    float dx, dy, dz;     // raw ray direction
+};
+
+__device__ __forceinline__ Sample sample_of(const float4 rec, const float* __restrict__ rays_o,
+                                            const float* __restrict__ rays_d, const n2m_s0_params& p) {
+    Sample s;
+    const int n = __float_as_int(rec.w);
+    const float ox = rays_o[3 * n], oy = rays_o[3 * n + 1], oz = rays_o[3 * n + 2];
+    s.dx = rays_d[3 * n]; s.dy = rays_d[3 * n + 1]; s.dz = rays_d[3 * n + 2];
+    const float t = rec.x;
+    s.x = clampf(ox + t * s.dx, -p.bound, p.bound);
+    s.y = clampf(oy + t * s.dy, -p.bound, p.bound);
+    s.z = clampf(oz + t * s.dz, -p.bound, p.bound);
+    const float mag = fmaxf(fabsf(s.x), fmaxf(fabsf(s.y), fabsf(s.z)));
+    if (p.contract && mag > 1) {
+        const float k = (2 - 1 / mag) / mag;
+        s.x *= k; s.y *= k; s.z *= k;
+    }
+    // GridEncoder.forward: (x + bound) / (2 * bound); torch divides by a python scalar as a
+    // multiplication with float32(1)/float32(2*bound)
+    s.u = __fmul_rn(__fadd_rn(s.x, p.grid_bound), p.inv_2gb);
+    s.v = __fmul_rn(__fadd_rn(s.y, p.grid_bound), p.inv_2gb);
+    s.w = __fmul_rn(__fadd_rn(s.z, p.grid_bound), p.inv_2gb);
+    return s;
+}
+
+// lattice geometry of one level for one sample: the 8 corner rows and trilinear weights
+struct Corners {
+    uint32_t row[8];
+    float w[8];
+};
+
+struct LevelGeom {
+    float scale;
+    uint32_t res, rows, row0;
+};
+
+__device__ __forceinline__ LevelGeom level_geom(const int32_t* __restrict__ offsets, uint32_t level, float S, uint32_t H) {
+    LevelGeom g;
+    g.row0 = (uint32_t)offsets[level];
+    g.rows = (uint32_t)offsets[level + 1] - g.row0;
+    g.scale = exp2f(level * S) * H - 1.0f;          // gridencoder.cu:138 (same expression, same flags)
+    g.res = (uint32_t)ceil(g.scale) + 1;
+    return g;
+}
+
+// returns false when the sample is outside [0,1]^3 (the encoders output zeros there)
+__device__ __forceinline__ void corners_of(const LevelGeom& g, float u, float v, float w, Corners& c,
+                                           uint32_t (&base)[3], bool& hashed) {
+    const float pu = u * g.scale + 0.5f, pv = v * g.scale + 0.5f, pw = w * g.scale + 0.5f;
+    const float fu0 = floorf(pu), fv0 = floorf(pv), fw0 = floorf(pw);
+    const uint32_t x0 = fu0, y0 = fv0, z0 = fw0;
+    base[0] = x0; base[1] = y0; base[2] = z0;
+    const float fx = pu - (float)x0, fy = pv - (float)y0, fz = pw - (float)z0;
+    // index: dense while the running stride fits the level's rows, else hashed (gridencoder.cu:66-84)
+    const uint32_t s1 = g.res + 1;
+    uint32_t stride = 1;
+    uint32_t mx = 0, my = 0, mz = 0;          // dense multipliers (0 = dimension not accumulated)
+    if (stride <= g.rows) { mx = stride; stride *= s1; }
+    if (stride <= g.rows) { my = stride; stride *= s1; }
+    if (stride <= g.rows) { mz = stride; stride *= s1; }
+    hashed = stride > g.rows;
+    uint32_t xs[2], ys[2], zs[2];
+    if (hashed) {
+        xs[0] = x0;                 xs[1] = x0 + 1u;
+        ys[0] = y0 * 2654435761u;   ys[1] = ys[0] + 2654435761u;
+        zs[0] = z0 * 805459861u;    zs[1] = zs[0] + 805459861u;
+    } else {
+        xs[0] = x0 * mx;            xs[1] = xs[0] + mx;
+        ys[0] = y0 * my;            ys[1] = ys[0] + my;
+        zs[0] = z0 * mz;            zs[1] = zs[0] + mz;
+    }
+    const float wx[2] = {1 - fx, fx}, wy[2] = {1 - fy, fy}, wz[2] = {1 - fz, fz};
+    const bool pow2 = (g.rows & (g.rows - 1)) == 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int ix = k & 1, iy = (k >> 1) & 1, iz = (k >> 2) & 1;
+        const uint32_t raw = hashed ? (xs[ix] ^ ys[iy] ^ zs[iz]) : (xs[ix] + ys[iy] + zs[iz]);
+        c.row[k] = pow2 ? (raw & (g.rows - 1)) : (raw % g.rows);
+        c.w[k] = wx[ix] * wy[iy] * wz[iz];
+    }
+}
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// ------------------------------------------------------------------------------------------------
+// encode forward: one block = one 128-sample tile image
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTile)
+k_s0_encode_fwd(n2m_s0_params p, const float4* __restrict__ recs, const int32_t* __restrict__ counters,
+                const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                const TableEntry* __restrict__ table, const int32_t* __restrict__ offsets,
+                uint8_t* __restrict__ enc_tiles) {
+    const uint32_t M = (uint32_t)counters[1];
+    const uint32_t tile = blockIdx.x, r = threadIdx.x;
+    if (tile * kTile >= M) return;
+    const uint32_t j = tile * kTile + r;
+    float feat[kTileCols];
+#pragma unroll
+    for (uint32_t i = 0; i < kTileCols; ++i) feat[i] = 0.f;
+
+    if (j < M) {
+        const Sample s = sample_of(recs[j], rays_o, rays_d, p);
+        feat[kColXyz] = s.x; feat[kColXyz + 1] = s.y; feat[kColXyz + 2] = s.z;
+        // safe_normalize (utils.py:41-42): d / sqrt(clamp(sum d^2, 1e-20))
+        const float n2 = __fadd_rn(__fadd_rn(__fmul_rn(s.dx, s.dx), __fmul_rn(s.dy, s.dy)), __fmul_rn(s.dz, s.dz));
+        const float nrm = __fsqrt_rn(fmaxf(n2, 1e-20f));
+        feat[kColDir] = __fdiv_rn(s.dx, nrm); feat[kColDir + 1] = __fdiv_rn(s.dy, nrm); feat[kColDir + 2] = __fdiv_rn(s.dz, nrm);
+        const bool oob = (s.u < 0 || s.u > 1) || (s.v < 0 || s.v > 1) || (s.w < 0 || s.w > 1);
+        if (!oob) {
+#pragma unroll
+            for (uint32_t l = 0; l < kLevels; ++l) {
+                const LevelGeom g = level_geom(offsets, l, p.S, p.base_res);
+                Corners c; uint32_t base[3]; bool hashed;
+                corners_of(g, s.u, s.v, s.w, c, base, hashed);
+                const TableEntry* tab = table + g.row0;
+                uint2 raw[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) raw[k] = __ldg(reinterpret_cast<const uint2*>(tab + c.row[k]));
+                float d = 0.f, c0 = 0.f, c1 = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float2 cc = __half22float2(*reinterpret_cast<const __half2*>(&raw[k].y));
+                    d += c.w[k] * __uint_as_float(raw[k].x);
+                    c0 += c.w[k] * cc.x;
+                    c1 += c.w[k] * cc.y;
+                }
+                feat[kColDens + l] = d;
+                feat[kColColor + 2 * l] = c0;
+                feat[kColColor + 2 * l + 1] = c1;
+            }
+        }
+    }
+    // write this row of the tile image: 8 chunks of 16 bytes, each chunk 2 KiB apart
+    uint8_t* img = enc_tiles + (size_t)tile * kTileBytes + r * 16;
+#pragma unroll
+    for (uint32_t ch = 0; ch < 8; ++ch) {
+        uint4 q;
+        q.x = pack2(feat[8 * ch + 0], feat[8 * ch + 1]);
+        q.y = pack2(feat[8 * ch + 2], feat[8 * ch + 3]);
+        q.z = pack2(feat[8 * ch + 4], feat[8 * ch + 5]);
+        q.w = pack2(feat[8 * ch + 6], feat[8 * ch + 7]);
+        *reinterpret_cast<uint4*>(img + ch * kChunkBytes) = q;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// encode backward: scatter the (loss-scaled, fp16) feature gradients + TV gradient
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTile)
+k_s0_encode_bwd(n2m_s0_params p, const float4* __restrict__ recs, const int32_t* __restrict__ counters,
+                const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                const uint8_t* __restrict__ denc_tiles, const TableEntry* __restrict__ table,
+                const int32_t* __restrict__ offsets, float4* __restrict__ gtable, const float* __restrict__ loss_scale) {
+    const uint32_t M = (uint32_t)counters[1];
+    const uint32_t tile = blockIdx.x, r = threadIdx.x;
+    const uint32_t j = tile * kTile + r;
+    if (j >= M) return;
+    const Sample s = sample_of(recs[j], rays_o, rays_d, p);
+    const bool oob = (s.u < 0 || s.u > 1) || (s.v < 0 || s.v > 1) || (s.w < 0 || s.w > 1);
+    if (oob) return;
+
+    // this row's gradients: cols 3..18 density, 19..50 colour  (chunks 0..6)
+    const uint8_t* img = denc_tiles + (size_t)tile * kTileBytes + r * 16;
+    float g[56];
+#pragma unroll
+    for (uint32_t ch = 0; ch < 7; ++ch) {
+        const uint4 q = *reinterpret_cast<const uint4*>(img + ch * kChunkBytes);
+        const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&qq[i]));
+            g[8 * ch + 2 * i] = f.x; g[8 * ch + 2 * i + 1] = f.y;
+        }
+    }
+    // TV weight: lambda inside the unit cube, 10 lambda outside when bound > 1 (utils.py:815-821)
+    const float mag = fmaxf(fabsf(s.x), fmaxf(fabsf(s.y), fabsf(s.z)));
+    const float lam = (p.grid_bound > 1 && mag > 1) ? p.lambda_tv * 10 : p.lambda_tv;
+    const float tvw = lam / 6 * loss_scale[0];       // w = weight / (2 * D), kept in the scaled domain
+    const bool do_tv = p.lambda_tv > 0;
+
+#pragma unroll
+    for (uint32_t l = 0; l < kLevels; ++l) {
+        const LevelGeom lg = level_geom(offsets, l, p.S, p.base_res);
+        Corners c; uint32_t base[3]; bool hashed;
+        corners_of(lg, s.u, s.v, s.w, c, base, hashed);
+        float4* gt = gtable + lg.row0;
+        const float gd = g[kColDens + l], g0 = g[kColColor + 2 * l], g1 = g[kColColor + 2 * l + 1];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            atomicAdd(gt + c.row[k], make_float4(c.w[k] * gd, c.w[k] * g0, c.w[k] * g1, 0.f));
+
+        if (do_tv) {        // gridencoder.cu:506-609 on the density feature
+            const TableEntry* tab = table + lg.row0;
+            const uint32_t s1 = lg.res + 1;
+            uint32_t stride = 1, mult[3] = {0, 0, 0};
+#pragma unroll
+            for (int d = 0; d < 3; ++d) if (stride <= lg.rows) { mult[d] = stride; stride *= s1; }
+            const uint32_t prime[3] = {1u, 2654435761u, 805459861u};
+            auto row_of = [&](uint32_t x, uint32_t y, uint32_t z) -> uint32_t {
+                const uint32_t raw = hashed ? ((x * prime[0]) ^ (y * prime[1]) ^ (z * prime[2]))
+                                            : (x * mult[0] + y * mult[1] + z * mult[2]);
+                return raw % lg.rows;
+            };
+            const float centre = __ldg(&tab[c.row[0]].d);
+            float sum = 0.f, sq = 0.f;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                uint32_t q[3] = {base[0], base[1], base[2]};
+                const uint32_t cur = base[d];
+                if (cur < lg.res) {
+                    q[d] = cur + 1;
+                    const float dv = centre - __ldg(&tab[row_of(q[0], q[1], q[2])].d);
+                    sum += dv; sq += dv * dv;
+                }
+                if (cur > 0) {
+                    q[d] = cur - 1;
+                    const float dv = centre - __ldg(&tab[row_of(q[0], q[1], q[2])].d);
+                    sum += dv; sq += dv * dv;
+                }
+            }
+            atomicAdd(&gt[c.row[0]].x, tvw * sum * rsqrtf(sq + 1e-9f));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// composite forward + loss + composite backward: one thread per ray
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_s0_composite_loss(n2m_s0_params p, const float4* __restrict__ out, const float4* __restrict__ recs,
+                    const int32_t* __restrict__ rays, const int32_t* __restrict__ counters, uint32_t N,
+                    const float* __restrict__ gt, const float* __restrict__ bg, const float* __restrict__ loss_scale,
+                    float4* __restrict__ dout, float* __restrict__ image, float* __restrict__ weights_sum,
+                    float* __restrict__ depth, float* __restrict__ loss_out) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    float my_loss = 0.f;
+    if (n < N) {
+        const uint32_t M = (uint32_t)counters[1];
+        const uint32_t off = rays[2 * n], cnt = rays[2 * n + 1];
+        const bool live = cnt != 0 && off + cnt <= M;
+        float T = 1.0f, r = 0, g = 0, b = 0, ws = 0, d = 0;
+        if (live) {
+            for (uint32_t k = 0; k < cnt; ++k) {
+                const float4 o = out[off + k];
+                const float4 rc = recs[off + k];
+                const float alpha = 1.0f - __expf(-o.x * rc.y);
+                const float w = alpha * T;
+                r += w * o.y; g += w * o.z; b += w * o.w;
+                ws += w;
+                d += w * rc.z;
+                T *= 1.0f - alpha;
+                if (T < p.T_thresh) break;
+            }
+        }
+        // background mix (renderer.py:804) and loss (utils.py:660-683), per ray
+        const float b0 = bg[3 * n], b1 = bg[3 * n + 1], b2 = bg[3 * n + 2];
+        const float om = 1 - ws;
+        const float pr = r + om * b0, pg = g + om * b1, pb = b + om * b2;
+        float t0, t1, t2, mask = 0.f;
+        if (p.gt_has_alpha) {
+            mask = gt[4 * n + 3];
+            t0 = gt[4 * n] * mask + b0 * (1 - mask);
+            t1 = gt[4 * n + 1] * mask + b1 * (1 - mask);
+            t2 = gt[4 * n + 2] * mask + b2 * (1 - mask);
+        } else {
+            t0 = gt[3 * n]; t1 = gt[3 * n + 1]; t2 = gt[3 * n + 2];
+        }
+        const float e0 = pr - t0, e1 = pg - t1, e2 = pb - t2;
+        my_loss = (e0 * e0 + e1 * e1 + e2 * e2) * (1.0f / 3.0f);
+        const float invN = 1.0f / (float)N;
+        const float sc = loss_scale[0] * invN;
+        // d loss / d pred (mean over 3 channels, mean over N rays), loss-scaled
+        const float gi0 = sc * (2.0f / 3.0f) * e0, gi1 = sc * (2.0f / 3.0f) * e1, gi2 = sc * (2.0f / 3.0f) * e2;
+        // pred = image + (1 - ws) * bg  =>  d/d ws picks up -bg . g_pred (+ the mask term)
+        float gws = -(gi0 * b0 + gi1 * b1 + gi2 * b2);
+        if (p.gt_has_alpha && p.lambda_mask > 0) {
+            const float em = ws - mask;
+            my_loss += p.lambda_mask * em * em;
+            gws += sc * p.lambda_mask * 2.0f * em;
+        }
+        my_loss *= invN;
+        image[3 * n] = pr; image[3 * n + 1] = pg; image[3 * n + 2] = pb;
+        weights_sum[n] = ws;
+        depth[n] = d;
+
+        // composite backward (raymarching.cu:605-694), grad_weights = grad_depth = 0
+        if (live) {
+            const float r_fin = r, g_fin = g, b_fin = b, ws_fin = ws;
+            T = 1.0f; r = g = b = ws = 0;
+            uint32_t k = 0;
+            for (; k < cnt; ++k) {
+                const float4 o = out[off + k];
+                const float dtj = recs[off + k].y;
+                const float alpha = 1.0f - __expf(-o.x * dtj);
+                const float w = alpha * T;
+                r += w * o.y; g += w * o.z; b += w * o.w;
+                ws += w;
+                T *= 1.0f - alpha;
+                const float gs = dtj * (gi0 * (T * o.y - (r_fin - r)) + gi1 * (T * o.z - (g_fin - g)) +
+                                        gi2 * (T * o.w - (b_fin - b)) + gws * (T - (ws_fin - ws)));
+                dout[off + k] = make_float4(gs, gi0 * w, gi1 * w, gi2 * w);
+                if (T < p.T_thresh) { ++k; break; }
+            }
+            for (; k < cnt; ++k) dout[off + k] = make_float4(0.f, 0.f, 0.f, 0.f);   // past the break
+        } else if (cnt != 0) {
+            for (uint32_t k = 0; k < cnt && off + k < M; ++k) dout[off + k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    // block-reduce the loss, one atomic per block
+    __shared__ float red[4];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) my_loss += __shfl_xor_sync(0xffffffffu, my_loss, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = my_loss;
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(loss_out, red[0] + red[1] + red[2] + red[3]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// table (de)interleave
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_s0_pack_tables(const float* __restrict__ ed, const float* __restrict__ ec, uint32_t rows,
+                 TableEntry* __restrict__ table, float2* __restrict__ cmaster) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    const float2 c = make_float2(ec[2 * i], ec[2 * i + 1]);
+    TableEntry e; e.d = ed[i]; e.c = __floats2half2_rn(c.x, c.y);
+    table[i] = e;
+    cmaster[i] = c;
+}
+
+__global__ void __launch_bounds__(256)
+k_s0_unpack_tables(const TableEntry* __restrict__ table, const float2* __restrict__ cmaster, uint32_t rows,
+                   float* __restrict__ ed, float* __restrict__ ec) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    ed[i] = table[i].d;
+    ec[2 * i] = cmaster[i].x; ec[2 * i + 1] = cmaster[i].y;
+}
+
+__global__ void __launch_bounds__(256)
+k_s0_unpack_grads(const float4* __restrict__ gtable, uint32_t rows, const float* __restrict__ loss_scale,
+                  float* __restrict__ gd, float* __restrict__ gc) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    const float inv = 1.0f / loss_scale[0];
+    const float4 g = gtable[i];
+    gd[i] = g.x * inv; gc[2 * i] = g.y * inv; gc[2 * i + 1] = g.z * inv;
+}
+
+}  // namespace
+}  // namespace n2m
+
+using namespace n2m;
+
+extern "C" {
+
+int n2m_s0_pack_tables(const float* emb_density, const float* emb_color, uint32_t rows, void* table, void* color_master,
+                       n2m_stream_t stream) {
+    N2M_REQUIRE(emb_density && emb_color && table && color_master, "s0_pack_tables", "null pointer");
+    k_s0_pack_tables<<<div_up(rows, 256u), 256, 0, as_stream(stream)>>>(emb_density, emb_color, rows,
+                                                                         static_cast<TableEntry*>(table), static_cast<float2*>(color_master));
+    return check_launch("s0_pack_tables");
+}
+
+int n2m_s0_unpack_tables(const void* table, const void* color_master, uint32_t rows, float* emb_density, float* emb_color,
+                         n2m_stream_t stream) {
+    N2M_REQUIRE(emb_density && emb_color && table && color_master, "s0_unpack_tables", "null pointer");
+    k_s0_unpack_tables<<<div_up(rows, 256u), 256, 0, as_stream(stream)>>>(static_cast<const TableEntry*>(table),
+                                                                           static_cast<const float2*>(color_master), rows, emb_density, emb_color);
+    return check_launch("s0_unpack_tables");
+}
+
+int n2m_s0_unpack_grads(const void* gtable, uint32_t rows, const float* loss_scale, float* g_density, float* g_color,
+                        n2m_stream_t stream) {
+    N2M_REQUIRE(gtable && loss_scale && g_density && g_color, "s0_unpack_grads", "null pointer");
+    k_s0_unpack_grads<<<div_up(rows, 256u), 256, 0, as_stream(stream)>>>(static_cast<const float4*>(gtable), rows, loss_scale, g_density, g_color);
+    return check_launch("s0_unpack_grads");
+}
+
+int n2m_s0_march(const n2m_s0_params* p, const float* rays_o, const float* rays_d, const float* aabb,
+                 const float* cam_near_far, const uint8_t* bitfield, const float* noises, uint32_t N, int32_t* rays,
+                 int32_t* counters, float* tbuf, void* recs, uint32_t Mcap, n2m_stream_t stream) {
+    N2M_REQUIRE(p && rays && counters, "s0_march", "null pointer");
+    cudaStream_t st = as_stream(stream);
+    if (N == 0) { cudaMemsetAsync(counters, 0, 4 * sizeof(int32_t), st); return 0; }
+    N2M_REQUIRE(rays_o && rays_d && aabb && bitfield && noises && tbuf && recs, "s0_march", "null pointer");
+    N2M_REQUIRE(p->max_steps > 0 && p->grid_size > 0 && p->cascades > 0, "s0_march", "bad params");
+    k_s0_count<<<div_up(N, 128u), 128, 0, st>>>(rays_o, rays_d, aabb, cam_near_far, bitfield, noises, *p, N, rays,
+                                                 reinterpret_cast<float2*>(tbuf));
+    if (int e = check_launch("s0_march(count)")) return e;
+    k_s0_scan<<<1, 1024, 0, st>>>(rays, N, Mcap, counters);
+    if (int e = check_launch("s0_march(scan)")) return e;
+    k_s0_records<<<div_up(N * 32u, 256u), 256, 0, st>>>(rays, reinterpret_cast<const float2*>(tbuf), N, p->max_steps, Mcap,
+                                                        static_cast<float4*>(recs));
+    return check_launch("s0_march(records)");
+}
+
+int n2m_s0_encode_fwd(const n2m_s0_params* p, const void* recs, const int32_t* counters, uint32_t Mcap,
+                      const float* rays_o, const float* rays_d, const void* table, const int32_t* offsets, void* enc_tiles,
+                      n2m_stream_t stream) {
+    N2M_REQUIRE(p && recs && counters && rays_o && rays_d && table && offsets && enc_tiles, "s0_encode_fwd", "null pointer");
+    N2M_REQUIRE(p->num_levels == kLevels, "s0_encode_fwd", "fused path supports num_levels == 16");
+    N2M_REQUIRE(Mcap % kTile == 0 && Mcap > 0, "s0_encode_fwd", "Mcap must be a positive multiple of 128");
+    k_s0_encode_fwd<<<Mcap / kTile, kTile, 0, as_stream(stream)>>>(*p, static_cast<const float4*>(recs), counters, rays_o, rays_d,
+                                                                   static_cast<const TableEntry*>(table), offsets,
+                                                                   static_cast<uint8_t*>(enc_tiles));
+    return check_launch("s0_encode_fwd");
+}
+
+int n2m_s0_encode_bwd(const n2m_s0_params* p, const void* recs, const int32_t* counters, uint32_t Mcap,
+                      const float* rays_o, const float* rays_d, const void* denc_tiles, const void* table,
+                      const int32_t* offsets, void* gtable, const float* loss_scale, n2m_stream_t stream) {
+    N2M_REQUIRE(p && recs && counters && rays_o && rays_d && denc_tiles && table && offsets && gtable && loss_scale,
+                "s0_encode_bwd", "null pointer");
+    N2M_REQUIRE(p->num_levels == kLevels, "s0_encode_bwd", "fused path supports num_levels == 16");
+    N2M_REQUIRE(Mcap % kTile == 0 && Mcap > 0, "s0_encode_bwd", "Mcap must be a positive multiple of 128");
+    k_s0_encode_bwd<<<Mcap / kTile, kTile, 0, as_stream(stream)>>>(*p, static_cast<const float4*>(recs), counters, rays_o, rays_d,
+                                                                   static_cast<const uint8_t*>(denc_tiles),
+                                                                   static_cast<const TableEntry*>(table), offsets,
+                                                                   static_cast<float4*>(gtable), loss_scale);
+    return check_launch("s0_encode_bwd");
+}
+
+int n2m_s0_composite_loss(const n2m_s0_params* p, const void* out, const void* recs, const int32_t* rays,
+                          const int32_t* counters, uint32_t N, uint32_t Mcap, const float* gt, const float* bg,
+                          const float* loss_scale, void* dout, float* image, float* weights_sum, float* depth,
+                          float* loss_out, n2m_stream_t stream) {
+    (void)Mcap;
+    if (N == 0) return 0;
+    N2M_REQUIRE(p && out && recs && rays && counters && gt && bg && loss_scale && dout && image && weights_sum && depth && loss_out,
+                "s0_composite_loss", "null pointer");
+    k_s0_composite_loss<<<div_up(N, 128u), 128, 0, as_stream(stream)>>>(*p, static_cast<const float4*>(out), static_cast<const float4*>(recs),
+                                                                        rays, counters, N, gt, bg, loss_scale, static_cast<float4*>(dout),
+                                                                        image, weights_sum, depth, loss_out);
+    return check_launch("s0_composite_loss");
+}
+
+}  // extern "C"
