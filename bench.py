@@ -1,0 +1,278 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native stage-0 train step (BASELINE.json metric:
+ray-samples/sec of one full train step, device-timed).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm
+    python bench.py --impl reference [--steps K] [--warmup W]      # CPU restatement of the reference step
+    torchrun --nproc-per-node N bench.py --gpus N ...              # one rank per GPU (NCCL)
+
+One "step" = one optimizer step of the fused pipeline on one batch of 4096 synthetic Lego-like rays
+(march -> hash-grid encode -> tcgen05 MLPs -> composite + loss -> backward -> TV -> Adam), workload
+"lego_stage0_converged" (SURVEY.md section 8d, config 2).  `value` = samples of all ranks / max-over-ranks
+device time with the batch already resident in HBM; `e2e` = the same through Stage0Trainer.step() with
+pinned-host batches (H2D inside the timed region) and a D2H read of the loss every step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "lego_stage0_converged"
+NUM_RAYS = 4096
+ALG_BYTES = {"encode_fwd": 1053, "encode_bwd": 1024, "step": 2077}      # SURVEY.md section 8(d), bytes per sample
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            pk = json.load(f)
+        return float(pk["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def make_batches(n_batches, seed, pin):
+    from nerf2mesh_b200 import synthetic as S
+    grid, bits, bricks = S.occupancy_regime("converged")
+    poses = S.orbit_cameras(100, seed=0)
+    intr = S.lego_intrinsics()
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(n_batches):
+        ro, rd, _, _ = S.sample_rays(poses, intr, 800, 800, NUM_RAYS, g)
+        gt = S.render_bricks(ro, rd, bricks)
+        bg = torch.rand(NUM_RAYS, 3, generator=g)
+        noises = torch.rand(NUM_RAYS, generator=g)
+        b = dict(ro=ro, rd=rd, gt=gt, bg=bg, noises=noises)
+        if pin:
+            b = {k: v.pin_memory() for k, v in b.items()}
+        out.append(b)
+    return out, grid, bits
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the repo's PyTorch restatement of the reference step (there is no reference CPU path)
+# ------------------------------------------------------------------------------------------------
+def cpu_step_rate(steps, warmup, rays=256):
+    from oracle import train_oracle as T
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    batches, grid, bits = make_batches(1, 123, False)
+    b = {k: v[:rays] for k, v in batches[0].items()}
+    f = T.OracleField(1.0)
+    opt = torch.optim.Adam(f.parameters(), lr=1e-2, eps=1e-15)
+    cfg = dict(bound=1.0, C=1, H=128)
+    samples, t_total = 0, 0.0
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        _, out = T.train_step(f, opt, b["ro"], b["rd"], b["gt"], bits, cfg, b["noises"], b["bg"], "full", True)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            samples += out["num_points"]; t_total += dt
+    return samples / t_total, t_total / max(steps, 1), torch.get_num_threads(), rays
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3)); warmup = min(args.warmup, 1)
+    v, sec, cores, rays = cpu_step_rate(steps, warmup)
+    line = {"impl": "reference", "metric": "ray-samples/sec (train step)", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "rays_per_batch": NUM_RAYS},
+            "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+                             "sample": f"{rays} of the {NUM_RAYS} rays of one batch, full train step (oracle/train_oracle.py), {steps} timed steps"},
+            "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (nerf2mesh_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from nerf2mesh_b200 import _lib
+    from nerf2mesh_b200.stage0 import Stage0Config, Stage0Trainer
+    from nerf2mesh_b200.parallel import GradSync
+
+    cfg = Stage0Config(bound=1.0, num_rays=NUM_RAYS, max_samples=NUM_RAYS * 128)
+    tr = Stage0Trainer(cfg, seed=0)
+    sync = GradSync(tr) if world > 1 else None
+    n_batches = 8
+    host_batches, grid, bits = make_batches(n_batches, 1000 + rank, True)
+    dev_batches = [{k: v.cuda(non_blocking=True) for k, v in b.items()} for b in host_batches]
+    tr.set_occupancy(bits, grid)
+    m_total = torch.zeros(1, dtype=torch.int64, device="cuda")
+    K, W = args.steps, args.warmup
+
+    def one_step(b, it):
+        tr.step(b["ro"], b["rd"], b["gt"], b["bg"], b["noises"], shading="full", use_graph=not args.no_graph, grad_sync=sync)
+        m_total.add_(tr.counters[1])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- launches per step (eager, counted by the library) ----
+    l0 = _lib.launch_count()
+    tr.step(dev_batches[0]["ro"], dev_batches[0]["rd"], dev_batches[0]["gt"], dev_batches[0]["bg"], dev_batches[0]["noises"],
+            use_graph=False, grad_sync=sync)
+    torch.cuda.synchronize()
+    launches_per_step = _lib.launch_count() - l0
+
+    # ---- leg 1: device-resident inputs ----
+    for it in range(W):
+        one_step(dev_batches[it % n_batches], it)
+    barrier()
+    m_total.zero_()
+    sampler = ClockSampler(local); sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for it in range(K):
+        one_step(dev_batches[it % n_batches], it)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    samples = m_total.clone().float()
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(samples, op=dist.ReduceOp.SUM)
+    ms_total = ms.item(); samples_total = samples.item()
+    value = samples_total / (ms_total * 1e-3)
+
+    # ---- leg 2: end to end (pinned host -> device inside the timed region, loss read back every step) ----
+    barrier()
+    m_total.zero_()
+    loss_host = torch.zeros(4).pin_memory(); cnt_host = torch.zeros(4, dtype=torch.int32).pin_memory()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    f0.record()
+    e2e_samples = 0
+    for it in range(K):
+        b = host_batches[it % n_batches]
+        tr.step(b["ro"], b["rd"], b["gt"], b["bg"], b["noises"], shading="full", use_graph=not args.no_graph, grad_sync=sync)
+        loss_host.copy_(tr.loss_acc, non_blocking=True); cnt_host.copy_(tr.counters, non_blocking=True)
+        torch.cuda.current_stream().synchronize()            # the user-visible result of the step
+        e2e_samples += int(cnt_host[1])
+    f1.record()
+    barrier()
+    ms2 = torch.tensor([f0.elapsed_time(f1)], device="cuda"); s2 = torch.tensor([float(e2e_samples)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX); dist.all_reduce(s2, op=dist.ReduceOp.SUM)
+    e2e_value = s2.item() / (ms2.item() * 1e-3)
+    h2d = sum(v.numel() * v.element_size() for v in host_batches[0].values())
+    d2h = loss_host.numel() * 4 + cnt_host.numel() * 4
+
+    # ---- per-stage device times (eager, CUDA events on the launching stream) -> roofline of the dominant kernel ----
+    stages = ["march", "encode_fwd", "mlp_fwd", "composite_loss", "mlp_bwd", "encode_bwd", "adam"]
+    acc = {s: 0.0 for s in stages}
+    reps = 5
+    flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda")     # > 126 MB L2
+    for r in range(reps):
+        b = dev_batches[r % n_batches]
+        tr.rays_o.copy_(b["ro"]); tr.rays_d.copy_(b["rd"]); tr.gt.copy_(b["gt"]); tr.bg.copy_(b["bg"]); tr.noises.copy_(b["noises"])
+        tr.loss_acc.zero_()
+        for s in stages:
+            flush.fill_(0.0)
+            a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); getattr(tr, s)(); z.record()
+            torch.cuda.synchronize()
+            acc[s] += a.elapsed_time(z) / reps
+    M_last = int(tr.counters[1].item())
+    peak, peak_kind = load_peaks()
+    dom = max(("encode_fwd", "encode_bwd"), key=lambda s: acc[s])
+    achieved = ALG_BYTES[dom] * M_last / (acc[dom] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_s0_" + dom, "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "alg_bytes_per_sample": ALG_BYTES[dom], "samples_per_launch": M_last,
+                "kernel_ms": acc[dom], "stage_ms_cold_l2": {k: round(v, 4) for k, v in acc.items()},
+                "step_frac_of_hbm": ALG_BYTES["step"] * value / 1e9 / peak}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.skip_cpu:
+            v, sec, cores, rays = cpu_step_rate(1, 1)
+            cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+                   "sample": f"{rays} of the {NUM_RAYS} rays of one batch, full train step (oracle/train_oracle.py), 1 warm-up + 1 timed"}
+        line = {"metric": "ray-samples/sec (train step)", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD, "rays_per_batch": NUM_RAYS, "global_rays": NUM_RAYS * world,
+                           "samples_per_step": samples_total / K, "parallelism": f"dp{world}", "cuda_graph": not args.no_graph,
+                           "l2": "inputs cycle over 8 batches; tables+grads+Adam state (0.6 GB touched per step) exceed the 126 MB L2"},
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms2.item() / K},
+                "gpu_launches": int(launches_per_step * K), "launches_per_step": int(launches_per_step),
+                "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -62,6 +62,9 @@ typedef struct {
     uint32_t gt_has_alpha;  /* gt is rgba: blend with bg and add the mask loss (utils.py:662-667,681-683) */
 } n2m_s0_params;
 
+/* one-time per-process setup (kernel attributes); call before the first fused launch / graph capture */
+int n2m_s0_init(void);
+
 /* sizes of the packed weight blob (bytes) and of the flat fp32 MLP parameter / gradient vector (floats) */
 uint32_t n2m_s0_wpack_bytes(void);
 uint32_t n2m_s0_mlp_param_count(void);      /* 7648 = 608+32 + 2240+4096+384 + 192+96 */
@@ -112,8 +115,9 @@ int n2m_s0_encode_bwd(const n2m_s0_params* p, const void* recs, const int32_t* c
                       const int32_t* offsets, void* gtable, const float* loss_scale, n2m_stream_t stream);
 
 /* optimizer state block (device, float[8]): [0] loss_scale, [1] growth_tracker, [2] adam step t,
- * [3] found_inf (set by n2m_s0_check_grads), [4] lr (host-written each step), [5..7] reserved */
-int n2m_s0_check_grads(const void* gtable, uint32_t rows, const float* g_mlp, float* opt_state, n2m_stream_t stream);
+ * [3] found_inf, [4] lr (host-written each step), [5] 1-beta1^t, [6] sqrt(1-beta2^t), [7] 1/loss_scale.
+ * Every `loss_scale` pointer argument above is the base of this block: the kernels read [0] and set [3]
+ * when they see a non-finite gradient (instead of GradScaler's separate unscale_/inf-check pass). */
 
 /* Adam (betas 0.9/0.999, eps) on tables + MLP; unscales by loss_scale, skips everything when found_inf,
  * refreshes the fp16 working copies (table, wpack), zeroes gtable / g_mlp, then updates the scaler. */

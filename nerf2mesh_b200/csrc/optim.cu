@@ -1,0 +1,129 @@
+// optim.cu -- optimizer stage of the fused train path: GradScaler bookkeeping + Adam (torch
+// semantics: betas (0.9, 0.999), eps 1e-15 as main.py:221, no weight decay) over the interleaved hash
+// tables and the MLP parameters, fused with the passes the reference runs separately every step:
+// unscale_ (utils.py:812), the fp32 -> fp16 colour-table cast (grid.py:45-46), zero_grad
+// (utils.py:1163) and GradScaler.step/update (utils.py:1176-1177).
+//
+// opt_state (device float[8]): [0] loss_scale  [1] growth_tracker  [2] adam step t  [3] found_inf
+//                              [4] lr (host-written)  [5] 1 - beta1^t  [6] sqrt(1 - beta2^t)  [7] 1 / loss_scale
+#include "n2m_common.cuh"
+#include "../../include/n2m_b200_fused.h"
+
+namespace n2m {
+namespace {
+
+constexpr float kBeta1 = 0.9f, kBeta2 = 0.999f;
+constexpr float kGrowth = 2.0f, kBackoff = 0.5f;
+constexpr float kGrowthInterval = 2000.f;
+
+struct __align__(8) TableEntry { float d; __half2 c; };
+
+__global__ void k_adam_prep(float* __restrict__ st) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const bool skip = st[3] != 0.f;
+    if (!skip) st[2] += 1.f;
+    const float t = fmaxf(st[2], 1.f);
+    st[5] = 1.f - powf(kBeta1, t);
+    st[6] = sqrtf(1.f - powf(kBeta2, t));
+    st[7] = 1.f / st[0];
+}
+
+__global__ void k_adam_post(float* __restrict__ st) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    // torch.amp.GradScaler.update: back off on inf, otherwise grow every growth_interval clean steps
+    if (st[3] != 0.f) { st[0] *= kBackoff; st[1] = 0.f; }
+    else {
+        st[1] += 1.f;
+        if (st[1] >= kGrowthInterval) { st[0] *= kGrowth; st[1] = 0.f; }
+    }
+    st[3] = 0.f;
+}
+
+__device__ __forceinline__ float adam_update(float p, float g, float& m, float& v, float lr_over_bc1, float bc2s, float eps) {
+    m = kBeta1 * m + (1.f - kBeta1) * g;
+    v = kBeta2 * v + (1.f - kBeta2) * g * g;
+    const float denom = __fdiv_rn(__fsqrt_rn(v), bc2s) + eps;
+    return p - lr_over_bc1 * __fdiv_rn(m, denom);
+}
+
+// one thread per table row: {density feature fp32 (master lives in the table), 2 colour features (fp32
+// masters in cmaster, fp16 copy in the table)}.  m/v: [rows] density then [rows][2] colour.
+__global__ void __launch_bounds__(256)
+k_adam_tables(TableEntry* __restrict__ table, float2* __restrict__ cmaster, float4* __restrict__ gtable,
+              float* __restrict__ m, float* __restrict__ v, uint32_t rows, const float* __restrict__ st, float eps) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    const bool skip = st[3] != 0.f;
+    float4 g = gtable[i];
+    gtable[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (skip) return;
+    const float inv = st[7];
+    g.x *= inv; g.y *= inv; g.z *= inv;
+    const float lr1 = __fdiv_rn(st[4], st[5]), bc2s = st[6];
+    float md = m[i], vd = v[i];
+    float2 mc = reinterpret_cast<float2*>(m + rows)[i], vc = reinterpret_cast<float2*>(v + rows)[i];
+    // untouched row with empty moments: the update is exactly zero -- skip the writes
+    if (g.x == 0.f && g.y == 0.f && g.z == 0.f && md == 0.f && vd == 0.f && mc.x == 0.f && mc.y == 0.f && vc.x == 0.f && vc.y == 0.f)
+        return;
+    TableEntry e = table[i];
+    float2 pc = cmaster[i];
+    e.d = adam_update(e.d, g.x, md, vd, lr1, bc2s, eps);
+    pc.x = adam_update(pc.x, g.y, mc.x, vc.x, lr1, bc2s, eps);
+    pc.y = adam_update(pc.y, g.z, mc.y, vc.y, lr1, bc2s, eps);
+    e.c = __floats2half2_rn(pc.x, pc.y);
+    table[i] = e;
+    cmaster[i] = pc;
+    m[i] = md; v[i] = vd;
+    reinterpret_cast<float2*>(m + rows)[i] = mc;
+    reinterpret_cast<float2*>(v + rows)[i] = vc;
+}
+
+__global__ void __launch_bounds__(256)
+k_adam_mlp(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, uint32_t n,
+           const float* __restrict__ st, float eps) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const bool skip = st[3] != 0.f;
+    const float gi = g[i] * st[7];
+    g[i] = 0.f;
+    if (skip) return;
+    float mi = m[i], vi = v[i];
+    p[i] = adam_update(p[i], gi, mi, vi, __fdiv_rn(st[4], st[5]), st[6], eps);
+    m[i] = mi; v[i] = vi;
+}
+
+// non-finite scan of the MLP gradient vector (the table gradients are checked where they are produced)
+__global__ void __launch_bounds__(256)
+k_check_mlp(const float* __restrict__ g, uint32_t n, float* __restrict__ st) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && !isfinite(g[i])) st[3] = 1.f;
+}
+
+}  // namespace
+}  // namespace n2m
+
+using namespace n2m;
+
+extern "C" int n2m_s0_pack_weights(const float* mlp_params, void* wpack, n2m_stream_t stream);
+extern "C" uint32_t n2m_s0_mlp_param_count(void);
+
+extern "C" int n2m_s0_adam(void* table, void* color_master, void* gtable, float* m_table, float* v_table, uint32_t rows,
+                           float* mlp_params, float* g_mlp, float* m_mlp, float* v_mlp, void* wpack, float* opt_state,
+                           float eps, n2m_stream_t stream) {
+    N2M_REQUIRE(table && color_master && gtable && m_table && v_table && mlp_params && g_mlp && m_mlp && v_mlp && wpack && opt_state,
+                "s0_adam", "null pointer");
+    cudaStream_t st = as_stream(stream);
+    const uint32_t n = n2m_s0_mlp_param_count();
+    k_check_mlp<<<div_up(n, 256u), 256, 0, st>>>(g_mlp, n, opt_state);
+    if (int e = check_launch("s0_adam(check)")) return e;
+    k_adam_prep<<<1, 32, 0, st>>>(opt_state);
+    if (int e = check_launch("s0_adam(prep)")) return e;
+    k_adam_tables<<<div_up(rows, 256u), 256, 0, st>>>(static_cast<TableEntry*>(table), static_cast<float2*>(color_master),
+                                                      static_cast<float4*>(gtable), m_table, v_table, rows, opt_state, eps);
+    if (int e = check_launch("s0_adam(tables)")) return e;
+    k_adam_mlp<<<div_up(n, 256u), 256, 0, st>>>(mlp_params, g_mlp, m_mlp, v_mlp, n, opt_state, eps);
+    if (int e = check_launch("s0_adam(mlp)")) return e;
+    if (int e = n2m_s0_pack_weights(mlp_params, wpack, stream)) return e;
+    k_adam_post<<<1, 32, 0, st>>>(opt_state);
+    return check_launch("s0_adam(post)");
+}

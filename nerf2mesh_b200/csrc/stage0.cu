@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(kTile)
 k_s0_encode_bwd(n2m_s0_params p, const float4* __restrict__ recs, const int32_t* __restrict__ counters,
                 const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                 const uint8_t* __restrict__ denc_tiles, const TableEntry* __restrict__ table,
-                const int32_t* __restrict__ offsets, float4* __restrict__ gtable, const float* __restrict__ loss_scale) {
+                const int32_t* __restrict__ offsets, float4* __restrict__ gtable, float* __restrict__ loss_scale) {
     const uint32_t M = (uint32_t)counters[1];
     const uint32_t tile = blockIdx.x, r = threadIdx.x;
     const uint32_t j = tile * kTile + r;
@@ -290,6 +290,12 @@ k_s0_encode_bwd(n2m_s0_params p, const float4* __restrict__ recs, const int32_t*
             const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&qq[i]));
             g[8 * ch + 2 * i] = f.x; g[8 * ch + 2 * i + 1] = f.y;
         }
+    }
+    {   // fp16 overflow of the loss-scaled gradients => GradScaler semantics: flag, step is skipped
+        bool bad = false;
+#pragma unroll
+        for (int i = (int)kColDens; i < (int)kColDir; ++i) bad |= !isfinite(g[i]);
+        if (bad) loss_scale[3] = 1.f;
     }
     // TV weight: lambda inside the unit cube, 10 lambda outside when bound > 1 (utils.py:815-821)
     const float mag = fmaxf(fabsf(s.x), fmaxf(fabsf(s.y), fabsf(s.z)));
@@ -537,7 +543,7 @@ int n2m_s0_encode_bwd(const n2m_s0_params* p, const void* recs, const int32_t* c
     k_s0_encode_bwd<<<Mcap / kTile, kTile, 0, as_stream(stream)>>>(*p, static_cast<const float4*>(recs), counters, rays_o, rays_d,
                                                                    static_cast<const uint8_t*>(denc_tiles),
                                                                    static_cast<const TableEntry*>(table), offsets,
-                                                                   static_cast<float4*>(gtable), loss_scale);
+                                                                   static_cast<float4*>(gtable), const_cast<float*>(loss_scale));
     return check_launch("s0_encode_bwd");
 }
 

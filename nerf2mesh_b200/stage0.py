@@ -1,0 +1,312 @@
+"""Fused stage-0 train path: host side (allocation, CUDA-graph capture, import/export of
+reference-format parameters).  All arithmetic runs in libn2m_b200.so (include/n2m_b200_fused.h).
+
+`Stage0Trainer` owns the model state in the B200-native layout (interleaved hash tables, packed
+tensor-core weights, flat gradient / Adam buffers) and exposes
+
+    loss = trainer.step(rays_o, rays_d, gt, bg_color)        # one full optimizer step
+
+which is the fused equivalent of one iteration of the reference's Trainer.train_one_epoch
+(nerf/utils.py:1152-1182: zero_grad, train_step -> NeRFRenderer.render, scaler.scale(loss).backward(),
+post_train_step TV gradient, scaler.step(optimizer), scaler.update(), lr_scheduler.step()).
+`load_reference_state` / `export_reference_state` convert to and from the reference checkpoint's
+parameter names (encoder.embeddings, sigma_net.net.0.weight, ...).
+"""
+import ctypes
+import math
+from ctypes import c_float, c_uint32
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import F, I, P, U, call, ptr, stream
+from .gridencoder.grid import level_offsets
+
+
+class S0Params(ctypes.Structure):
+    _fields_ = [(n, c_float) for n in ("bound", "grid_bound", "inv_2gb", "dt_gamma", "min_near", "T_thresh", "S",
+                                       "lambda_mask", "lambda_specular", "lambda_tv")] + \
+               [(n, c_uint32) for n in ("contract", "max_steps", "cascades", "grid_size", "num_levels", "base_res",
+                                        "shading_full", "gt_has_alpha")]
+
+
+PP = ctypes.POINTER(S0Params)
+
+_lib.register({
+    "n2m_s0_init": [],
+    "n2m_s0_pack_weights": [P, P, P],
+    "n2m_s0_pack_tables": [P, P, U, P, P, P],
+    "n2m_s0_unpack_tables": [P, P, U, P, P, P],
+    "n2m_s0_unpack_grads": [P, U, P, P, P, P],
+    "n2m_s0_march": [PP, P, P, P, P, P, P, U, P, P, P, P, U, P],
+    "n2m_s0_encode_fwd": [PP, P, P, U, P, P, P, P, P, P],
+    "n2m_s0_mlp_fwd": [PP, P, P, U, P, P, P, P],
+    "n2m_s0_composite_loss": [PP, P, P, P, P, U, U, P, P, P, P, P, P, P, P, P],
+    "n2m_s0_mlp_bwd": [PP, P, P, P, U, P, P, P, P, P],
+    "n2m_s0_encode_bwd": [PP, P, P, U, P, P, P, P, P, P, P, P],
+    "n2m_s0_adam": [P, P, P, P, P, U, P, P, P, P, P, P, F, P],
+})
+_lib.lib.n2m_s0_wpack_bytes.restype = c_uint32
+_lib.lib.n2m_s0_mlp_param_count.restype = c_uint32
+
+# flat MLP parameter vector: (reference parameter name, shape)
+MLP_LAYOUT = [
+    ("sigma_net.net.0.weight", (32, 19)), ("sigma_net.net.1.weight", (1, 32)),
+    ("color_net.net.0.weight", (64, 35)), ("color_net.net.1.weight", (64, 64)), ("color_net.net.2.weight", (6, 64)),
+    ("specular_net.net.0.weight", (32, 6)), ("specular_net.net.1.weight", (3, 32)),
+]
+
+
+class Stage0Config:
+    """The operator arguments the reference passes down from `opt` (SURVEY.md section 5 defaults)."""
+
+    def __init__(self, bound=1.0, contract=False, dt_gamma=0.0, max_steps=1024, grid_size=128, min_near=0.05,
+                 T_thresh=1e-4, num_levels=16, base_resolution=16, log2_hashmap_size=19, lambda_mask=0.1,
+                 lambda_specular=1e-5, lambda_tv=1e-8, lr=1e-2, eps=1e-15, max_samples=None, num_rays=4096,
+                 loss_scale=65536.0):
+        self.real_bound = float(bound)
+        self.contract = bool(contract)
+        self.bound = 2.0 if contract else float(bound)          # renderer.py:74-80
+        self.cascade = 1 + math.ceil(math.log2(self.bound))     # renderer.py:82
+        self.dt_gamma, self.max_steps, self.grid_size, self.min_near = float(dt_gamma), int(max_steps), int(grid_size), float(min_near)
+        self.T_thresh = float(T_thresh)
+        self.num_levels, self.base_resolution, self.log2_hashmap_size = int(num_levels), int(base_resolution), int(log2_hashmap_size)
+        desired = 2048 * self.bound                             # network.py:66,71
+        self.per_level_scale = float(np.exp2(np.log2(desired / base_resolution) / (num_levels - 1)))
+        self.lambda_mask, self.lambda_specular, self.lambda_tv = float(lambda_mask), float(lambda_specular), float(lambda_tv)
+        self.lr, self.eps = float(lr), float(eps)
+        self.num_rays = int(num_rays)
+        # sample capacity of the per-step buffers; rays whose samples do not fit are dropped for the
+        # step (like the reference's `offset + num_steps > M` guard, raymarching.cu:521)
+        self.max_samples = int(max_samples) if max_samples else self.num_rays * 128
+        self.max_samples = (self.max_samples + 127) // 128 * 128
+        self.loss_scale = float(loss_scale)
+
+
+class Stage0Trainer:
+    def __init__(self, cfg: Stage0Config, device="cuda", seed=0):
+        self.cfg = cfg
+        self.device = torch.device(device)
+        dev = self.device
+        call("n2m_s0_init")
+        c = cfg
+        offs = level_offsets(3, c.num_levels, c.per_level_scale, c.base_resolution, c.log2_hashmap_size, False)
+        self.offsets = torch.from_numpy(offs).to(dev)
+        self.rows = int(offs[-1])
+        R = self.rows
+        self.n_mlp = int(_lib.lib.n2m_s0_mlp_param_count())
+        # ---- model state (B200 layout) ----
+        self.table = torch.zeros(R, 2, dtype=torch.float32, device=dev)          # 8-byte entries {f32, half2}
+        self.color_master = torch.zeros(R, 2, dtype=torch.float32, device=dev)
+        self.gtable = torch.zeros(R, 4, dtype=torch.float32, device=dev)
+        self.m_table = torch.zeros(R * 3, dtype=torch.float32, device=dev)
+        self.v_table = torch.zeros(R * 3, dtype=torch.float32, device=dev)
+        self.mlp = torch.zeros(self.n_mlp, dtype=torch.float32, device=dev)
+        self.g_mlp = torch.zeros_like(self.mlp); self.m_mlp = torch.zeros_like(self.mlp); self.v_mlp = torch.zeros_like(self.mlp)
+        self.wpack = torch.zeros(int(_lib.lib.n2m_s0_wpack_bytes()), dtype=torch.uint8, device=dev)
+        self.opt_state = torch.zeros(8, dtype=torch.float32, device=dev)
+        self.opt_state[0] = c.loss_scale
+        self.opt_state[4] = c.lr
+        # ---- scene state ----
+        self.density_grid = torch.zeros(c.cascade, c.grid_size ** 3, device=dev)
+        self.density_bitfield = torch.zeros(c.cascade * c.grid_size ** 3 // 8, dtype=torch.uint8, device=dev)
+        b = c.real_bound
+        self.aabb = torch.tensor([-b, -b, -b, b, b, b], dtype=torch.float32, device=dev)
+        # ---- per-step buffers ----
+        N, Mc = c.num_rays, c.max_samples
+        self.N, self.Mcap = N, Mc
+        self.rays_o = torch.zeros(N, 3, device=dev); self.rays_d = torch.zeros(N, 3, device=dev)
+        self.gt = torch.zeros(N, 4, device=dev); self.bg = torch.zeros(N, 3, device=dev)
+        self.noises = torch.zeros(N, device=dev)
+        self.rays = torch.zeros(N, 2, dtype=torch.int32, device=dev)
+        self.counters = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.tbuf = torch.empty(N * c.max_steps * 2, device=dev)
+        self.recs = torch.zeros(Mc, 4, device=dev)
+        self.enc_tiles = torch.zeros(Mc * 64, dtype=torch.float16, device=dev)
+        self.denc_tiles = torch.zeros(Mc * 64, dtype=torch.float16, device=dev)
+        self.out = torch.zeros(Mc, 4, device=dev)
+        self.dout = torch.zeros(Mc, 4, device=dev)
+        self.image = torch.zeros(N, 3, device=dev); self.weights_sum = torch.zeros(N, device=dev); self.depth = torch.zeros(N, device=dev)
+        self.loss_acc = torch.zeros(4, device=dev)          # [0] rgb(+mask) loss, [1] sum |spec|^2
+        self.params = S0Params()
+        self._fill_params(shading_full=True, gt_has_alpha=True)
+        self.global_step = 0
+        self._graph = None
+        self._graph_key = None
+        self.reset_parameters(seed)
+
+    # -------------------------------------------------------------------------------------------
+    def _fill_params(self, shading_full, gt_has_alpha):
+        c, p = self.cfg, self.params
+        p.bound, p.grid_bound = c.real_bound, c.bound
+        p.inv_2gb = float(np.float32(1.0) / np.float32(2.0 * c.bound))
+        p.dt_gamma, p.min_near, p.T_thresh = c.dt_gamma, c.min_near, c.T_thresh
+        p.S = float(np.float32(np.log2(c.per_level_scale)))
+        p.lambda_mask, p.lambda_specular, p.lambda_tv = c.lambda_mask, c.lambda_specular, c.lambda_tv
+        p.contract, p.max_steps, p.cascades, p.grid_size = int(c.contract), c.max_steps, c.cascade, c.grid_size
+        p.num_levels, p.base_res = c.num_levels, c.base_resolution
+        p.shading_full, p.gt_has_alpha = int(shading_full), int(gt_has_alpha)
+
+    def reset_parameters(self, seed=0):
+        """Reference initialisation: embeddings U(-1e-4, 1e-4) (grid.py:144-146), nn.Linear default
+        (kaiming_uniform(a=sqrt(5)) == U(-1/sqrt(fan_in), 1/sqrt(fan_in)))."""
+        g = torch.Generator().manual_seed(seed)
+        state = {"encoder.embeddings": torch.rand(self.rows, 1, generator=g) * 2e-4 - 1e-4,
+                 "encoder_color.embeddings": torch.rand(self.rows, 2, generator=g) * 2e-4 - 1e-4}
+        for name, (o, i) in MLP_LAYOUT:
+            k = 1.0 / math.sqrt(i)
+            state[name] = (torch.rand(o, i, generator=g) * 2 - 1) * k
+        self.load_reference_state(state)
+
+    def load_reference_state(self, state):
+        dev = self.device
+        ed = state["encoder.embeddings"].to(dev, torch.float32).contiguous()
+        ec = state["encoder_color.embeddings"].to(dev, torch.float32).contiguous()
+        assert ed.shape == (self.rows, 1) and ec.shape == (self.rows, 2)
+        call("n2m_s0_pack_tables", ptr(ed), ptr(ec), self.rows, ptr(self.table), ptr(self.color_master), stream())
+        flat = torch.cat([state[n].to(dev, torch.float32).reshape(-1) for n, _ in MLP_LAYOUT])
+        assert flat.numel() == self.n_mlp
+        self.mlp.copy_(flat)
+        call("n2m_s0_pack_weights", ptr(self.mlp), ptr(self.wpack), stream())
+        if "density_bitfield" in state:
+            self.density_bitfield.copy_(state["density_bitfield"].to(dev))
+        if "density_grid" in state:
+            self.density_grid.copy_(state["density_grid"].to(dev))
+        torch.cuda.synchronize()
+
+    def export_reference_state(self):
+        ed = torch.empty(self.rows, 1, device=self.device); ec = torch.empty(self.rows, 2, device=self.device)
+        call("n2m_s0_unpack_tables", ptr(self.table), ptr(self.color_master), self.rows, ptr(ed), ptr(ec), stream())
+        state = {"encoder.embeddings": ed, "encoder_color.embeddings": ec,
+                 "density_grid": self.density_grid.clone(), "density_bitfield": self.density_bitfield.clone()}
+        o = 0
+        for name, shp in MLP_LAYOUT:
+            n = shp[0] * shp[1]
+            state[name] = self.mlp[o:o + n].view(shp).clone(); o += n
+        return state
+
+    def export_reference_grads(self):
+        """Current (un-scaled) gradients in reference layout -- for parity tests; call before the optimizer."""
+        gd = torch.empty(self.rows, 1, device=self.device); gc = torch.empty(self.rows, 2, device=self.device)
+        call("n2m_s0_unpack_grads", ptr(self.gtable), self.rows, ptr(self.opt_state), ptr(gd), ptr(gc), stream())
+        grads = {"encoder.embeddings": gd, "encoder_color.embeddings": gc}
+        g = self.g_mlp / self.opt_state[0]
+        o = 0
+        for name, shp in MLP_LAYOUT:
+            n = shp[0] * shp[1]
+            grads[name] = g[o:o + n].view(shp).clone(); o += n
+        return grads
+
+    def set_occupancy(self, density_bitfield, density_grid=None):
+        self.density_bitfield.copy_(density_bitfield.to(self.device))
+        if density_grid is not None:
+            self.density_grid.copy_(density_grid.to(self.device))
+
+    # -------------------------------------------------------------------------------------------
+    # the stages (all asynchronous on the current stream)
+    # -------------------------------------------------------------------------------------------
+    def _pp(self):
+        return ctypes.byref(self.params)
+
+    def march(self):
+        call("n2m_s0_march", self._pp(), ptr(self.rays_o), ptr(self.rays_d), ptr(self.aabb), None, ptr(self.density_bitfield),
+             ptr(self.noises), self.N, ptr(self.rays), ptr(self.counters), ptr(self.tbuf), ptr(self.recs), self.Mcap, stream())
+
+    def encode_fwd(self):
+        call("n2m_s0_encode_fwd", self._pp(), ptr(self.recs), ptr(self.counters), self.Mcap, ptr(self.rays_o), ptr(self.rays_d),
+             ptr(self.table), ptr(self.offsets), ptr(self.enc_tiles), stream())
+
+    def mlp_fwd(self):
+        call("n2m_s0_mlp_fwd", self._pp(), ptr(self.enc_tiles), ptr(self.counters), self.Mcap, ptr(self.wpack), ptr(self.out),
+             self.loss_acc.data_ptr() + 4, stream())
+
+    def composite_loss(self):
+        call("n2m_s0_composite_loss", self._pp(), ptr(self.out), ptr(self.recs), ptr(self.rays), ptr(self.counters), self.N, self.Mcap,
+             ptr(self.gt), ptr(self.bg), ptr(self.opt_state), ptr(self.dout), ptr(self.image), ptr(self.weights_sum), ptr(self.depth),
+             ptr(self.loss_acc), stream())
+
+    def mlp_bwd(self):
+        call("n2m_s0_mlp_bwd", self._pp(), ptr(self.enc_tiles), ptr(self.dout), ptr(self.counters), self.Mcap, ptr(self.wpack),
+             ptr(self.denc_tiles), ptr(self.g_mlp), ptr(self.opt_state), stream())
+
+    def encode_bwd(self):
+        call("n2m_s0_encode_bwd", self._pp(), ptr(self.recs), ptr(self.counters), self.Mcap, ptr(self.rays_o), ptr(self.rays_d),
+             ptr(self.denc_tiles), ptr(self.table), ptr(self.offsets), ptr(self.gtable), ptr(self.opt_state), stream())
+
+    def adam(self):
+        call("n2m_s0_adam", ptr(self.table), ptr(self.color_master), ptr(self.gtable), ptr(self.m_table), ptr(self.v_table), self.rows,
+             ptr(self.mlp), ptr(self.g_mlp), ptr(self.m_mlp), ptr(self.v_mlp), ptr(self.wpack), ptr(self.opt_state), self.cfg.eps, stream())
+
+    def forward_backward(self):
+        """march -> encode -> MLP -> composite+loss -> MLP backward -> scatter(+TV); gradients stay in
+        gtable / g_mlp (loss-scaled)."""
+        self.loss_acc.zero_()
+        self.march()
+        self.encode_fwd()
+        self.mlp_fwd()
+        self.composite_loss()
+        self.mlp_bwd()
+        self.encode_bwd()
+
+    def _step_body(self):
+        self.forward_backward()
+        self.adam()
+
+    # -------------------------------------------------------------------------------------------
+    def step(self, rays_o=None, rays_d=None, gt=None, bg_color=None, noises=None, shading="full", lr=None, use_graph=True,
+             grad_sync=None):
+        """One optimizer step.  With tensors given, they are copied into the step buffers first
+        (pinned host tensors -> async H2D on the current stream).  Returns nothing; read
+        `loss_acc` / `counters` (device) afterwards -- no host sync happens here."""
+        has_alpha = bool(self.params.gt_has_alpha)
+        if rays_o is not None:
+            if gt.shape[-1] == 3:
+                self.gt.view(-1)[: self.N * 3].view(self.N, 3).copy_(gt, non_blocking=True)
+                has_alpha = False
+            else:
+                self.gt.copy_(gt, non_blocking=True)
+                has_alpha = True
+            self.rays_o.copy_(rays_o, non_blocking=True); self.rays_d.copy_(rays_d, non_blocking=True)
+            self.bg.copy_(bg_color, non_blocking=True)
+            if noises is not None:
+                self.noises.copy_(noises, non_blocking=True)
+        if lr is not None:
+            self.opt_state[4:5].fill_(float(lr))
+        key = (shading == "full", has_alpha)
+        if key != (bool(self.params.shading_full), bool(self.params.gt_has_alpha)):
+            self._fill_params(*key)
+            self._graph = None
+        if grad_sync is None:
+            if not use_graph:
+                self._step_body()
+            else:
+                if self._graph is None:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._step_body()
+                    self._graph = g
+                self._graph.replay()
+        else:
+            # data parallel: [forward+backward] -> gradient all-reduce (NCCL) -> [optimizer]
+            if not use_graph:
+                self.forward_backward(); grad_sync(); self.adam()
+            else:
+                if self._graph is None:
+                    g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g1):
+                        self.forward_backward()
+                    with torch.cuda.graph(g2):
+                        self.adam()
+                    self._graph = (g1, g2)
+                self._graph[0].replay(); grad_sync(); self._graph[1].replay()
+        self.global_step += 1
+
+    def read_loss(self):
+        """(host sync) loss of the last step as the reference reports it: rgb/mask part + specular regulariser."""
+        acc = self.loss_acc.tolist()
+        M = max(int(self.counters[1].item()), 1)
+        loss = acc[0]
+        if self.params.shading_full and self.cfg.lambda_specular > 0:
+            loss += self.cfg.lambda_specular * acc[1] / M
+        return loss
