@@ -65,6 +65,9 @@ typedef struct {
 /* one-time per-process setup (kernel attributes); call before the first fused launch / graph capture */
 int n2m_s0_init(void);
 
+/* test hook: 1 = sequential one-thread-per-ray marcher, 0 = warp-per-ray marcher (default); same results */
+int n2m_s0_set_serial_march(int on);
+
 /* sizes of the packed weight blob (bytes) and of the flat fp32 MLP parameter / gradient vector (floats) */
 uint32_t n2m_s0_wpack_bytes(void);
 uint32_t n2m_s0_mlp_param_count(void);      /* 7648 = 608+32 + 2240+4096+384 + 192+96 */

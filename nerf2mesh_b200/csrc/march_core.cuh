@@ -103,14 +103,21 @@ __device__ __forceinline__ Probe probe_at(const MarchCfg& c, float t, float ox, 
     return p;
 }
 
-// Empty cell: advance t past the voxel's exit face in dt-sized hops (raymarching.cu:452-464).
-__device__ __forceinline__ float hop_to_exit(const MarchCfg& c, const Probe& p, float t,
-                                             float dx, float dy, float dz,
-                                             float rdx, float rdy, float rdz) {
+// Distance at which the ray leaves the current (empty) voxel (raymarching.cu:452-458).
+__device__ __forceinline__ float exit_time(const MarchCfg& c, const Probe& p, float t,
+                                           float dx, float dy, float dz,
+                                           float rdx, float rdy, float rdz) {
     const float tx = (((p.nx + 0.5f + 0.5f * copysignf(1.0f, dx)) * c.rH * 2 - 1) * p.mip_bound - p.cx) * rdx;
     const float ty = (((p.ny + 0.5f + 0.5f * copysignf(1.0f, dy)) * c.rH * 2 - 1) * p.mip_bound - p.cy) * rdy;
     const float tz = (((p.nz + 0.5f + 0.5f * copysignf(1.0f, dz)) * c.rH * 2 - 1) * p.mip_bound - p.cz) * rdz;
-    const float tt = t + fmaxf(0.0f, fminf(tx, fminf(ty, tz)));
+    return t + fmaxf(0.0f, fminf(tx, fminf(ty, tz)));
+}
+
+// Empty cell: advance t past the voxel's exit face in dt-sized hops (raymarching.cu:459-464).
+__device__ __forceinline__ float hop_to_exit(const MarchCfg& c, const Probe& p, float t,
+                                             float dx, float dy, float dz,
+                                             float rdx, float rdy, float rdz) {
+    const float tt = exit_time(c, p, t, dx, dy, dz, rdx, rdy, rdz);
     do {
         const float dt = clampf(t * c.dt_gamma, c.dt_min, c.dt_max);
         t += dt;

@@ -46,36 +46,53 @@ __device__ __forceinline__ float adam_update(float p, float g, float& m, float& 
     return p - lr_over_bc1 * __fdiv_rn(m, denom);
 }
 
-// one thread per table row: {density feature fp32 (master lives in the table), 2 colour features (fp32
-// masters in cmaster, fp16 copy in the table)}.  m/v: [rows] density then [rows][2] colour.
+// Table rows: {density feature fp32 (master lives in the table), 2 colour features (fp32 masters in cmaster,
+// fp16 copy in the table)}.  m/v: [rows] density then [rows][2] colour.  Pure streaming (112 B/row, ~0.7 GB per
+// step): each thread handles kRowsPerThread rows, block-strided so every access stays coalesced, and issues ALL
+// of its loads before the first dependent instruction -- with one row per thread the kernel was latency bound
+// at 1.6 TB/s (profiles/r1_notes.md).
+constexpr int kRowsPerThread = 4;
+
 __global__ void __launch_bounds__(256)
 k_adam_tables(TableEntry* __restrict__ table, float2* __restrict__ cmaster, float4* __restrict__ gtable,
               float* __restrict__ m, float* __restrict__ v, uint32_t rows, const float* __restrict__ st, float eps) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= rows) return;
+    const uint32_t i0 = blockIdx.x * (256 * kRowsPerThread) + threadIdx.x;
     const bool skip = st[3] != 0.f;
-    float4 g = gtable[i];
-    gtable[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (skip) return;
     const float inv = st[7];
-    g.x *= inv; g.y *= inv; g.z *= inv;
     const float lr1 = __fdiv_rn(st[4], st[5]), bc2s = st[6];
-    float md = m[i], vd = v[i];
-    float2 mc = reinterpret_cast<float2*>(m + rows)[i], vc = reinterpret_cast<float2*>(v + rows)[i];
-    // untouched row with empty moments: the update is exactly zero -- skip the writes
-    if (g.x == 0.f && g.y == 0.f && g.z == 0.f && md == 0.f && vd == 0.f && mc.x == 0.f && mc.y == 0.f && vc.x == 0.f && vc.y == 0.f)
-        return;
-    TableEntry e = table[i];
-    float2 pc = cmaster[i];
-    e.d = adam_update(e.d, g.x, md, vd, lr1, bc2s, eps);
-    pc.x = adam_update(pc.x, g.y, mc.x, vc.x, lr1, bc2s, eps);
-    pc.y = adam_update(pc.y, g.z, mc.y, vc.y, lr1, bc2s, eps);
-    e.c = __floats2half2_rn(pc.x, pc.y);
-    table[i] = e;
-    cmaster[i] = pc;
-    m[i] = md; v[i] = vd;
-    reinterpret_cast<float2*>(m + rows)[i] = mc;
-    reinterpret_cast<float2*>(v + rows)[i] = vc;
+    float2* mc_p = reinterpret_cast<float2*>(m + rows);
+    float2* vc_p = reinterpret_cast<float2*>(v + rows);
+    float4 g[kRowsPerThread]; float md[kRowsPerThread], vd[kRowsPerThread];
+    float2 mc[kRowsPerThread], vc[kRowsPerThread], pc[kRowsPerThread];
+    TableEntry e[kRowsPerThread];
+#pragma unroll
+    for (int j = 0; j < kRowsPerThread; ++j) {
+        const uint32_t i = i0 + j * 256;
+        if (i < rows) {
+            g[j] = gtable[i];
+            if (!skip) { md[j] = m[i]; vd[j] = v[i]; mc[j] = mc_p[i]; vc[j] = vc_p[i]; e[j] = table[i]; pc[j] = cmaster[i]; }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < kRowsPerThread; ++j) {
+        const uint32_t i = i0 + j * 256;
+        if (i >= rows) continue;
+        gtable[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (skip) continue;
+        const float gx = g[j].x * inv, gy = g[j].y * inv, gz = g[j].z * inv;
+        // untouched row with empty moments: the update is exactly zero -- skip the writes
+        if (gx == 0.f && gy == 0.f && gz == 0.f && md[j] == 0.f && vd[j] == 0.f && mc[j].x == 0.f && mc[j].y == 0.f &&
+            vc[j].x == 0.f && vc[j].y == 0.f)
+            continue;
+        e[j].d = adam_update(e[j].d, gx, md[j], vd[j], lr1, bc2s, eps);
+        pc[j].x = adam_update(pc[j].x, gy, mc[j].x, vc[j].x, lr1, bc2s, eps);
+        pc[j].y = adam_update(pc[j].y, gz, mc[j].y, vc[j].y, lr1, bc2s, eps);
+        e[j].c = __floats2half2_rn(pc[j].x, pc[j].y);
+        table[i] = e[j];
+        cmaster[i] = pc[j];
+        m[i] = md[j]; v[i] = vd[j];
+        mc_p[i] = mc[j]; vc_p[i] = vc[j];
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -118,7 +135,7 @@ extern "C" int n2m_s0_adam(void* table, void* color_master, void* gtable, float*
     if (int e = check_launch("s0_adam(check)")) return e;
     k_adam_prep<<<1, 32, 0, st>>>(opt_state);
     if (int e = check_launch("s0_adam(prep)")) return e;
-    k_adam_tables<<<div_up(rows, 256u), 256, 0, st>>>(static_cast<TableEntry*>(table), static_cast<float2*>(color_master),
+    k_adam_tables<<<div_up(rows, 256u * kRowsPerThread), 256, 0, st>>>(static_cast<TableEntry*>(table), static_cast<float2*>(color_master),
                                                       static_cast<float4*>(gtable), m_table, v_table, rows, opt_state, eps);
     if (int e = check_launch("s0_adam(tables)")) return e;
     k_adam_mlp<<<div_up(n, 256u), 256, 0, st>>>(mlp_params, g_mlp, m_mlp, v_mlp, n, opt_state, eps);

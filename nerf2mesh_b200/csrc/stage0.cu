@@ -4,6 +4,7 @@
 //   table (de)interleave helpers.  The MLP stages live in mlp_tc.cu, the optimizer in optim.cu.
 #include "march_core.cuh"
 #include "tc05.cuh"
+#include <cstdlib>
 #include "../../include/n2m_b200_fused.h"
 
 namespace n2m {
@@ -44,6 +45,93 @@ k_s0_count(const float* __restrict__ rays_o, const float* __restrict__ rays_d, c
     CountSink sink{tbuf + (size_t)n * p.max_steps};
     const uint32_t cnt = march_one(c, t0, far, p.max_steps, ox, oy, oz, dx, dy, dz, rdx, rdy, rdz, sink);
     rays[2 * n + 1] = (int32_t)cnt;
+}
+
+// Warp-per-ray marcher.  The sequential marcher's t only ever advances by dt(t) = clamp(t * dt_gamma,
+// dt_min, dt_max) -- in the "emit" branch and in every hop of the "skip" branch alike -- so every t it visits
+// belongs to the one-parameter sequence tau_0 = t0, tau_{j+1} = tau_j + dt(tau_j).  The warp generates 32
+// consecutive tau's (serial fp32 adds, identical rounding), probes all 32 positions in parallel (cell,
+// cascade, occupancy bit, voxel-exit time: the expensive part), and then replays the sequential control flow
+// over the precomputed probes with ballots: runs of occupied samples are consumed in one go, an empty probe
+// jumps to the first tau that is not < its exit time.  Same visited set, same (t, dt) per sample, bit for bit.
+__global__ void __launch_bounds__(128)
+k_s0_count_warp(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ aabb,
+                const float* __restrict__ cam_nf, const uint8_t* __restrict__ bits, const float* __restrict__ noises,
+                n2m_s0_params p, uint32_t N, int32_t* __restrict__ rays, float2* __restrict__ tbuf) {
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const MarchCfg c = make_cfg(p.bound, p.contract != 0, p.dt_gamma, p.max_steps, p.cascades, p.grid_size, bits);
+    float near, far;
+    near_far_aabb(rays_o + 3 * n, rays_d + 3 * n, aabb, p.min_near, near, far);
+    if (cam_nf) {
+        near = fmaxf(near, cam_nf[2 * n]);
+        far = fminf(far, cam_nf[2 * n + 1]);
+    }
+    const float ox = rays_o[3 * n], oy = rays_o[3 * n + 1], oz = rays_o[3 * n + 2];
+    const float dx = rays_d[3 * n], dy = rays_d[3 * n + 1], dz = rays_d[3 * n + 2];
+    const float rdx = 1 / dx, rdy = 1 / dy, rdz = 1 / dz;
+    float t_start = near;
+    t_start += clampf(t_start * c.dt_gamma, c.dt_min, c.dt_max) * noises[n];
+    float2* slab = tbuf + (size_t)n * p.max_steps;
+
+    uint32_t step = 0;
+    bool pending = false;          // a hop whose target lies beyond the chunk it started in
+    float pending_tt = 0.f;
+    bool done = !(t_start < far);
+    uint32_t chunks = 0;
+    while (!done && ++chunks < (1u << 20)) {       // the cap only guards against a t that cannot advance
+        // tau for this lane: `lane` serial steps from the chunk start (all lanes run the loop in lock step)
+        float tau = t_start;
+        float t_next = t_start;    // value after 32 steps = next chunk start (lane 31 computes it)
+#pragma unroll 1
+        for (uint32_t i = 0; i < 32; ++i) {
+            const float adv = t_next + clampf(t_next * c.dt_gamma, c.dt_min, c.dt_max);
+            if (i < lane) tau = adv;
+            t_next = adv;
+        }
+        const float dt = clampf(tau * c.dt_gamma, c.dt_min, c.dt_max);
+        const bool in_range = tau < far;
+        bool emit = false;
+        float tt = 0.f;
+        if (in_range) {
+            const Probe pr = probe_at(c, tau, ox, oy, oz, dx, dy, dz);
+            emit = pr.emit;
+            if (!emit) tt = exit_time(c, pr, tau, dx, dy, dz, rdx, rdy, rdz);
+        }
+        const uint32_t range_mask = __ballot_sync(0xffffffffu, in_range);     // a prefix of the warp (tau increases)
+        const uint32_t emit_mask = __ballot_sync(0xffffffffu, emit);
+        uint32_t cur = 0;
+        if (pending) {
+            const uint32_t ge = __ballot_sync(0xffffffffu, !(tau < pending_tt));
+            if (ge == 0) cur = 32; else { cur = __ffs(ge) - 1; pending = false; }
+        }
+        while (cur < 32) {
+            if (!((range_mask >> cur) & 1u) || step >= p.max_steps) { done = true; break; }
+            if ((emit_mask >> cur) & 1u) {
+                // run of consecutive occupied probes starting at `cur`
+                const uint32_t run_bits = ~(emit_mask >> cur);
+                uint32_t run = run_bits ? (uint32_t)(__ffs(run_bits) - 1) : 32u;
+                run = min(run, 32u - cur);
+                run = min(run, p.max_steps - step);
+                if (lane >= cur && lane < cur + run) slab[step + (lane - cur)] = make_float2(tau, dt);
+                step += run;
+                cur += run;
+            } else {
+                const float tt_c = __shfl_sync(0xffffffffu, tt, cur);
+                uint32_t ge = __ballot_sync(0xffffffffu, !(tau < tt_c));
+                ge &= (cur >= 31) ? 0u : (0xffffffffu << (cur + 1));             // at least one dt step is taken
+                if (ge == 0) { pending = true; pending_tt = tt_c; cur = 32; }
+                else cur = __ffs(ge) - 1;
+            }
+        }
+        t_start = __shfl_sync(0xffffffffu, t_next, 31);
+        if (!done && !(t_start < far) ) {
+            // the next chunk starts beyond `far`: nothing left to visit (a pending hop lands past far too)
+            done = true;
+        }
+    }
+    if (lane == 0) rays[2 * n + 1] = (int32_t)step;
 }
 
 // single-block exclusive scan (N is a few thousand rays) -> offsets + counters
@@ -263,7 +351,12 @@ k_s0_encode_fwd(n2m_s0_params p, const float4* __restrict__ recs, const int32_t*
 }
 
 // ------------------------------------------------------------------------------------------------
-// encode backward: scatter the (loss-scaled, fp16) feature gradients + TV gradient
+// encode backward: scatter the (loss-scaled, fp16) feature gradients + TV gradient.
+// L2 atomic throughput bounds this kernel (profiles/r1_notes.md), so at the coarse levels -- where the
+// consecutive samples of a ray (= consecutive lanes) sit in the same lattice cell -- the 8 corner
+// contributions are first summed across each run of same-cell lanes with a segmented warp scan and only the
+// last lane of a run issues the red.global.add.v4.f32; the TV term (identical for every sample of a cell) is
+// evaluated once per run.  Fine levels (every lane its own cell) go straight to the atomics.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kTile)
 k_s0_encode_bwd(n2m_s0_params p, const float4* __restrict__ recs, const int32_t* __restrict__ counters,
@@ -272,18 +365,25 @@ k_s0_encode_bwd(n2m_s0_params p, const float4* __restrict__ recs, const int32_t*
                 const int32_t* __restrict__ offsets, float4* __restrict__ gtable, float* __restrict__ loss_scale) {
     const uint32_t M = (uint32_t)counters[1];
     const uint32_t tile = blockIdx.x, r = threadIdx.x;
+    if (tile * kTile >= M) return;                       // whole block idle
+    const uint32_t lane = r & 31;
     const uint32_t j = tile * kTile + r;
-    if (j >= M) return;
-    const Sample s = sample_of(recs[j], rays_o, rays_d, p);
-    const bool oob = (s.u < 0 || s.u > 1) || (s.v < 0 || s.v > 1) || (s.w < 0 || s.w > 1);
-    if (oob) return;
+    Sample s;
+    bool active = j < M;
+    if (active) {
+        s = sample_of(recs[j], rays_o, rays_d, p);
+        active = !((s.u < 0 || s.u > 1) || (s.v < 0 || s.v > 1) || (s.w < 0 || s.w > 1));
+    } else {
+        s.x = s.y = s.z = s.u = s.v = s.w = 0.5f; s.dx = s.dy = s.dz = 0.f;
+    }
 
     // this row's gradients: cols 3..18 density, 19..50 colour  (chunks 0..6)
     const uint8_t* img = denc_tiles + (size_t)tile * kTileBytes + r * 16;
     float g[56];
 #pragma unroll
     for (uint32_t ch = 0; ch < 7; ++ch) {
-        const uint4 q = *reinterpret_cast<const uint4*>(img + ch * kChunkBytes);
+        uint4 q = make_uint4(0, 0, 0, 0);
+        if (active) q = *reinterpret_cast<const uint4*>(img + ch * kChunkBytes);
         const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -300,144 +400,210 @@ k_s0_encode_bwd(n2m_s0_params p, const float4* __restrict__ recs, const int32_t*
     // TV weight: lambda inside the unit cube, 10 lambda outside when bound > 1 (utils.py:815-821)
     const float mag = fmaxf(fabsf(s.x), fmaxf(fabsf(s.y), fabsf(s.z)));
     const float lam = (p.grid_bound > 1 && mag > 1) ? p.lambda_tv * 10 : p.lambda_tv;
-    const float tvw = lam / 6 * loss_scale[0];       // w = weight / (2 * D), kept in the scaled domain
+    const float tvw_lane = active ? lam / 6 * loss_scale[0] : 0.f;     // w = weight / (2 * D), kept in the scaled domain
     const bool do_tv = p.lambda_tv > 0;
 
-#pragma unroll
+#pragma unroll 1
     for (uint32_t l = 0; l < kLevels; ++l) {
         const LevelGeom lg = level_geom(offsets, l, p.S, p.base_res);
         Corners c; uint32_t base[3]; bool hashed;
         corners_of(lg, s.u, s.v, s.w, c, base, hashed);
         float4* gt = gtable + lg.row0;
-        const float gd = g[kColDens + l], g0 = g[kColColor + 2 * l], g1 = g[kColColor + 2 * l + 1];
+        const float gd = active ? g[kColDens + l] : 0.f;
+        const float g0 = active ? g[kColColor + 2 * l] : 0.f, g1 = active ? g[kColColor + 2 * l + 1] : 0.f;
+        float vd[8], v0[8], v1[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-            atomicAdd(gt + c.row[k], make_float4(c.w[k] * gd, c.w[k] * g0, c.w[k] * g1, 0.f));
+        for (int k = 0; k < 8; ++k) { vd[k] = c.w[k] * gd; v0[k] = c.w[k] * g0; v1[k] = c.w[k] * g1; }
+        float tvw = tvw_lane;
 
-        if (do_tv) {        // gridencoder.cu:506-609 on the density feature
-            const TableEntry* tab = table + lg.row0;
-            const uint32_t s1 = lg.res + 1;
-            uint32_t stride = 1, mult[3] = {0, 0, 0};
+        // runs of consecutive lanes in the same cell
+        const uint32_t key = active ? (base[0] | (base[1] << 10) | (base[2] << 20)) : 0xffffffffu;
+        const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+        const uint32_t heads = __ballot_sync(0xffffffffu, lane == 0 || key != prev);
+        const bool merge = lg.res < 1023u && __popc(heads) <= 20;
+        bool issue = active;
+        if (merge) {
+            const uint32_t run_start = 31u - __clz(heads & (0xffffffffu >> (31u - lane)));
 #pragma unroll
-            for (int d = 0; d < 3; ++d) if (stride <= lg.rows) { mult[d] = stride; stride *= s1; }
-            const uint32_t prime[3] = {1u, 2654435761u, 805459861u};
-            auto row_of = [&](uint32_t x, uint32_t y, uint32_t z) -> uint32_t {
-                const uint32_t raw = hashed ? ((x * prime[0]) ^ (y * prime[1]) ^ (z * prime[2]))
-                                            : (x * mult[0] + y * mult[1] + z * mult[2]);
-                return raw % lg.rows;
-            };
-            const float centre = __ldg(&tab[c.row[0]].d);
-            float sum = 0.f, sq = 0.f;
+            for (int o = 1; o < 32; o <<= 1) {
+                const bool take = lane >= run_start + (uint32_t)o;
 #pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                uint32_t q[3] = {base[0], base[1], base[2]};
-                const uint32_t cur = base[d];
-                if (cur < lg.res) {
-                    q[d] = cur + 1;
-                    const float dv = centre - __ldg(&tab[row_of(q[0], q[1], q[2])].d);
-                    sum += dv; sq += dv * dv;
+                for (int k = 0; k < 8; ++k) {
+                    const float a = __shfl_up_sync(0xffffffffu, vd[k], o), b = __shfl_up_sync(0xffffffffu, v0[k], o),
+                                cc = __shfl_up_sync(0xffffffffu, v1[k], o);
+                    if (take) { vd[k] += a; v0[k] += b; v1[k] += cc; }
                 }
-                if (cur > 0) {
-                    q[d] = cur - 1;
-                    const float dv = centre - __ldg(&tab[row_of(q[0], q[1], q[2])].d);
-                    sum += dv; sq += dv * dv;
-                }
+                const float t = __shfl_up_sync(0xffffffffu, tvw, o);
+                if (take) tvw += t;
             }
-            atomicAdd(&gt[c.row[0]].x, tvw * sum * rsqrtf(sq + 1e-9f));
+            const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
+            issue = active && tail;
+        }
+        if (issue) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) atomicAdd(gt + c.row[k], make_float4(vd[k], v0[k], v1[k], 0.f));
+            if (do_tv) {        // gridencoder.cu:506-609 on the density feature
+                const TableEntry* tab = table + lg.row0;
+                const uint32_t s1 = lg.res + 1;
+                uint32_t stride = 1, mult[3] = {0, 0, 0};
+#pragma unroll
+                for (int d = 0; d < 3; ++d) if (stride <= lg.rows) { mult[d] = stride; stride *= s1; }
+                const uint32_t prime[3] = {1u, 2654435761u, 805459861u};
+                auto row_of = [&](uint32_t x, uint32_t y, uint32_t z) -> uint32_t {
+                    const uint32_t raw = hashed ? ((x * prime[0]) ^ (y * prime[1]) ^ (z * prime[2]))
+                                                : (x * mult[0] + y * mult[1] + z * mult[2]);
+                    return raw % lg.rows;
+                };
+                const float centre = __ldg(&tab[c.row[0]].d);
+                float sum = 0.f, sq = 0.f;
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    uint32_t q[3] = {base[0], base[1], base[2]};
+                    const uint32_t cur = base[d];
+                    if (cur < lg.res) {
+                        q[d] = cur + 1;
+                        const float dv = centre - __ldg(&tab[row_of(q[0], q[1], q[2])].d);
+                        sum += dv; sq += dv * dv;
+                    }
+                    if (cur > 0) {
+                        q[d] = cur - 1;
+                        const float dv = centre - __ldg(&tab[row_of(q[0], q[1], q[2])].d);
+                        sum += dv; sq += dv * dv;
+                    }
+                }
+                atomicAdd(&gt[c.row[0]].x, tvw * sum * rsqrtf(sq + 1e-9f));
+            }
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// composite forward + loss + composite backward: one thread per ray
+// composite forward + loss + composite backward: one WARP per ray.
+// The reference walks each ray sequentially in one thread (raymarching.cu:541-568, 651-693); here the
+// transmittance is a warp prefix product, the accumulations are warp scans / reductions and early
+// termination is a ballot, so a 70-sample ray costs ~3 chunk iterations instead of 140 dependent steps.
+// Same formulas; the summation order differs (1e-6-level), which is why the bit-exact drop-in operator
+// (raymarching.cu in this repo) keeps the sequential order and this fused stage is tolerance-checked.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_incl_scan_add(float v, uint32_t lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const float u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= (uint32_t)o) v += u; }
+    return v;
+}
+__device__ __forceinline__ float warp_incl_scan_mul(float v, uint32_t lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const float u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= (uint32_t)o) v *= u; }
+    return v;
+}
+
 __global__ void __launch_bounds__(128)
 k_s0_composite_loss(n2m_s0_params p, const float4* __restrict__ out, const float4* __restrict__ recs,
                     const int32_t* __restrict__ rays, const int32_t* __restrict__ counters, uint32_t N,
                     const float* __restrict__ gt, const float* __restrict__ bg, const float* __restrict__ loss_scale,
                     float4* __restrict__ dout, float* __restrict__ image, float* __restrict__ weights_sum,
                     float* __restrict__ depth, float* __restrict__ loss_out) {
-    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
-    float my_loss = 0.f;
-    if (n < N) {
-        const uint32_t M = (uint32_t)counters[1];
-        const uint32_t off = rays[2 * n], cnt = rays[2 * n + 1];
-        const bool live = cnt != 0 && off + cnt <= M;
-        float T = 1.0f, r = 0, g = 0, b = 0, ws = 0, d = 0;
-        if (live) {
-            for (uint32_t k = 0; k < cnt; ++k) {
-                const float4 o = out[off + k];
-                const float4 rc = recs[off + k];
-                const float alpha = 1.0f - __expf(-o.x * rc.y);
-                const float w = alpha * T;
-                r += w * o.y; g += w * o.z; b += w * o.w;
-                ws += w;
-                d += w * rc.z;
-                T *= 1.0f - alpha;
-                if (T < p.T_thresh) break;
-            }
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const uint32_t M = (uint32_t)counters[1];
+    const uint32_t off = rays[2 * n], cnt = rays[2 * n + 1];
+    const bool live = cnt != 0 && off + cnt <= M;
+
+    // ---- forward ----
+    float T_in = 1.0f, r = 0, g = 0, b = 0, ws = 0, d = 0;
+    uint32_t n_used = 0;                 // samples up to and including the one that crossed T_thresh
+    if (live) {
+        for (uint32_t base = 0; base < cnt; base += 32) {
+            const uint32_t k = base + lane;
+            const bool valid = k < cnt;
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f); float4 rc = o;
+            if (valid) { o = out[off + k]; rc = recs[off + k]; }
+            const float alpha = valid ? 1.0f - __expf(-o.x * rc.y) : 0.f;
+            const float Tpost = T_in * warp_incl_scan_mul(1.0f - alpha, lane);      // transmittance after sample k
+            float Tpre = __shfl_up_sync(0xffffffffu, Tpost, 1);
+            if (lane == 0) Tpre = T_in;
+            const uint32_t stop = __ballot_sync(0xffffffffu, valid && Tpost < p.T_thresh);
+            const uint32_t last = stop ? (uint32_t)(__ffs(stop) - 1) : 31u;           // last contributing lane
+            const bool use = valid && lane <= last;
+            const float w = use ? alpha * Tpre : 0.f;
+            r += warp_sum(w * o.y); g += warp_sum(w * o.z); b += warp_sum(w * o.w);
+            ws += warp_sum(w); d += warp_sum(w * rc.z);
+            n_used = base + min(last + 1u, cnt - base);
+            if (stop) break;
+            T_in = __shfl_sync(0xffffffffu, Tpost, 31);
         }
-        // background mix (renderer.py:804) and loss (utils.py:660-683), per ray
-        const float b0 = bg[3 * n], b1 = bg[3 * n + 1], b2 = bg[3 * n + 2];
-        const float om = 1 - ws;
-        const float pr = r + om * b0, pg = g + om * b1, pb = b + om * b2;
-        float t0, t1, t2, mask = 0.f;
-        if (p.gt_has_alpha) {
-            mask = gt[4 * n + 3];
-            t0 = gt[4 * n] * mask + b0 * (1 - mask);
-            t1 = gt[4 * n + 1] * mask + b1 * (1 - mask);
-            t2 = gt[4 * n + 2] * mask + b2 * (1 - mask);
-        } else {
-            t0 = gt[3 * n]; t1 = gt[3 * n + 1]; t2 = gt[3 * n + 2];
-        }
-        const float e0 = pr - t0, e1 = pg - t1, e2 = pb - t2;
-        my_loss = (e0 * e0 + e1 * e1 + e2 * e2) * (1.0f / 3.0f);
-        const float invN = 1.0f / (float)N;
-        const float sc = loss_scale[0] * invN;
-        // d loss / d pred (mean over 3 channels, mean over N rays), loss-scaled
-        const float gi0 = sc * (2.0f / 3.0f) * e0, gi1 = sc * (2.0f / 3.0f) * e1, gi2 = sc * (2.0f / 3.0f) * e2;
-        // pred = image + (1 - ws) * bg  =>  d/d ws picks up -bg . g_pred (+ the mask term)
-        float gws = -(gi0 * b0 + gi1 * b1 + gi2 * b2);
-        if (p.gt_has_alpha && p.lambda_mask > 0) {
-            const float em = ws - mask;
-            my_loss += p.lambda_mask * em * em;
-            gws += sc * p.lambda_mask * 2.0f * em;
-        }
-        my_loss *= invN;
+    }
+    // ---- background mix (renderer.py:804) and loss (utils.py:660-683): identical on all lanes ----
+    const float b0 = bg[3 * n], b1 = bg[3 * n + 1], b2 = bg[3 * n + 2];
+    const float om = 1 - ws;
+    const float pr = r + om * b0, pg = g + om * b1, pb = b + om * b2;
+    float t0, t1, t2, mask = 0.f;
+    if (p.gt_has_alpha) {
+        mask = gt[4 * n + 3];
+        t0 = gt[4 * n] * mask + b0 * (1 - mask);
+        t1 = gt[4 * n + 1] * mask + b1 * (1 - mask);
+        t2 = gt[4 * n + 2] * mask + b2 * (1 - mask);
+    } else {
+        t0 = gt[3 * n]; t1 = gt[3 * n + 1]; t2 = gt[3 * n + 2];
+    }
+    const float e0 = pr - t0, e1 = pg - t1, e2 = pb - t2;
+    float my_loss = (e0 * e0 + e1 * e1 + e2 * e2) * (1.0f / 3.0f);
+    const float invN = 1.0f / (float)N;
+    const float sc = loss_scale[0] * invN;
+    const float gi0 = sc * (2.0f / 3.0f) * e0, gi1 = sc * (2.0f / 3.0f) * e1, gi2 = sc * (2.0f / 3.0f) * e2;
+    float gws = -(gi0 * b0 + gi1 * b1 + gi2 * b2);          // pred = image + (1 - ws) * bg
+    if (p.gt_has_alpha && p.lambda_mask > 0) {
+        const float em = ws - mask;
+        my_loss += p.lambda_mask * em * em;
+        gws += sc * p.lambda_mask * 2.0f * em;
+    }
+    if (lane == 0) {
         image[3 * n] = pr; image[3 * n + 1] = pg; image[3 * n + 2] = pb;
         weights_sum[n] = ws;
         depth[n] = d;
-
-        // composite backward (raymarching.cu:605-694), grad_weights = grad_depth = 0
-        if (live) {
-            const float r_fin = r, g_fin = g, b_fin = b, ws_fin = ws;
-            T = 1.0f; r = g = b = ws = 0;
-            uint32_t k = 0;
-            for (; k < cnt; ++k) {
-                const float4 o = out[off + k];
-                const float dtj = recs[off + k].y;
-                const float alpha = 1.0f - __expf(-o.x * dtj);
-                const float w = alpha * T;
-                r += w * o.y; g += w * o.z; b += w * o.w;
-                ws += w;
-                T *= 1.0f - alpha;
-                const float gs = dtj * (gi0 * (T * o.y - (r_fin - r)) + gi1 * (T * o.z - (g_fin - g)) +
-                                        gi2 * (T * o.w - (b_fin - b)) + gws * (T - (ws_fin - ws)));
-                dout[off + k] = make_float4(gs, gi0 * w, gi1 * w, gi2 * w);
-                if (T < p.T_thresh) { ++k; break; }
-            }
-            for (; k < cnt; ++k) dout[off + k] = make_float4(0.f, 0.f, 0.f, 0.f);   // past the break
-        } else if (cnt != 0) {
-            for (uint32_t k = 0; k < cnt && off + k < M; ++k) dout[off + k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        atomicAdd(loss_out, my_loss * invN);
     }
-    // block-reduce the loss, one atomic per block
-    __shared__ float red[4];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) my_loss += __shfl_xor_sync(0xffffffffu, my_loss, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = my_loss;
-    __syncthreads();
-    if (threadIdx.x == 0) atomicAdd(loss_out, red[0] + red[1] + red[2] + red[3]);
+
+    // ---- backward (raymarching.cu:605-694 with grad_weights = grad_depth = 0) ----
+    if (live) {
+        float Tc = 1.0f, cr = 0, cg = 0, cb = 0, cw = 0;     // carries: transmittance and prefix sums
+        for (uint32_t base = 0; base < cnt; base += 32) {
+            const uint32_t k = base + lane;
+            if (base >= n_used) {                            // past the break: zero gradient
+                if (k < cnt) dout[off + k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                continue;
+            }
+            const bool use = k < n_used;
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f); float dtk = 0.f;
+            if (use) { o = out[off + k]; dtk = recs[off + k].y; }
+            const float alpha = use ? 1.0f - __expf(-o.x * dtk) : 0.f;
+            const float Tpost = Tc * warp_incl_scan_mul(1.0f - alpha, lane);
+            float Tpre = __shfl_up_sync(0xffffffffu, Tpost, 1);
+            if (lane == 0) Tpre = Tc;
+            const float w = alpha * Tpre;
+            const float sr = cr + warp_incl_scan_add(w * o.y, lane), sg = cg + warp_incl_scan_add(w * o.z, lane);
+            const float sb = cb + warp_incl_scan_add(w * o.w, lane), sw = cw + warp_incl_scan_add(w, lane);
+            if (k < cnt) {
+                float4 gq = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (use) {
+                    gq.x = dtk * (gi0 * (Tpost * o.y - (r - sr)) + gi1 * (Tpost * o.z - (g - sg)) +
+                                  gi2 * (Tpost * o.w - (b - sb)) + gws * (Tpost - (ws - sw)));
+                    gq.y = gi0 * w; gq.z = gi1 * w; gq.w = gi2 * w;
+                }
+                dout[off + k] = gq;
+            }
+            Tc = __shfl_sync(0xffffffffu, Tpost, 31);
+            cr = __shfl_sync(0xffffffffu, sr, 31); cg = __shfl_sync(0xffffffffu, sg, 31);
+            cb = __shfl_sync(0xffffffffu, sb, 31); cw = __shfl_sync(0xffffffffu, sw, 31);
+        }
+    } else if (cnt != 0) {
+        for (uint32_t k = lane; k < cnt && off + k < M; k += 32) dout[off + k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -478,7 +644,12 @@ k_s0_unpack_grads(const float4* __restrict__ gtable, uint32_t rows, const float*
 
 using namespace n2m;
 
+static bool g_serial_march = false;
+
 extern "C" {
+
+/* test hook: 1 = one-thread-per-ray sequential marcher (the reference's structure), 0 = warp-per-ray (default) */
+int n2m_s0_set_serial_march(int on) { g_serial_march = on != 0; return 0; }
 
 int n2m_s0_pack_tables(const float* emb_density, const float* emb_color, uint32_t rows, void* table, void* color_master,
                        n2m_stream_t stream) {
@@ -511,8 +682,12 @@ int n2m_s0_march(const n2m_s0_params* p, const float* rays_o, const float* rays_
     if (N == 0) { cudaMemsetAsync(counters, 0, 4 * sizeof(int32_t), st); return 0; }
     N2M_REQUIRE(rays_o && rays_d && aabb && bitfield && noises && tbuf && recs, "s0_march", "null pointer");
     N2M_REQUIRE(p->max_steps > 0 && p->grid_size > 0 && p->cascades > 0, "s0_march", "bad params");
-    k_s0_count<<<div_up(N, 128u), 128, 0, st>>>(rays_o, rays_d, aabb, cam_near_far, bitfield, noises, *p, N, rays,
-                                                 reinterpret_cast<float2*>(tbuf));
+    if (g_serial_march)
+        k_s0_count<<<div_up(N, 128u), 128, 0, st>>>(rays_o, rays_d, aabb, cam_near_far, bitfield, noises, *p, N, rays,
+                                                     reinterpret_cast<float2*>(tbuf));
+    else
+        k_s0_count_warp<<<div_up(N * 32u, 128u), 128, 0, st>>>(rays_o, rays_d, aabb, cam_near_far, bitfield, noises, *p, N, rays,
+                                                                reinterpret_cast<float2*>(tbuf));
     if (int e = check_launch("s0_march(count)")) return e;
     k_s0_scan<<<1, 1024, 0, st>>>(rays, N, Mcap, counters);
     if (int e = check_launch("s0_march(scan)")) return e;
@@ -555,7 +730,7 @@ int n2m_s0_composite_loss(const n2m_s0_params* p, const void* out, const void* r
     if (N == 0) return 0;
     N2M_REQUIRE(p && out && recs && rays && counters && gt && bg && loss_scale && dout && image && weights_sum && depth && loss_out,
                 "s0_composite_loss", "null pointer");
-    k_s0_composite_loss<<<div_up(N, 128u), 128, 0, as_stream(stream)>>>(*p, static_cast<const float4*>(out), static_cast<const float4*>(recs),
+    k_s0_composite_loss<<<div_up(N * 32u, 128u), 128, 0, as_stream(stream)>>>(*p, static_cast<const float4*>(out), static_cast<const float4*>(recs),
                                                                         rays, counters, N, gt, bg, loss_scale, static_cast<float4*>(dout),
                                                                         image, weights_sum, depth, loss_out);
     return check_launch("s0_composite_loss");

@@ -35,6 +35,7 @@ PP = ctypes.POINTER(S0Params)
 
 _lib.register({
     "n2m_s0_init": [],
+    "n2m_s0_set_serial_march": [I],
     "n2m_s0_pack_weights": [P, P, P],
     "n2m_s0_pack_tables": [P, P, U, P, P, P],
     "n2m_s0_unpack_tables": [P, P, U, P, P, P],

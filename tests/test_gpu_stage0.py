@@ -186,3 +186,30 @@ def test_overflow_drops_rays_and_inf_skips_step():
     torch.cuda.synchronize()
     assert torch.equal(before, tr.mlp) and tr.opt_state[2].item() == 0
     assert tr.opt_state[0].item() == pytest.approx(5e29, rel=1e-3)
+
+
+@pytest.mark.parametrize("name", cases.MARCH_CASES)
+def test_warp_marcher_equals_serial_marcher(name):
+    """The warp-per-ray marcher must reproduce the sequential marcher bit for bit (counts and (t, dt) of every
+    sample), for every marching configuration incl. cascades, dt_gamma > 0 and contraction."""
+    from nerf2mesh_b200._lib import call
+    c = cases.march_case(name)
+    Nr = c["rays_o"].shape[0]
+    cfg = Stage0Config(bound=c["bound"], contract=c["contract"], dt_gamma=c["dt_gamma"], num_rays=Nr, max_samples=Nr * 1024)
+    assert cfg.cascade == c["C"]
+    tr = Stage0Trainer(cfg)
+    tr.set_occupancy(c["bits"])
+    tr.rays_o.copy_(c["rays_o"]); tr.rays_d.copy_(c["rays_d"]); tr.noises.copy_(c["noises"])
+    res = []
+    for serial in (1, 0):
+        call("n2m_s0_set_serial_march", serial)
+        tr.recs.zero_()
+        tr.march()
+        torch.cuda.synchronize()
+        res.append((tr.counters.clone(), tr.rays.clone(), tr.recs.clone()))
+    call("n2m_s0_set_serial_march", 0)
+    (c0, r0, s0), (c1, r1, s1) = res
+    assert torch.equal(c0, c1) and c0[0].item() > 0
+    assert torch.equal(r0, r1)
+    M = int(c0[1].item())
+    assert torch.equal(s0[:M], s1[:M])
