@@ -140,11 +140,13 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from nerf2mesh_b200 import _lib
     from nerf2mesh_b200.stage0 import Stage0Config, Stage0Trainer
-    from nerf2mesh_b200.parallel import GradSync
+    from nerf2mesh_b200.parallel import GradSync, PeerAdam
 
     cfg = Stage0Config(bound=1.0, num_rays=NUM_RAYS, max_samples=NUM_RAYS * 128)
     tr = Stage0Trainer(cfg, seed=0)
-    sync = GradSync(tr) if world > 1 else None
+    sync = None
+    if world > 1:
+        sync = GradSync(tr) if args.dp == "nccl" else PeerAdam(tr)
     n_batches = 8
     host_batches, grid, bits = make_batches(n_batches, 1000 + rank, True)
     dev_batches = [{k: v.cuda(non_blocking=True) for k, v in b.items()} for b in host_batches]
@@ -152,8 +154,14 @@ def run_ours(args):
     m_total = torch.zeros(1, dtype=torch.int64, device="cuda")
     K, W = args.steps, args.warmup
 
-    def one_step(b, it):
-        tr.step(b["ro"], b["rd"], b["gt"], b["bg"], b["noises"], shading="full", use_graph=not args.no_graph, grad_sync=sync)
+    def tup(b):
+        return (b["ro"], b["rd"], b["gt"], b["bg"], b["noises"])
+
+    def one_step(batches, it):
+        # the next batch is handed over too: its H2D copy + march overlap this step on a side stream
+        b = batches[it % n_batches]
+        nb = None if args.no_prefetch else tup(batches[(it + 1) % n_batches])
+        tr.step(*tup(b), shading="full", use_graph=not args.no_graph, grad_sync=sync, next_batch=nb)
         m_total.add_(tr.counters[1])
 
     def barrier():
@@ -170,7 +178,7 @@ def run_ours(args):
 
     # ---- leg 1: device-resident inputs ----
     for it in range(W):
-        one_step(dev_batches[it % n_batches], it)
+        one_step(dev_batches, it)
     barrier()
     m_total.zero_()
     sampler = ClockSampler(local); sampler.start()
@@ -178,7 +186,7 @@ def run_ours(args):
     barrier()
     e0.record()
     for it in range(K):
-        one_step(dev_batches[it % n_batches], it)
+        one_step(dev_batches, W + it)
     e1.record()
     barrier()
     clocks = sampler.stop()
@@ -191,6 +199,7 @@ def run_ours(args):
     value = samples_total / (ms_total * 1e-3)
 
     # ---- leg 2: end to end (pinned host -> device inside the timed region, loss read back every step) ----
+    tr.drop_prefetch()
     barrier()
     m_total.zero_()
     loss_host = torch.zeros(4).pin_memory(); cnt_host = torch.zeros(4, dtype=torch.int32).pin_memory()
@@ -199,8 +208,7 @@ def run_ours(args):
     f0.record()
     e2e_samples = 0
     for it in range(K):
-        b = host_batches[it % n_batches]
-        tr.step(b["ro"], b["rd"], b["gt"], b["bg"], b["noises"], shading="full", use_graph=not args.no_graph, grad_sync=sync)
+        one_step(host_batches, it)
         loss_host.copy_(tr.loss_acc, non_blocking=True); cnt_host.copy_(tr.counters, non_blocking=True)
         torch.cuda.current_stream().synchronize()            # the user-visible result of the step
         e2e_samples += int(cnt_host[1])
@@ -214,6 +222,8 @@ def run_ours(args):
     d2h = loss_host.numel() * 4 + cnt_host.numel() * 4
 
     # ---- per-stage device times (eager, CUDA events on the launching stream) -> roofline of the dominant kernel ----
+    tr.drop_prefetch()
+    torch.cuda.synchronize()
     stages = ["march", "encode_fwd", "mlp_fwd", "composite_loss", "mlp_bwd", "encode_bwd", "adam"]
     acc = {s: 0.0 for s in stages}
     reps = 5
@@ -247,7 +257,7 @@ def run_ours(args):
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16",
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "rays_per_batch": NUM_RAYS, "global_rays": NUM_RAYS * world,
-                           "samples_per_step": samples_total / K, "parallelism": f"dp{world}", "cuda_graph": not args.no_graph,
+                           "samples_per_step": samples_total / K, "parallelism": f"dp{world}" + ("" if world == 1 else f"-{args.dp}"), "cuda_graph": not args.no_graph, "march_prefetch": not args.no_prefetch,
                            "l2": "inputs cycle over 8 batches; tables+grads+Adam state (0.6 GB touched per step) exceed the 126 MB L2"},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -266,7 +276,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-prefetch", action="store_true", help="do not overlap the next batch's march with this step")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--dp", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: 'peer' = fused reduce-scatter+Adam+all-gather over NVLink peer memory, 'nccl' = all-reduce + replicated Adam")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -8,13 +8,13 @@
  *   n2m_s0_march          raymarching.near_far_from_aabb + march_rays_train (raymarching.py:19-49,181-245;
  *                          raymarching.cu:92-145,338-475) without the .item() sync (raymarching.py:232)
  *   n2m_s0_encode_fwd     GridEncoder.forward x2 (grid.py:151-168; gridencoder.cu:88-196) + cat + safe_normalize
+ *                          + grad_total_variation (gridencoder.cu:506-609; utils.py:801-823)
  *   n2m_s0_mlp_fwd        sigma_net / color_net / specular_net + trunc_exp / sigmoid / clamp
  *                          (nerf/network.py:81-108,159-189) on tcgen05 tensor cores
  *   n2m_s0_composite_loss composite_rays_train fwd+bwd (raymarching.cu:501-694), background mix
  *                          (renderer.py:804) and the MSE(+mask, +specular) loss (utils.py:660-738)
  *   n2m_s0_mlp_bwd        autograd of the three MLPs (dgrad + wgrad) on tcgen05
- *   n2m_s0_encode_bwd     grid_encode backward x2 (gridencoder.cu:248-339) + grad_total_variation
- *                          (gridencoder.cu:506-609; utils.py:801-823)
+ *   n2m_s0_encode_bwd     grid_encode backward x2 (gridencoder.cu:248-339)
  *   n2m_s0_adam           GradScaler.unscale_/step/update + Adam(eps 1e-15) + the per-step fp32->fp16
  *                          table cast (grid.py:45-46) + zero_grad  (utils.py:549,1163,1176-1177)
  *
@@ -68,6 +68,12 @@ int n2m_s0_init(void);
 /* test hook: 1 = sequential one-thread-per-ray marcher, 0 = warp-per-ray marcher (default); same results */
 int n2m_s0_set_serial_march(int on);
 
+/* tuning hook: 1 = TV gradient in the forward gather kernel, 0 = in the backward scatter kernel (default) */
+int n2m_s0_set_tv_in_fwd(int on);
+
+/* test hook: MLP backward variant, 1 = two tiles in flight + issuer warp (default), 0 = one tile per CTA */
+int n2m_s0_set_mlp_bwd_pipelined(int on);
+
 /* sizes of the packed weight blob (bytes) and of the flat fp32 MLP parameter / gradient vector (floats) */
 uint32_t n2m_s0_wpack_bytes(void);
 uint32_t n2m_s0_mlp_param_count(void);      /* 7648 = 608+32 + 2240+4096+384 + 192+96 */
@@ -91,9 +97,26 @@ int n2m_s0_march(const n2m_s0_params* p, const float* rays_o, const float* rays_
                  int32_t* rays, int32_t* counters, float* tbuf, void* recs, uint32_t Mcap,
                  n2m_stream_t stream);
 
+/* gtable / loss_scale nullable: when given (and lambda_tv > 0) the TV gradient of the density features is added
+ * to gtable here, where 4 of its 7 stencil values are already in registers */
 int n2m_s0_encode_fwd(const n2m_s0_params* p, const void* recs, const int32_t* counters, uint32_t Mcap,
                       const float* rays_o, const float* rays_d, const void* table, const int32_t* offsets,
-                      void* enc_tiles, n2m_stream_t stream);
+                      void* enc_tiles, void* gtable, const float* loss_scale, n2m_stream_t stream);
+
+/* same gather for explicit positions xyz [P,3] in [-bound, bound] (dirs [P,3] nullable); counters[1] = P.  Used by the
+ * density-grid update and by tests. */
+int n2m_s0_encode_points(const n2m_s0_params* p, const float* xyz, const float* dirs, const int32_t* counters, uint32_t Pcap,
+                         const void* table, const int32_t* offsets, void* enc_tiles, n2m_stream_t stream);
+
+/* density-grid update pieces (NeRFRenderer.update_extra_state, renderer.py:1074-1149):
+ *   grid_points : jittered centres of cells [first_cell, first_cell+count) of one cascade, Morton order; noise [count,3] in [0,1)
+ *   grid_update : cells[i] = max(cells[i] * decay, sigma_i) where both >= 0 (sigma_i = out[i].x)
+ *   packbits_dev: bit = grid > min(*mean_density, density_thresh), threshold read on the device */
+int n2m_s0_grid_points(uint32_t H, uint32_t first_cell, uint32_t count, float cas_bound, const float* noise, float* xyz,
+                       n2m_stream_t stream);
+int n2m_s0_grid_update(const void* out, uint32_t count, float decay, float* grid_cells, n2m_stream_t stream);
+int n2m_s0_packbits_dev(const float* grid, uint32_t nbytes, const float* mean_density, float density_thresh, uint8_t* bitfield,
+                        n2m_stream_t stream);
 
 /* out [Mcap] float4 {sigma, r, g, b}; spec_sq_sum: += sum over samples of |specular|^2 (for the loss value) */
 int n2m_s0_mlp_fwd(const n2m_s0_params* p, const void* enc_tiles, const int32_t* counters, uint32_t Mcap,
@@ -112,7 +135,7 @@ int n2m_s0_mlp_bwd(const n2m_s0_params* p, const void* enc_tiles, const void* do
                    uint32_t Mcap, const void* wpack, void* denc_tiles, float* g_mlp, const float* loss_scale,
                    n2m_stream_t stream);
 
-/* scatter denc into gtable (+ TV gradient of the density features, scaled by *loss_scale) */
+/* scatter denc into gtable */
 int n2m_s0_encode_bwd(const n2m_s0_params* p, const void* recs, const int32_t* counters, uint32_t Mcap,
                       const float* rays_o, const float* rays_d, const void* denc_tiles, const void* table,
                       const int32_t* offsets, void* gtable, const float* loss_scale, n2m_stream_t stream);
@@ -127,6 +150,26 @@ int n2m_s0_encode_bwd(const n2m_s0_params* p, const void* recs, const int32_t* c
 int n2m_s0_adam(void* table, void* color_master, void* gtable, float* m_table, float* v_table, uint32_t rows,
                 float* mlp_params, float* g_mlp, float* m_mlp, float* v_mlp, void* wpack,
                 float* opt_state, float eps, n2m_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Data-parallel optimizer fused with its collective over NVLink peer memory (csrc/dp.cu).
+ * One process per GPU; buffers of the other ranks are mapped with CUDA IPC.
+ * ---------------------------------------------------------------------------------------- */
+int n2m_ipc_export(const void* ptr, void* handle_out /* 64 bytes */, uint64_t* offset_out);
+int n2m_ipc_open(const void* handle, void** base_out);
+int n2m_ipc_close(void* base);
+uint32_t n2m_dp_ctx_bytes(void);
+/* host image of the device context: per-peer pointers to gradient tables (two parities), working tables, MLP
+ * gradient vectors, optimizer state blocks and flag arrays (>= 16 uint32 each, zero-initialised) */
+int n2m_dp_ctx_fill(void* host_ctx, uint32_t world, uint32_t rank, uint32_t rows, uint32_t n_mlp,
+                    void* const* gtab0, void* const* gtab1, void* const* table, void* const* gmlp0, void* const* gmlp1,
+                    void* const* opt, void* const* flags, void* epoch);
+int n2m_dp_barrier(const void* ctx, n2m_stream_t stream);
+/* barrier -> reduce-scatter + Adam + all-gather on this rank's row slice -> MLP -> zero next-parity grads -> barrier.
+ * color_master / m / v are slice-sized: ceil(rows / world) rows. */
+int n2m_dp_adam(const void* ctx, uint32_t parity, uint32_t world, uint32_t rows, uint32_t n_mlp, void* color_master_slice,
+                float* m_slice, float* v_slice, float* mlp_params, float* m_mlp, float* v_mlp, void* wpack,
+                void* gtab_next, float* gmlp_next, float* opt_state, float eps, n2m_stream_t stream);
 
 #ifdef __cplusplus
 }

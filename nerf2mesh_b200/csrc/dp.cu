@@ -1,0 +1,281 @@
+// dp.cu -- data-parallel optimizer step fused with its collective, over NVLink peer memory.
+//
+// With rays sharded across W GPUs every rank ends its backward pass with a full-size gradient table
+// (98 MB).  The library baseline (NCCL all-reduce of 98 MB, then a full Adam on every rank) costs
+// ~245 us of NVLink time + ~96 us of HBM streaming per step at W = 8.  This file does it as ONE pass:
+//
+//   reduce-scatter : rank r reads rows [r R/W, (r+1) R/W) of every peer's gradient table straight from the
+//                    peers' HBM (P2P loads over NVLink 5 / NVSwitch) and sums them,
+//   optimizer      : applies GradScaler-unscale + Adam to that 1/W slice only (moments and fp32 colour
+//                    masters exist only for the slice it owns: the Adam stream shrinks W-fold),
+//   all-gather     : writes the updated 8-byte table entries into every peer's table (P2P stores),
+//
+// so the NVLink payload per rank is (W-1)/W * (16 + 8) bytes per row instead of 2 * (W-1)/W * 16 for the
+// ring all-reduce, and it overlaps with the arithmetic row by row.  Two system-scope flag barriers
+// (k_dp_barrier) order it against the backward pass before and the forward pass after; gradient tables
+// are double-buffered per step parity so the table being reduced by peers is never the one being zeroed.
+#include "n2m_common.cuh"
+#include "../../include/n2m_b200_fused.h"
+#include <cuda.h>
+
+namespace n2m {
+namespace {
+
+constexpr int kMaxWorld = 8;
+constexpr float kBeta1 = 0.9f, kBeta2 = 0.999f;
+
+struct __align__(8) TableEntry { float d; __half2 c; };
+
+struct DpCtx {
+    uint32_t world, rank;
+    uint32_t rows, n_mlp;
+    float4* gtab[kMaxWorld][2];        // [peer][parity] gradient tables (peer pointers mapped through CUDA IPC)
+    TableEntry* table[kMaxWorld];      // [peer] working tables
+    float* gmlp[kMaxWorld][2];         // [peer][parity] MLP gradient vectors
+    float* opt[kMaxWorld];             // [peer] optimizer state blocks (found_inf at [3])
+    uint32_t* flags[kMaxWorld];        // [peer] flag arrays: slots 0..7 barrier epochs, slots 8+parity "this rank saw inf"
+    uint32_t* epoch;                   // local barrier epoch counter (device)
+};
+
+// system-scope flag barrier: every rank bumps its slot in every peer's flag array, then waits until all
+// slots of its own array have reached the new epoch.
+__global__ void k_dp_barrier(const DpCtx* __restrict__ ctx) {
+    const uint32_t p = threadIdx.x;
+    const uint32_t W = ctx->world, r = ctx->rank;
+    const uint32_t e = *ctx->epoch + 1;
+    if (p < W) {
+        __threadfence_system();
+        volatile uint32_t* remote = ctx->flags[p] + r;
+        *remote = e;
+        __threadfence_system();
+        volatile uint32_t* mine = ctx->flags[r] + p;
+        uint64_t spins = 0;
+        while ((int32_t)(*mine - e) < 0) {
+            if (++spins > (1ull << 31)) __trap();          // a missing peer traps instead of hanging forever
+        }
+    }
+    __syncthreads();
+    if (p == 0) *ctx->epoch = e;
+}
+
+__device__ __forceinline__ float adam_update(float p, float g, float& m, float& v, float lr_over_bc1, float bc2s, float eps) {
+    m = kBeta1 * m + (1.f - kBeta1) * g;
+    v = kBeta2 * v + (1.f - kBeta2) * g * g;
+    const float denom = __fdiv_rn(__fsqrt_rn(v), bc2s) + eps;
+    return p - lr_over_bc1 * __fdiv_rn(m, denom);
+}
+
+// publish this rank's found_inf for the step (parity-indexed slot: rewritten only two steps later, so a slow peer
+// can still read it after this rank has moved on)
+__global__ void k_dp_publish_inf(const DpCtx* __restrict__ ctx, uint32_t parity, const float* __restrict__ st) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    ctx->flags[ctx->rank][kMaxWorld + parity] = st[3] != 0.f ? 1u : 0u;
+    __threadfence_system();
+}
+
+// found_inf = OR over ranks (every rank computes the same value), then the usual per-step constants
+__global__ void k_dp_prep(const DpCtx* __restrict__ ctx, uint32_t parity, float* __restrict__ st) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float inf = 0.f;
+    for (uint32_t p = 0; p < ctx->world; ++p)
+        if (*reinterpret_cast<volatile uint32_t*>(ctx->flags[p] + kMaxWorld + parity) != 0u) inf = 1.f;
+    st[3] = inf;
+    if (inf == 0.f) st[2] += 1.f;
+    const float t = fmaxf(st[2], 1.f);
+    st[5] = 1.f - powf(kBeta1, t);
+    st[6] = sqrtf(1.f - powf(kBeta2, t));
+    st[7] = 1.f / (st[0] * (float)ctx->world);          // unscale and average over ranks in one factor
+}
+
+constexpr int kRowsPerThread = 2;
+
+// reduce-scatter + Adam + all-gather on this rank's row slice; also zeroes the local gradient table of the
+// other parity (the one the next step's backward accumulates into).
+__global__ void __launch_bounds__(256)
+k_dp_adam_tables(const DpCtx* __restrict__ ctx, uint32_t parity, float2* __restrict__ cmaster, float* __restrict__ m,
+                 float* __restrict__ v, const float* __restrict__ st, float eps) {
+    const uint32_t W = ctx->world, r = ctx->rank, rows = ctx->rows;
+    const uint32_t per = (rows + W - 1) / W;
+    const uint32_t lo = r * per, hi = min(rows, lo + per);
+    const bool skip = st[3] != 0.f;
+    const float inv = st[7];
+    const float lr1 = __fdiv_rn(st[4], st[5]), bc2s = st[6];
+    // slice-local optimizer state: index i - lo
+    float2* mc_p = reinterpret_cast<float2*>(m + per);
+    float2* vc_p = reinterpret_cast<float2*>(v + per);
+    const uint32_t i0 = lo + blockIdx.x * (256 * kRowsPerThread) + threadIdx.x;
+
+    float4 g[kRowsPerThread];
+#pragma unroll
+    for (int j = 0; j < kRowsPerThread; ++j) {
+        const uint32_t i = i0 + j * 256;
+        g[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < hi) {
+            float4 q[kMaxWorld];
+#pragma unroll
+            for (int p = 0; p < kMaxWorld; ++p)
+                if (p < (int)W) q[p] = __ldcv(ctx->gtab[p][parity] + i);       // peer HBM over NVLink (L2-bypassing on the reader)
+#pragma unroll
+            for (int p = 0; p < kMaxWorld; ++p)
+                if (p < (int)W) { g[j].x += q[p].x; g[j].y += q[p].y; g[j].z += q[p].z; }
+        }
+    }
+    if (skip) return;
+#pragma unroll
+    for (int j = 0; j < kRowsPerThread; ++j) {
+        const uint32_t i = i0 + j * 256;
+        if (i >= hi) continue;
+        const uint32_t k = i - lo;
+        const float gx = g[j].x * inv, gy = g[j].y * inv, gz = g[j].z * inv;
+        float md = m[k], vd = v[k];
+        float2 mc = mc_p[k], vc = vc_p[k];
+        if (gx == 0.f && gy == 0.f && gz == 0.f && md == 0.f && vd == 0.f && mc.x == 0.f && mc.y == 0.f && vc.x == 0.f && vc.y == 0.f)
+            continue;
+        TableEntry e = ctx->table[r][i];
+        float2 pc = cmaster[k];
+        e.d = adam_update(e.d, gx, md, vd, lr1, bc2s, eps);
+        pc.x = adam_update(pc.x, gy, mc.x, vc.x, lr1, bc2s, eps);
+        pc.y = adam_update(pc.y, gz, mc.y, vc.y, lr1, bc2s, eps);
+        e.c = __floats2half2_rn(pc.x, pc.y);
+        cmaster[k] = pc;
+        m[k] = md; v[k] = vd; mc_p[k] = mc; vc_p[k] = vc;
+#pragma unroll
+        for (int p = 0; p < kMaxWorld; ++p)
+            if (p < (int)W) ctx->table[p][i] = e;                               // all-gather: P2P stores
+    }
+}
+
+// zero the local gradient buffers of the next parity (full size, local HBM only)
+__global__ void __launch_bounds__(256)
+k_dp_zero(float4* __restrict__ gtab, uint32_t rows, float* __restrict__ gmlp, uint32_t n_mlp) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < rows) gtab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < n_mlp) gmlp[i] = 0.f;
+}
+
+// MLP parameters: every rank reduces all peers' (tiny) gradient vectors and applies the same update
+__global__ void __launch_bounds__(256)
+k_dp_adam_mlp(const DpCtx* __restrict__ ctx, uint32_t parity, float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+              const float* __restrict__ st, float eps) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ctx->n_mlp) return;
+    float g = 0.f;
+    for (uint32_t q = 0; q < ctx->world; ++q) g += __ldcv(ctx->gmlp[q][parity] + i);
+    if (st[3] != 0.f) return;
+    g *= st[7];
+    float mi = m[i], vi = v[i];
+    p[i] = adam_update(p[i], g, mi, vi, __fdiv_rn(st[4], st[5]), st[6], eps);
+    m[i] = mi; v[i] = vi;
+}
+
+__global__ void k_dp_post(float* __restrict__ st) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (st[3] != 0.f) { st[0] *= 0.5f; st[1] = 0.f; }
+    else {
+        st[1] += 1.f;
+        if (st[1] >= 2000.f) { st[0] *= 2.0f; st[1] = 0.f; }
+    }
+    st[3] = 0.f;
+}
+
+}  // namespace
+}  // namespace n2m
+
+using namespace n2m;
+
+extern "C" {
+
+int n2m_s0_pack_weights(const float* mlp_params, void* wpack, n2m_stream_t stream);
+
+/* ---- CUDA IPC helpers (one process per GPU): export the allocation that contains `ptr` ---- */
+int n2m_ipc_export(const void* ptr, void* handle_out, uint64_t* offset_out) {
+    N2M_REQUIRE(ptr && handle_out && offset_out, "ipc_export", "null pointer");
+    CUdeviceptr base = 0; size_t size = 0;
+    // driver entry point resolved at run time: the library must stay loadable on hosts without libcuda.so
+    typedef CUresult (*range_fn)(CUdeviceptr*, size_t*, CUdeviceptr);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
+        return fail("ipc_export", "cuMemGetAddressRange entry point not available");
+    if (reinterpret_cast<range_fn>(fn)(&base, &size, (CUdeviceptr)ptr) != CUDA_SUCCESS) return fail("ipc_export", "cuMemGetAddressRange failed");
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, (void*)base);
+    if (e != cudaSuccess) return fail("ipc_export", cudaGetErrorString(e));
+    memcpy(handle_out, &h, sizeof(h));
+    *offset_out = (uint64_t)((CUdeviceptr)ptr - base);
+    return 0;
+}
+
+int n2m_ipc_open(const void* handle, void** base_out) {
+    N2M_REQUIRE(handle && base_out, "ipc_open", "null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    cudaError_t e = cudaIpcOpenMemHandle(base_out, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail("ipc_open", cudaGetErrorString(e));
+    return 0;
+}
+
+int n2m_ipc_close(void* base) {
+    cudaError_t e = cudaIpcCloseMemHandle(base);
+    if (e != cudaSuccess) return fail("ipc_close", cudaGetErrorString(e));
+    return 0;
+}
+
+uint32_t n2m_dp_ctx_bytes(void) { return (uint32_t)sizeof(DpCtx); }
+
+/* host-side fill of a DpCtx image (then cudaMemcpy'd to the device by the caller) */
+int n2m_dp_ctx_fill(void* host_ctx, uint32_t world, uint32_t rank, uint32_t rows, uint32_t n_mlp,
+                    void* const* gtab0, void* const* gtab1, void* const* table, void* const* gmlp0, void* const* gmlp1,
+                    void* const* opt, void* const* flags, void* epoch) {
+    N2M_REQUIRE(host_ctx && world >= 1 && world <= (uint32_t)kMaxWorld && rank < world, "dp_ctx_fill", "bad arguments");
+    DpCtx c;
+    memset(&c, 0, sizeof(c));
+    c.world = world; c.rank = rank; c.rows = rows; c.n_mlp = n_mlp;
+    for (uint32_t p = 0; p < world; ++p) {
+        c.gtab[p][0] = (float4*)gtab0[p]; c.gtab[p][1] = (float4*)gtab1[p];
+        c.table[p] = (TableEntry*)table[p];
+        c.gmlp[p][0] = (float*)gmlp0[p]; c.gmlp[p][1] = (float*)gmlp1[p];
+        c.opt[p] = (float*)opt[p]; c.flags[p] = (uint32_t*)flags[p];
+    }
+    c.epoch = (uint32_t*)epoch;
+    memcpy(host_ctx, &c, sizeof(c));
+    return 0;
+}
+
+int n2m_dp_barrier(const void* ctx, n2m_stream_t stream) {
+    N2M_REQUIRE(ctx, "dp_barrier", "null pointer");
+    k_dp_barrier<<<1, 32, 0, as_stream(stream)>>>(static_cast<const DpCtx*>(ctx));
+    return check_launch("dp_barrier");
+}
+
+/* barrier -> [found_inf OR, step constants] -> reduce-scatter + Adam + all-gather (tables) -> MLP -> repack ->
+ * zero next-parity gradients -> scaler update -> barrier.   m/v/color_master are SLICE-sized (ceil(rows/world) rows). */
+int n2m_dp_adam(const void* ctx, uint32_t parity, uint32_t world, uint32_t rows, uint32_t n_mlp, void* color_master_slice,
+                float* m_slice, float* v_slice, float* mlp_params, float* m_mlp, float* v_mlp, void* wpack,
+                void* gtab_next, float* gmlp_next, float* opt_state, float eps, n2m_stream_t stream) {
+    N2M_REQUIRE(ctx && color_master_slice && m_slice && v_slice && mlp_params && m_mlp && v_mlp && wpack && gtab_next && gmlp_next && opt_state,
+                "dp_adam", "null pointer");
+    cudaStream_t st = as_stream(stream);
+    const DpCtx* c = static_cast<const DpCtx*>(ctx);
+    k_dp_publish_inf<<<1, 32, 0, st>>>(c, parity, opt_state);
+    if (int e = check_launch("dp_adam(publish)")) return e;
+    k_dp_barrier<<<1, 32, 0, st>>>(c);
+    if (int e = check_launch("dp_adam(barrier A)")) return e;
+    k_dp_prep<<<1, 32, 0, st>>>(c, parity, opt_state);
+    if (int e = check_launch("dp_adam(prep)")) return e;
+    const uint32_t per = (rows + world - 1) / world;
+    k_dp_adam_tables<<<div_up(per, 256u * kRowsPerThread), 256, 0, st>>>(c, parity, static_cast<float2*>(color_master_slice), m_slice, v_slice,
+                                                                       opt_state, eps);
+    if (int e = check_launch("dp_adam(tables)")) return e;
+    k_dp_adam_mlp<<<div_up(n_mlp, 256u), 256, 0, st>>>(c, parity, mlp_params, m_mlp, v_mlp, opt_state, eps);
+    if (int e = check_launch("dp_adam(mlp)")) return e;
+    if (int e = n2m_s0_pack_weights(mlp_params, wpack, stream)) return e;
+    k_dp_zero<<<div_up(rows, 256u), 256, 0, st>>>(static_cast<float4*>(gtab_next), rows, gmlp_next, n_mlp);
+    if (int e = check_launch("dp_adam(zero)")) return e;
+    k_dp_post<<<1, 32, 0, st>>>(opt_state);
+    if (int e = check_launch("dp_adam(post)")) return e;
+    k_dp_barrier<<<1, 32, 0, st>>>(c);
+    return check_launch("dp_adam(barrier B)");
+}
+
+}  // extern "C"

@@ -83,12 +83,24 @@ k_s0_count_warp(const float* __restrict__ rays_o, const float* __restrict__ rays
     while (!done && ++chunks < (1u << 20)) {       // the cap only guards against a t that cannot advance
         // tau for this lane: `lane` serial steps from the chunk start (all lanes run the loop in lock step)
         float tau = t_start;
-        float t_next = t_start;    // value after 32 steps = next chunk start (lane 31 computes it)
+        float t_next = t_start;    // value after 32 steps = next chunk start
+        if (c.dt_gamma == 0.f) {
+            // dt(t) = clamp(t * 0, dt_min, dt_max) is the same constant for every t (also inf/NaN: fmaxf drops
+            // the NaN), so the chain is 32 dependent FADDs
+            const float dt0 = clampf(0.f, c.dt_min, c.dt_max);
+#pragma unroll
+            for (uint32_t i = 0; i < 32; ++i) {
+                const float adv = t_next + dt0;
+                if (i < lane) tau = adv;
+                t_next = adv;
+            }
+        } else {
 #pragma unroll 1
-        for (uint32_t i = 0; i < 32; ++i) {
-            const float adv = t_next + clampf(t_next * c.dt_gamma, c.dt_min, c.dt_max);
-            if (i < lane) tau = adv;
-            t_next = adv;
+            for (uint32_t i = 0; i < 32; ++i) {
+                const float adv = t_next + clampf(t_next * c.dt_gamma, c.dt_min, c.dt_max);
+                if (i < lane) tau = adv;
+                t_next = adv;
+            }
         }
         const float dt = clampf(tau * c.dt_gamma, c.dt_min, c.dt_max);
         const bool in_range = tau < far;
@@ -249,7 +261,7 @@ __device__ __forceinline__ LevelGeom level_geom(const int32_t* __restrict__ offs
 
 // returns false when the sample is outside [0,1]^3 (the encoders output zeros there)
 __device__ __forceinline__ void corners_of(const LevelGeom& g, float u, float v, float w, Corners& c,
-                                           uint32_t (&base)[3], bool& hashed) {
+                                           uint32_t (&base)[3], bool& hashed, uint32_t* left = nullptr) {
     const float pu = u * g.scale + 0.5f, pv = v * g.scale + 0.5f, pw = w * g.scale + 0.5f;
     const float fu0 = floorf(pu), fv0 = floorf(pv), fw0 = floorf(pw);
     const uint32_t x0 = fu0, y0 = fv0, z0 = fw0;
@@ -282,6 +294,21 @@ __device__ __forceinline__ void corners_of(const LevelGeom& g, float u, float v,
         c.row[k] = pow2 ? (raw & (g.rows - 1)) : (raw % g.rows);
         c.w[k] = wx[ix] * wy[iy] * wz[iz];
     }
+    if (left) {     // rows of the cells at base - 1 along each axis (TV neighbours); callers check base[d] > 0
+        uint32_t lx, ly, lz;
+        if (hashed) {
+            lx = (x0 - 1u) ^ ys[0] ^ zs[0];
+            ly = xs[0] ^ (ys[0] - 2654435761u) ^ zs[0];
+            lz = xs[0] ^ ys[0] ^ (zs[0] - 805459861u);
+        } else {
+            lx = xs[0] - mx + ys[0] + zs[0];
+            ly = xs[0] + ys[0] - my + zs[0];
+            lz = xs[0] + ys[0] + zs[0] - mz;
+        }
+        left[0] = pow2 ? (lx & (g.rows - 1)) : (lx % g.rows);
+        left[1] = pow2 ? (ly & (g.rows - 1)) : (ly % g.rows);
+        left[2] = pow2 ? (lz & (g.rows - 1)) : (lz % g.rows);
+    }
 }
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
@@ -290,51 +317,118 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// encode forward: one block = one 128-sample tile image
+// encode forward: one block = one 128-sample tile image.
+// Also adds the total-variation gradient of the density features (gridencoder.cu:506-609, called from
+// utils.py:801-823) into gtable: the centre and the three +1 neighbours ARE trilinear corners 0,1,2,4 that
+// were just gathered, so TV costs three extra loads here instead of seven in the backward scatter; it is
+// evaluated once per run of consecutive same-cell lanes (it is identical for every sample of a cell).
 // ------------------------------------------------------------------------------------------------
+// POINTS = false: samples come from the march records (training / eval rendering);
+// POINTS = true : explicit positions xyz [P,3] (rays_o) and optional directions [P,3] (rays_d) -- used for the
+//                 density-grid update (renderer.py:1112-1113 evaluates self.density on cell centres) and tests.
+template <bool POINTS, bool TV>
 __global__ void __launch_bounds__(kTile)
 k_s0_encode_fwd(n2m_s0_params p, const float4* __restrict__ recs, const int32_t* __restrict__ counters,
                 const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                 const TableEntry* __restrict__ table, const int32_t* __restrict__ offsets,
-                uint8_t* __restrict__ enc_tiles) {
+                uint8_t* __restrict__ enc_tiles, float4* __restrict__ gtable, const float* __restrict__ loss_scale) {
     const uint32_t M = (uint32_t)counters[1];
     const uint32_t tile = blockIdx.x, r = threadIdx.x;
     if (tile * kTile >= M) return;
+    const uint32_t lane = r & 31;
     const uint32_t j = tile * kTile + r;
     float feat[kTileCols];
 #pragma unroll
     for (uint32_t i = 0; i < kTileCols; ++i) feat[i] = 0.f;
 
+    Sample s;
+    bool active = j < M;
     if (j < M) {
-        const Sample s = sample_of(recs[j], rays_o, rays_d, p);
+        if (POINTS) {
+            s.x = rays_o[3 * j]; s.y = rays_o[3 * j + 1]; s.z = rays_o[3 * j + 2];
+            s.u = __fmul_rn(__fadd_rn(s.x, p.grid_bound), p.inv_2gb);
+            s.v = __fmul_rn(__fadd_rn(s.y, p.grid_bound), p.inv_2gb);
+            s.w = __fmul_rn(__fadd_rn(s.z, p.grid_bound), p.inv_2gb);
+            s.dx = rays_d ? rays_d[3 * j] : 0.f; s.dy = rays_d ? rays_d[3 * j + 1] : 0.f; s.dz = rays_d ? rays_d[3 * j + 2] : 1.f;
+        } else
+        s = sample_of(recs[j], rays_o, rays_d, p);
         feat[kColXyz] = s.x; feat[kColXyz + 1] = s.y; feat[kColXyz + 2] = s.z;
         // safe_normalize (utils.py:41-42): d / sqrt(clamp(sum d^2, 1e-20))
         const float n2 = __fadd_rn(__fadd_rn(__fmul_rn(s.dx, s.dx), __fmul_rn(s.dy, s.dy)), __fmul_rn(s.dz, s.dz));
         const float nrm = __fsqrt_rn(fmaxf(n2, 1e-20f));
         feat[kColDir] = __fdiv_rn(s.dx, nrm); feat[kColDir + 1] = __fdiv_rn(s.dy, nrm); feat[kColDir + 2] = __fdiv_rn(s.dz, nrm);
-        const bool oob = (s.u < 0 || s.u > 1) || (s.v < 0 || s.v > 1) || (s.w < 0 || s.w > 1);
-        if (!oob) {
+        active = !((s.u < 0 || s.u > 1) || (s.v < 0 || s.v > 1) || (s.w < 0 || s.w > 1));
+    } else {
+        s.x = s.y = s.z = s.u = s.v = s.w = 0.5f; s.dx = s.dy = s.dz = 0.f;
+    }
+    const bool do_tv = TV && p.lambda_tv > 0 && gtable != nullptr;
+    // TV weight: lambda inside the unit cube, 10 lambda outside when bound > 1 (utils.py:815-821); w = weight / (2 D)
+    const float mag = fmaxf(fabsf(s.x), fmaxf(fabsf(s.y), fabsf(s.z)));
+    const float lam = (p.grid_bound > 1 && mag > 1) ? p.lambda_tv * 10 : p.lambda_tv;
+    const float tvw_lane = (active && do_tv) ? lam / 6 * loss_scale[0] : 0.f;
+
 #pragma unroll
-            for (uint32_t l = 0; l < kLevels; ++l) {
-                const LevelGeom g = level_geom(offsets, l, p.S, p.base_res);
-                Corners c; uint32_t base[3]; bool hashed;
-                corners_of(g, s.u, s.v, s.w, c, base, hashed);
-                const TableEntry* tab = table + g.row0;
-                uint2 raw[8];
+    for (uint32_t l = 0; l < kLevels; ++l) {
+        const LevelGeom g = level_geom(offsets, l, p.S, p.base_res);
+        Corners c; uint32_t base[3]; bool hashed; uint32_t left[3];
+        corners_of(g, s.u, s.v, s.w, c, base, hashed, TV ? left : nullptr);
+        const TableEntry* tab = table + g.row0;
+        // which lane evaluates the TV term of its cell: the last lane of each run of consecutive same-cell lanes
+        // (decided from the cell ids alone, BEFORE any load, so that the TV neighbours ride in the same load batch)
+        bool issue = false;
+        float tvw = tvw_lane;
+        if (TV && do_tv) {
+            const uint32_t key = active ? (base[0] | (base[1] << 10) | (base[2] << 20)) : 0xffffffffu;
+            const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+            const uint32_t heads = __ballot_sync(0xffffffffu, lane == 0 || key != prev);
+            issue = active;
+            if (g.res < 1023u && heads != 0xffffffffu) {
+                const uint32_t run_start = 31u - __clz(heads & (0xffffffffu >> (31u - lane)));
 #pragma unroll
-                for (int k = 0; k < 8; ++k) raw[k] = __ldg(reinterpret_cast<const uint2*>(tab + c.row[k]));
-                float d = 0.f, c0 = 0.f, c1 = 0.f;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const float2 cc = __half22float2(*reinterpret_cast<const __half2*>(&raw[k].y));
-                    d += c.w[k] * __uint_as_float(raw[k].x);
-                    c0 += c.w[k] * cc.x;
-                    c1 += c.w[k] * cc.y;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const float t = __shfl_up_sync(0xffffffffu, tvw, o);
+                    if (lane >= run_start + (uint32_t)o) tvw += t;
                 }
-                feat[kColDens + l] = d;
-                feat[kColColor + 2 * l] = c0;
-                feat[kColColor + 2 * l + 1] = c1;
+                issue = active && (lane == 31 || ((heads >> (lane + 1)) & 1u));
             }
+        }
+        uint2 raw[8];
+        float lv[3] = {0.f, 0.f, 0.f};
+        if (active) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) raw[k] = __ldg(reinterpret_cast<const uint2*>(tab + c.row[k]));
+            if (TV && issue) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) if (base[d] > 0) lv[d] = __ldg(&tab[left[d]].d);
+            }
+            float d = 0.f, c0 = 0.f, c1 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float2 cc = __half22float2(*reinterpret_cast<const __half2*>(&raw[k].y));
+                d += c.w[k] * __uint_as_float(raw[k].x);
+                c0 += c.w[k] * cc.x;
+                c1 += c.w[k] * cc.y;
+            }
+            feat[kColDens + l] = d;
+            feat[kColColor + 2 * l] = c0;
+            feat[kColColor + 2 * l + 1] = c1;
+        }
+        if (TV && issue) {
+            const float centre = __uint_as_float(raw[0].x);
+            float sum = 0.f, sq = 0.f;
+            const int right_corner[3] = {1, 2, 4};
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                if (base[d] < g.res) {
+                    const float dv = centre - __uint_as_float(raw[right_corner[d]].x);
+                    sum += dv; sq += dv * dv;
+                }
+                if (base[d] > 0) {
+                    const float dv = centre - lv[d];
+                    sum += dv; sq += dv * dv;
+                }
+            }
+            atomicAdd(&gtable[g.row0 + c.row[0]].x, tvw * sum * rsqrtf(sq + 1e-9f));
         }
     }
     // write this row of the tile image: 8 chunks of 16 bytes, each chunk 2 KiB apart
@@ -351,13 +445,13 @@ k_s0_encode_fwd(n2m_s0_params p, const float4* __restrict__ recs, const int32_t*
 }
 
 // ------------------------------------------------------------------------------------------------
-// encode backward: scatter the (loss-scaled, fp16) feature gradients + TV gradient.
+// encode backward: scatter the (loss-scaled, fp16) feature gradients (the TV gradient is added by the forward kernel).
 // L2 atomic throughput bounds this kernel (profiles/r1_notes.md), so at the coarse levels -- where the
 // consecutive samples of a ray (= consecutive lanes) sit in the same lattice cell -- the 8 corner
 // contributions are first summed across each run of same-cell lanes with a segmented warp scan and only the
-// last lane of a run issues the red.global.add.v4.f32; the TV term (identical for every sample of a cell) is
-// evaluated once per run.  Fine levels (every lane its own cell) go straight to the atomics.
+// last lane of a run issues the red.global.add.v4.f32.  Fine levels (every lane its own cell) go straight to the atomics.
 // ------------------------------------------------------------------------------------------------
+template <bool TV>
 __global__ void __launch_bounds__(kTile)
 k_s0_encode_bwd(n2m_s0_params p, const float4* __restrict__ recs, const int32_t* __restrict__ counters,
                 const float* __restrict__ rays_o, const float* __restrict__ rays_d,
@@ -397,25 +491,26 @@ k_s0_encode_bwd(n2m_s0_params p, const float4* __restrict__ recs, const int32_t*
         for (int i = (int)kColDens; i < (int)kColDir; ++i) bad |= !isfinite(g[i]);
         if (bad) loss_scale[3] = 1.f;
     }
-    // TV weight: lambda inside the unit cube, 10 lambda outside when bound > 1 (utils.py:815-821)
-    const float mag = fmaxf(fabsf(s.x), fmaxf(fabsf(s.y), fabsf(s.z)));
-    const float lam = (p.grid_bound > 1 && mag > 1) ? p.lambda_tv * 10 : p.lambda_tv;
-    const float tvw_lane = active ? lam / 6 * loss_scale[0] : 0.f;     // w = weight / (2 * D), kept in the scaled domain
-    const bool do_tv = p.lambda_tv > 0;
-
+    // TV weight: lambda inside the unit cube, 10 lambda outside when bound > 1 (utils.py:815-821); w = weight / (2 D),
+    // kept in the loss-scaled domain
+    float tvw_lane = 0.f;
+    if (TV) {
+        const float mag = fmaxf(fabsf(s.x), fmaxf(fabsf(s.y), fabsf(s.z)));
+        const float lam = (p.grid_bound > 1 && mag > 1) ? p.lambda_tv * 10 : p.lambda_tv;
+        tvw_lane = active ? lam / 6 * loss_scale[0] : 0.f;
+    }
 #pragma unroll 1
     for (uint32_t l = 0; l < kLevels; ++l) {
         const LevelGeom lg = level_geom(offsets, l, p.S, p.base_res);
-        Corners c; uint32_t base[3]; bool hashed;
-        corners_of(lg, s.u, s.v, s.w, c, base, hashed);
+        Corners c; uint32_t base[3]; bool hashed; uint32_t left[3];
+        corners_of(lg, s.u, s.v, s.w, c, base, hashed, TV ? left : nullptr);
+        float tvw = tvw_lane;
         float4* gt = gtable + lg.row0;
         const float gd = active ? g[kColDens + l] : 0.f;
         const float g0 = active ? g[kColColor + 2 * l] : 0.f, g1 = active ? g[kColColor + 2 * l + 1] : 0.f;
         float vd[8], v0[8], v1[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) { vd[k] = c.w[k] * gd; v0[k] = c.w[k] * g0; v1[k] = c.w[k] * g1; }
-        float tvw = tvw_lane;
-
         // runs of consecutive lanes in the same cell
         const uint32_t key = active ? (base[0] | (base[1] << 10) | (base[2] << 20)) : 0xffffffffu;
         const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
@@ -433,8 +528,10 @@ k_s0_encode_bwd(n2m_s0_params p, const float4* __restrict__ recs, const int32_t*
                                 cc = __shfl_up_sync(0xffffffffu, v1[k], o);
                     if (take) { vd[k] += a; v0[k] += b; v1[k] += cc; }
                 }
-                const float t = __shfl_up_sync(0xffffffffu, tvw, o);
-                if (take) tvw += t;
+                if (TV) {
+                    const float t = __shfl_up_sync(0xffffffffu, tvw, o);
+                    if (take) tvw += t;
+                }
             }
             const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
             issue = active && tail;
@@ -442,34 +539,20 @@ k_s0_encode_bwd(n2m_s0_params p, const float4* __restrict__ recs, const int32_t*
         if (issue) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) atomicAdd(gt + c.row[k], make_float4(vd[k], v0[k], v1[k], 0.f));
-            if (do_tv) {        // gridencoder.cu:506-609 on the density feature
+            if (TV) {        // gridencoder.cu:506-609 on the density feature: centre, +1 neighbours = corners 1,2,4, -1 = left[]
                 const TableEntry* tab = table + lg.row0;
-                const uint32_t s1 = lg.res + 1;
-                uint32_t stride = 1, mult[3] = {0, 0, 0};
+                const int right_corner[3] = {1, 2, 4};
+                float centre = __ldg(&tab[c.row[0]].d), rv[3], lv[3];
 #pragma unroll
-                for (int d = 0; d < 3; ++d) if (stride <= lg.rows) { mult[d] = stride; stride *= s1; }
-                const uint32_t prime[3] = {1u, 2654435761u, 805459861u};
-                auto row_of = [&](uint32_t x, uint32_t y, uint32_t z) -> uint32_t {
-                    const uint32_t raw = hashed ? ((x * prime[0]) ^ (y * prime[1]) ^ (z * prime[2]))
-                                                : (x * mult[0] + y * mult[1] + z * mult[2]);
-                    return raw % lg.rows;
-                };
-                const float centre = __ldg(&tab[c.row[0]].d);
+                for (int d = 0; d < 3; ++d) {          // all seven loads are independent: issue them back to back
+                    rv[d] = __ldg(&tab[c.row[right_corner[d]]].d);
+                    lv[d] = base[d] > 0 ? __ldg(&tab[left[d]].d) : 0.f;
+                }
                 float sum = 0.f, sq = 0.f;
 #pragma unroll
                 for (int d = 0; d < 3; ++d) {
-                    uint32_t q[3] = {base[0], base[1], base[2]};
-                    const uint32_t cur = base[d];
-                    if (cur < lg.res) {
-                        q[d] = cur + 1;
-                        const float dv = centre - __ldg(&tab[row_of(q[0], q[1], q[2])].d);
-                        sum += dv; sq += dv * dv;
-                    }
-                    if (cur > 0) {
-                        q[d] = cur - 1;
-                        const float dv = centre - __ldg(&tab[row_of(q[0], q[1], q[2])].d);
-                        sum += dv; sq += dv * dv;
-                    }
+                    if (base[d] < lg.res) { const float dv = centre - rv[d]; sum += dv; sq += dv * dv; }
+                    if (base[d] > 0) { const float dv = centre - lv[d]; sum += dv; sq += dv * dv; }
                 }
                 atomicAdd(&gt[c.row[0]].x, tvw * sum * rsqrtf(sq + 1e-9f));
             }
@@ -607,6 +690,51 @@ k_s0_composite_loss(n2m_s0_params p, const float4* __restrict__ out, const float
 }
 
 // ------------------------------------------------------------------------------------------------
+// density-grid update (NeRFRenderer.update_extra_state, renderer.py:1074-1149)
+// ------------------------------------------------------------------------------------------------
+// jittered cell centres of one cascade, cells enumerated in MORTON order (cell m <-> coords morton3D_invert(m)),
+// so sigma lands directly at density_grid[cas, m] (renderer.py:1100-1118)
+__global__ void __launch_bounds__(256)
+k_s0_grid_points(uint32_t H, uint32_t first_cell, uint32_t count, float cas_bound, const float* __restrict__ noise,
+                 float* __restrict__ xyz) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint32_t m = first_cell + i;
+    const float hgs = cas_bound / (float)H;                  // half_grid_size = bound / grid_size (:1105)
+    const float span = cas_bound - hgs;
+    const uint32_t c[3] = {compact3(m), compact3(m >> 1), compact3(m >> 2)};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float base = __fadd_rn(__fdiv_rn(__fmul_rn(2.0f, (float)c[a]), (float)(H - 1)), -1.0f);   // 2*coord/(H-1) - 1
+        const float jit = __fmul_rn(__fadd_rn(__fmul_rn(noise[3 * i + a], 2.0f), -1.0f), hgs);           // (rand*2-1)*hgs
+        xyz[3 * i + a] = __fadd_rn(__fmul_rn(base, span), jit);
+    }
+}
+
+// grid = max(grid * decay, sigma) where both are >= 0 (renderer.py:1121-1124); sigma = out[i].x
+__global__ void __launch_bounds__(256)
+k_s0_grid_update(const float4* __restrict__ out, uint32_t count, float decay, float* __restrict__ cells) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const float g = cells[i], sg = out[i].x;
+    if (g >= 0.f && sg >= 0.f) cells[i] = fmaxf(g * decay, sg);
+}
+
+// packbits with the threshold min(mean_density, density_thresh) read from device memory (no .item() sync)
+__global__ void __launch_bounds__(256)
+k_s0_packbits_dev(const float* __restrict__ grid, uint32_t nbytes, const float* __restrict__ mean_density, float density_thresh,
+                  uint8_t* __restrict__ bits) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= nbytes) return;
+    const float thresh = fminf(mean_density[0], density_thresh);
+    const float4 a = reinterpret_cast<const float4*>(grid)[2 * n], b = reinterpret_cast<const float4*>(grid)[2 * n + 1];
+    uint32_t v = 0;
+    v |= (a.x > thresh) << 0; v |= (a.y > thresh) << 1; v |= (a.z > thresh) << 2; v |= (a.w > thresh) << 3;
+    v |= (b.x > thresh) << 4; v |= (b.y > thresh) << 5; v |= (b.z > thresh) << 6; v |= (b.w > thresh) << 7;
+    bits[n] = (uint8_t)v;
+}
+
+// ------------------------------------------------------------------------------------------------
 // table (de)interleave
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -645,11 +773,14 @@ k_s0_unpack_grads(const float4* __restrict__ gtable, uint32_t rows, const float*
 using namespace n2m;
 
 static bool g_serial_march = false;
+static bool g_tv_in_fwd = false;     // where the TV gradient is evaluated (measured: cheaper in the scatter kernel)
 
 extern "C" {
 
 /* test hook: 1 = one-thread-per-ray sequential marcher (the reference's structure), 0 = warp-per-ray (default) */
 int n2m_s0_set_serial_march(int on) { g_serial_march = on != 0; return 0; }
+/* test / tuning hook: 1 = TV gradient evaluated by the forward gather kernel, 0 = by the backward scatter kernel (default) */
+int n2m_s0_set_tv_in_fwd(int on) { g_tv_in_fwd = on != 0; return 0; }
 
 int n2m_s0_pack_tables(const float* emb_density, const float* emb_color, uint32_t rows, void* table, void* color_master,
                        n2m_stream_t stream) {
@@ -698,14 +829,54 @@ int n2m_s0_march(const n2m_s0_params* p, const float* rays_o, const float* rays_
 
 int n2m_s0_encode_fwd(const n2m_s0_params* p, const void* recs, const int32_t* counters, uint32_t Mcap,
                       const float* rays_o, const float* rays_d, const void* table, const int32_t* offsets, void* enc_tiles,
-                      n2m_stream_t stream) {
+                      void* gtable, const float* loss_scale, n2m_stream_t stream) {
     N2M_REQUIRE(p && recs && counters && rays_o && rays_d && table && offsets && enc_tiles, "s0_encode_fwd", "null pointer");
+    N2M_REQUIRE(!gtable || loss_scale, "s0_encode_fwd", "gtable given but loss_scale null");
     N2M_REQUIRE(p->num_levels == kLevels, "s0_encode_fwd", "fused path supports num_levels == 16");
     N2M_REQUIRE(Mcap % kTile == 0 && Mcap > 0, "s0_encode_fwd", "Mcap must be a positive multiple of 128");
-    k_s0_encode_fwd<<<Mcap / kTile, kTile, 0, as_stream(stream)>>>(*p, static_cast<const float4*>(recs), counters, rays_o, rays_d,
-                                                                   static_cast<const TableEntry*>(table), offsets,
-                                                                   static_cast<uint8_t*>(enc_tiles));
+    if (g_tv_in_fwd && gtable && p->lambda_tv > 0)
+        k_s0_encode_fwd<false, true><<<Mcap / kTile, kTile, 0, as_stream(stream)>>>(*p, static_cast<const float4*>(recs), counters, rays_o, rays_d,
+                                                                                   static_cast<const TableEntry*>(table), offsets,
+                                                                                   static_cast<uint8_t*>(enc_tiles), static_cast<float4*>(gtable), loss_scale);
+    else
+        k_s0_encode_fwd<false, false><<<Mcap / kTile, kTile, 0, as_stream(stream)>>>(*p, static_cast<const float4*>(recs), counters, rays_o, rays_d,
+                                                                                    static_cast<const TableEntry*>(table), offsets,
+                                                                                    static_cast<uint8_t*>(enc_tiles), nullptr, nullptr);
     return check_launch("s0_encode_fwd");
+}
+
+int n2m_s0_encode_points(const n2m_s0_params* p, const float* xyz, const float* dirs, const int32_t* counters, uint32_t Pcap,
+                         const void* table, const int32_t* offsets, void* enc_tiles, n2m_stream_t stream) {
+    N2M_REQUIRE(p && xyz && counters && table && offsets && enc_tiles, "s0_encode_points", "null pointer");
+    N2M_REQUIRE(p->num_levels == kLevels, "s0_encode_points", "fused path supports num_levels == 16");
+    N2M_REQUIRE(Pcap % kTile == 0 && Pcap > 0, "s0_encode_points", "Pcap must be a positive multiple of 128");
+    k_s0_encode_fwd<true, false><<<Pcap / kTile, kTile, 0, as_stream(stream)>>>(*p, nullptr, counters, xyz, dirs,
+                                                                        static_cast<const TableEntry*>(table), offsets,
+                                                                        static_cast<uint8_t*>(enc_tiles), nullptr, nullptr);
+    return check_launch("s0_encode_points");
+}
+
+int n2m_s0_grid_points(uint32_t H, uint32_t first_cell, uint32_t count, float cas_bound, const float* noise, float* xyz,
+                       n2m_stream_t stream) {
+    N2M_REQUIRE(noise && xyz && H > 1, "s0_grid_points", "bad arguments");
+    if (count == 0) return 0;
+    k_s0_grid_points<<<div_up(count, 256u), 256, 0, as_stream(stream)>>>(H, first_cell, count, cas_bound, noise, xyz);
+    return check_launch("s0_grid_points");
+}
+
+int n2m_s0_grid_update(const void* out, uint32_t count, float decay, float* grid_cells, n2m_stream_t stream) {
+    N2M_REQUIRE(out && grid_cells, "s0_grid_update", "null pointer");
+    if (count == 0) return 0;
+    k_s0_grid_update<<<div_up(count, 256u), 256, 0, as_stream(stream)>>>(static_cast<const float4*>(out), count, decay, grid_cells);
+    return check_launch("s0_grid_update");
+}
+
+int n2m_s0_packbits_dev(const float* grid, uint32_t nbytes, const float* mean_density, float density_thresh, uint8_t* bitfield,
+                        n2m_stream_t stream) {
+    N2M_REQUIRE(grid && mean_density && bitfield, "s0_packbits_dev", "null pointer");
+    if (nbytes == 0) return 0;
+    k_s0_packbits_dev<<<div_up(nbytes, 256u), 256, 0, as_stream(stream)>>>(grid, nbytes, mean_density, density_thresh, bitfield);
+    return check_launch("s0_packbits_dev");
 }
 
 int n2m_s0_encode_bwd(const n2m_s0_params* p, const void* recs, const int32_t* counters, uint32_t Mcap,
@@ -715,10 +886,17 @@ int n2m_s0_encode_bwd(const n2m_s0_params* p, const void* recs, const int32_t* c
                 "s0_encode_bwd", "null pointer");
     N2M_REQUIRE(p->num_levels == kLevels, "s0_encode_bwd", "fused path supports num_levels == 16");
     N2M_REQUIRE(Mcap % kTile == 0 && Mcap > 0, "s0_encode_bwd", "Mcap must be a positive multiple of 128");
-    k_s0_encode_bwd<<<Mcap / kTile, kTile, 0, as_stream(stream)>>>(*p, static_cast<const float4*>(recs), counters, rays_o, rays_d,
-                                                                   static_cast<const uint8_t*>(denc_tiles),
-                                                                   static_cast<const TableEntry*>(table), offsets,
-                                                                   static_cast<float4*>(gtable), const_cast<float*>(loss_scale));
+    // the TV gradient is added here unless the forward kernel was asked to do it (g_tv_in_fwd)
+    if (p->lambda_tv > 0 && !g_tv_in_fwd)
+        k_s0_encode_bwd<true><<<Mcap / kTile, kTile, 0, as_stream(stream)>>>(*p, static_cast<const float4*>(recs), counters, rays_o, rays_d,
+                                                                             static_cast<const uint8_t*>(denc_tiles),
+                                                                             static_cast<const TableEntry*>(table), offsets,
+                                                                             static_cast<float4*>(gtable), const_cast<float*>(loss_scale));
+    else
+        k_s0_encode_bwd<false><<<Mcap / kTile, kTile, 0, as_stream(stream)>>>(*p, static_cast<const float4*>(recs), counters, rays_o, rays_d,
+                                                                              static_cast<const uint8_t*>(denc_tiles),
+                                                                              static_cast<const TableEntry*>(table), offsets,
+                                                                              static_cast<float4*>(gtable), const_cast<float*>(loss_scale));
     return check_launch("s0_encode_bwd");
 }
 

@@ -143,4 +143,34 @@ __device__ __forceinline__ void gemm_issue(uint32_t d_tmem, const Operand& a, co
         mma_f16(d_tmem, a.desc(k), b.desc(k), idesc, accumulate_first || k > 0);
 }
 
+// ---- cheap issue path ------------------------------------------------------------------------------
+// A single thread issues every tcgen05.mma of a CTA, so descriptor arithmetic is on the critical path
+// (profiles/r1_notes.md: ~125 cycles per MMA with smem_desc() rebuilt each time).  The descriptor of k-step
+// `s` differs from that of k-step 0 only in the 14-bit start-address field (low word), by a constant:
+//   K-major : 16 k = 2 chunks          -> += 2 * chunk_bytes / 16 = rows * 2
+//   MN-major: 16 k = 2 groups of 8 rows -> += 256 / 16 = 16
+// so operands are described ONCE (outside the tile loop) and the unrolled issue loop is one IADD per operand.
+struct OpDesc {
+    uint32_t lo, hi, step;       // 64-bit descriptor of k-step 0 (split) and the per-k-step increment of `lo`
+};
+__device__ __forceinline__ OpDesc make_opdesc(const Operand& o) {
+    const uint64_t d = o.desc(0);
+    OpDesc r;
+    r.lo = static_cast<uint32_t>(d);
+    r.hi = static_cast<uint32_t>(d >> 32);
+    r.step = o.mn_major ? 16u : (o.rows * 2u);
+    return r;
+}
+__device__ __forceinline__ uint64_t desc_at(const OpDesc& o, uint32_t s) {
+    return (static_cast<uint64_t>(o.hi) << 32) | static_cast<uint64_t>(o.lo + s * o.step);
+}
+// D[tmem] (+)= A * B over KSTEPS k-steps of 16; shapes and majors are compile-time so the loop unrolls fully
+template <uint32_t N, uint32_t KSTEPS, bool A_MN, bool B_MN>
+__device__ __forceinline__ void gemm_issue_fast(uint32_t d_tmem, const OpDesc& a, const OpDesc& b, bool accumulate_first) {
+    constexpr uint32_t idesc = instr_desc(128, N, A_MN, B_MN);
+#pragma unroll
+    for (uint32_t s = 0; s < KSTEPS; ++s)
+        mma_f16(d_tmem, desc_at(a, s), desc_at(b, s), idesc, accumulate_first || s > 0);
+}
+
 }  // namespace tc

@@ -57,10 +57,62 @@ k_tc_probe(const __half* __restrict__ A, const __half* __restrict__ B, float* __
     if (warp == 0) tc::tmem_dealloc(tmem, 64);
 }
 
+// micro-benchmark: `reps` GEMMs of 128 x N x K issued back to back by one thread (mode 0: one commit + wait at
+// the end => tensor-pipe throughput; mode 1: commit + wait after every GEMM => issue->completion round trip).
+// out[0] = total cycles (clock64 of the issuing thread), out[1] = MMA instructions issued.
+template <uint32_t N, uint32_t KSTEPS, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(128)
+k_tc_bench(uint32_t reps, int mode, unsigned long long* __restrict__ out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) { tc::mbar_init(&bar, 1); tc::mbar_init_fence(); }
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 64);
+    for (uint32_t i = tid; i < 49152 / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    tc::fence_async_smem(); tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+    if (tid == 0) {
+        const tc::OpDesc a = tc::make_opdesc(tc::Operand{tc::smem_u32(smem), 128, A_MN});
+        const tc::OpDesc b = tc::make_opdesc(tc::Operand{tc::smem_u32(smem + 32768), B_MN ? 128u : N, B_MN});
+        uint32_t ph = 0;
+        const long long t0 = clock64();
+        for (uint32_t r = 0; r < reps; ++r) {
+            tc::gemm_issue_fast<N, KSTEPS, A_MN, B_MN>(tmem, a, b, r > 0);
+            if (mode == 1) { tc::mma_commit(&bar); tc::mbar_wait(&bar, ph); ph ^= 1; }
+        }
+        if (mode == 0) { tc::mma_commit(&bar); tc::mbar_wait(&bar, ph); }
+        const long long t1 = clock64();
+        out[0] = (unsigned long long)(t1 - t0);
+        out[1] = (unsigned long long)reps * KSTEPS;
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 64);
+}
+
 }  // namespace
 }  // namespace n2m
 
 using namespace n2m;
+
+extern "C" int n2m_tc_bench(uint32_t N, uint32_t ksteps, int a_mn, int b_mn, uint32_t reps, int mode, unsigned long long* out,
+                            n2m_stream_t stream) {
+    N2M_REQUIRE(out, "tc_bench", "null pointer");
+    cudaStream_t st = as_stream(stream);
+#define RUN(NN, KS, AM, BM)                                                                                         \
+    if (N == NN && ksteps == KS && (a_mn != 0) == AM && (b_mn != 0) == BM) {                                          \
+        cudaFuncSetAttribute(k_tc_bench<NN, KS, AM, BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 49152 + 1024);  \
+        k_tc_bench<NN, KS, AM, BM><<<1, 128, 49152 + 1024, st>>>(reps, mode, out);                                    \
+        return check_launch("tc_bench");                                                                             \
+    }
+    RUN(64, 4, false, false) RUN(16, 4, false, false) RUN(64, 4, false, true) RUN(64, 8, true, true) RUN(16, 8, true, true)
+    RUN(32, 8, true, true) RUN(64, 1, false, true) RUN(32, 1, false, true)
+#undef RUN
+    return fail("tc_bench", "configuration not instantiated");
+}
 
 extern "C" int n2m_tc_probe(const void* A, const void* B, float* D, uint32_t N, uint32_t K, int a_mn, int b_mn,
                             n2m_stream_t stream) {

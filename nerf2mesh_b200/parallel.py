@@ -33,3 +33,114 @@ class GradSync:
 
     def bytes_per_step(self):
         return sum(b.numel() * b.element_size() for b in self.buffers()) + 4
+
+
+# ------------------------------------------------------------------------------------------------
+# fused reduce-scatter + Adam + all-gather over NVLink peer memory (csrc/dp.cu)
+# ------------------------------------------------------------------------------------------------
+import ctypes  # noqa: E402
+
+from . import _lib  # noqa: E402
+from ._lib import F, P, U, call, ptr, stream  # noqa: E402
+
+_lib.register({
+    "n2m_ipc_export": [P, P, ctypes.POINTER(ctypes.c_uint64)],
+    "n2m_ipc_open": [P, ctypes.POINTER(ctypes.c_void_p)],
+    "n2m_ipc_close": [P],
+    "n2m_dp_ctx_fill": [P, U, U, U, U, P, P, P, P, P, P, P, P],
+    "n2m_dp_barrier": [P, P],
+    "n2m_dp_adam": [P, U, U, U, U, P, P, P, P, P, P, P, P, P, P, F, P],
+})
+_lib.lib.n2m_dp_ctx_bytes.restype = ctypes.c_uint32
+
+
+class PeerAdam:
+    """Sharded optimizer for data-parallel training of a Stage0Trainer: each rank owns rows
+    [r*ceil(R/W), (r+1)*ceil(R/W)) of the hash tables.  After the backward pass one kernel per rank reads its
+    slice of every peer's gradient table over NVLink, applies Adam to the slice and stores the refreshed table
+    entries into every peer's table (include/n2m_b200_fused.h, "Data-parallel optimizer").  Replaces
+    GradSync + Stage0Trainer.adam(); the fp32 colour masters and Adam moments exist only for the owned slice."""
+
+    fused = True
+
+    def __init__(self, trainer, group=None):
+        t = self.t = trainer
+        self.group = group
+        self.world = W = dist.get_world_size(group)
+        self.rank = r = dist.get_rank(group)
+        assert W <= 8, "PeerAdam supports up to 8 ranks (one NVSwitch domain)"
+        dev = t.device
+        R = t.rows
+        self.per = per = (R + W - 1) // W
+        lo, hi = r * per, min(R, (r + 1) * per)
+        # second-parity gradient buffers (peers may still be reading parity p while parity p^1 is being zeroed)
+        t.gtables = [t.gtable, torch.zeros_like(t.gtable)]
+        t.g_mlps = [t.g_mlp, torch.zeros_like(t.g_mlp)]
+        self.flags = torch.zeros(16, dtype=torch.int32, device=dev)
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=dev)
+        # slice-sized optimizer state, initialised from the replicated parameters
+        self.cm = torch.zeros(per, 2, device=dev)
+        self.cm[: hi - lo].copy_(t.color_master[lo:hi])
+        self.m = torch.zeros(per * 3, device=dev)
+        self.v = torch.zeros(per * 3, device=dev)
+        torch.cuda.synchronize()
+
+        bufs = {"gtab0": t.gtables[0], "gtab1": t.gtables[1], "table": t.table, "gmlp0": t.g_mlps[0], "gmlp1": t.g_mlps[1],
+                "opt": t.opt_state, "flags": self.flags}
+        mine = {}
+        for k, b in bufs.items():
+            h = ctypes.create_string_buffer(64)
+            off = ctypes.c_uint64(0)
+            call("n2m_ipc_export", ptr(b), ctypes.cast(h, ctypes.c_void_p), ctypes.byref(off))
+            mine[k] = (bytes(h.raw), int(off.value))
+        everyone = [None] * W
+        dist.all_gather_object(everyone, mine, group=group)
+        self._opened = {}
+        ptrs = {k: [0] * W for k in bufs}
+        for p in range(W):
+            for k in bufs:
+                if p == r:
+                    ptrs[k][p] = bufs[k].data_ptr()
+                    continue
+                hb, off = everyone[p][k]
+                base = self._opened.get((p, hb))
+                if base is None:
+                    out = ctypes.c_void_p()
+                    hbuf = ctypes.create_string_buffer(hb, 64)
+                    call("n2m_ipc_open", ctypes.cast(hbuf, ctypes.c_void_p), ctypes.byref(out))
+                    base = out.value
+                    self._opened[(p, hb)] = base
+                ptrs[k][p] = base + off
+
+        def arr(k):
+            a = (ctypes.c_void_p * W)(*ptrs[k])
+            return ctypes.cast(a, ctypes.c_void_p), a          # keep `a` alive
+
+        keep = []
+        args = []
+        for k in ("gtab0", "gtab1", "table", "gmlp0", "gmlp1", "opt", "flags"):
+            c, a = arr(k); keep.append(a); args.append(c)
+        nbytes = int(_lib.lib.n2m_dp_ctx_bytes())
+        host = ctypes.create_string_buffer(nbytes)
+        call("n2m_dp_ctx_fill", ctypes.cast(host, ctypes.c_void_p), W, r, R, t.n_mlp, *args, ptr(self.epoch))
+        self.ctx = torch.frombuffer(bytearray(host.raw), dtype=torch.uint8).to(dev)
+        torch.cuda.synchronize()
+        dist.barrier(group=group)
+
+    def run(self, parity):
+        """Enqueue barrier -> reduce-scatter + Adam + all-gather -> barrier for gradient parity `parity`."""
+        t = self.t
+        nxt = parity ^ 1
+        call("n2m_dp_adam", ptr(self.ctx), parity, self.world, t.rows, t.n_mlp, ptr(self.cm), ptr(self.m), ptr(self.v),
+             ptr(t.mlp), ptr(t.m_mlp), ptr(t.v_mlp), ptr(t.wpack), ptr(t.gtables[nxt]), ptr(t.g_mlps[nxt]), ptr(t.opt_state),
+             t.cfg.eps, stream())
+
+    def nvlink_bytes_per_step(self):
+        W = self.world
+        return int((W - 1) * self.per * (16 + 8) + (W - 1) * self.t.n_mlp * 4)
+
+    def gather_color_master(self):
+        """Full fp32 colour master table (for export): all-gather of the slices."""
+        parts = [torch.zeros_like(self.cm) for _ in range(self.world)]
+        dist.all_gather(parts, self.cm, group=self.group)
+        return torch.cat(parts)[: self.t.rows]

@@ -36,12 +36,18 @@ PP = ctypes.POINTER(S0Params)
 _lib.register({
     "n2m_s0_init": [],
     "n2m_s0_set_serial_march": [I],
+    "n2m_s0_set_mlp_bwd_pipelined": [I],
+    "n2m_s0_set_tv_in_fwd": [I],
     "n2m_s0_pack_weights": [P, P, P],
     "n2m_s0_pack_tables": [P, P, U, P, P, P],
     "n2m_s0_unpack_tables": [P, P, U, P, P, P],
     "n2m_s0_unpack_grads": [P, U, P, P, P, P],
     "n2m_s0_march": [PP, P, P, P, P, P, P, U, P, P, P, P, U, P],
-    "n2m_s0_encode_fwd": [PP, P, P, U, P, P, P, P, P, P],
+    "n2m_s0_encode_fwd": [PP, P, P, U, P, P, P, P, P, P, P, P],
+    "n2m_s0_encode_points": [PP, P, P, P, U, P, P, P, P],
+    "n2m_s0_grid_points": [U, U, U, F, P, P, P],
+    "n2m_s0_grid_update": [P, U, F, P, P],
+    "n2m_s0_packbits_dev": [P, U, P, F, P, P],
     "n2m_s0_mlp_fwd": [PP, P, P, U, P, P, P, P],
     "n2m_s0_composite_loss": [PP, P, P, P, P, U, U, P, P, P, P, P, P, P, P, P],
     "n2m_s0_mlp_bwd": [PP, P, P, P, U, P, P, P, P, P],
@@ -85,6 +91,33 @@ class Stage0Config:
         self.loss_scale = float(loss_scale)
 
 
+class _Slot:
+    """Buffers tied to one batch of rays: inputs, ray (offset, count) table, sample records."""
+
+    def __init__(self, N, Mc, max_steps, dev):
+        self.rays_o = torch.zeros(N, 3, device=dev); self.rays_d = torch.zeros(N, 3, device=dev)
+        self.gt = torch.zeros(N, 4, device=dev); self.bg = torch.zeros(N, 3, device=dev)
+        self.noises = torch.zeros(N, device=dev)
+        self.rays = torch.zeros(N, 2, dtype=torch.int32, device=dev)
+        self.counters = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.tbuf = torch.empty(N * max_steps * 2, device=dev)
+        self.recs = torch.zeros(Mc, 4, device=dev)
+        self.has_alpha = True
+
+    def load(self, rays_o, rays_d, gt, bg, noises=None):
+        N = self.rays_o.shape[0]
+        if gt.shape[-1] == 3:
+            self.gt.view(-1)[: N * 3].view(N, 3).copy_(gt, non_blocking=True)       # packed [N,3] at the front
+            self.has_alpha = False
+        else:
+            self.gt.copy_(gt, non_blocking=True)
+            self.has_alpha = True
+        self.rays_o.copy_(rays_o, non_blocking=True); self.rays_d.copy_(rays_d, non_blocking=True)
+        self.bg.copy_(bg, non_blocking=True)
+        if noises is not None:
+            self.noises.copy_(noises, non_blocking=True)
+
+
 class Stage0Trainer:
     def __init__(self, cfg: Stage0Config, device="cuda", seed=0):
         self.cfg = cfg
@@ -114,16 +147,17 @@ class Stage0Trainer:
         self.density_bitfield = torch.zeros(c.cascade * c.grid_size ** 3 // 8, dtype=torch.uint8, device=dev)
         b = c.real_bound
         self.aabb = torch.tensor([-b, -b, -b, b, b, b], dtype=torch.float32, device=dev)
-        # ---- per-step buffers ----
+        # ---- per-batch buffers: two slots, so the (parameter-independent) march of batch i+1 can run on a side
+        # stream while batch i is in encode / MLP / scatter / Adam ----
         N, Mc = c.num_rays, c.max_samples
         self.N, self.Mcap = N, Mc
-        self.rays_o = torch.zeros(N, 3, device=dev); self.rays_d = torch.zeros(N, 3, device=dev)
-        self.gt = torch.zeros(N, 4, device=dev); self.bg = torch.zeros(N, 3, device=dev)
-        self.noises = torch.zeros(N, device=dev)
-        self.rays = torch.zeros(N, 2, dtype=torch.int32, device=dev)
-        self.counters = torch.zeros(4, dtype=torch.int32, device=dev)
-        self.tbuf = torch.empty(N * c.max_steps * 2, device=dev)
-        self.recs = torch.zeros(Mc, 4, device=dev)
+        self.slots = [_Slot(N, Mc, c.max_steps, dev) for _ in range(2)]
+        self.cur = 0
+        self._prefetched = None                 # slot index holding an already staged + marched batch
+        self._side = None
+        self._ev_march = [None, None]
+        self._ev_done = [None, None]
+        # ---- per-step buffers shared by both slots (consumed within the step) ----
         self.enc_tiles = torch.zeros(Mc * 64, dtype=torch.float16, device=dev)
         self.denc_tiles = torch.zeros(Mc * 64, dtype=torch.float16, device=dev)
         self.out = torch.zeros(Mc, 4, device=dev)
@@ -132,10 +166,23 @@ class Stage0Trainer:
         self.loss_acc = torch.zeros(4, device=dev)          # [0] rgb(+mask) loss, [1] sum |spec|^2
         self.params = S0Params()
         self._fill_params(shading_full=True, gt_has_alpha=True)
+        self.gtables = [self.gtable]        # PeerAdam adds a second parity (parallel.py)
+        self.g_mlps = [self.g_mlp]
+        self.parity = 0
         self.global_step = 0
-        self._graph = None
-        self._graph_key = None
+        self._graphs = {}
         self.reset_parameters(seed)
+
+    # current slot's buffers under their historical names
+    rays_o = property(lambda self: self.slots[self.cur].rays_o)
+    rays_d = property(lambda self: self.slots[self.cur].rays_d)
+    gt = property(lambda self: self.slots[self.cur].gt)
+    bg = property(lambda self: self.slots[self.cur].bg)
+    noises = property(lambda self: self.slots[self.cur].noises)
+    rays = property(lambda self: self.slots[self.cur].rays)
+    counters = property(lambda self: self.slots[self.cur].counters)
+    tbuf = property(lambda self: self.slots[self.cur].tbuf)
+    recs = property(lambda self: self.slots[self.cur].recs)
 
     # -------------------------------------------------------------------------------------------
     def _fill_params(self, shading_full, gt_has_alpha):
@@ -216,7 +263,7 @@ class Stage0Trainer:
 
     def encode_fwd(self):
         call("n2m_s0_encode_fwd", self._pp(), ptr(self.recs), ptr(self.counters), self.Mcap, ptr(self.rays_o), ptr(self.rays_d),
-             ptr(self.table), ptr(self.offsets), ptr(self.enc_tiles), stream())
+             ptr(self.table), ptr(self.offsets), ptr(self.enc_tiles), ptr(self.gtables[self.parity]), ptr(self.opt_state), stream())
 
     def mlp_fwd(self):
         call("n2m_s0_mlp_fwd", self._pp(), ptr(self.enc_tiles), ptr(self.counters), self.Mcap, ptr(self.wpack), ptr(self.out),
@@ -229,11 +276,11 @@ class Stage0Trainer:
 
     def mlp_bwd(self):
         call("n2m_s0_mlp_bwd", self._pp(), ptr(self.enc_tiles), ptr(self.dout), ptr(self.counters), self.Mcap, ptr(self.wpack),
-             ptr(self.denc_tiles), ptr(self.g_mlp), ptr(self.opt_state), stream())
+             ptr(self.denc_tiles), ptr(self.g_mlps[self.parity]), ptr(self.opt_state), stream())
 
     def encode_bwd(self):
         call("n2m_s0_encode_bwd", self._pp(), ptr(self.recs), ptr(self.counters), self.Mcap, ptr(self.rays_o), ptr(self.rays_d),
-             ptr(self.denc_tiles), ptr(self.table), ptr(self.offsets), ptr(self.gtable), ptr(self.opt_state), stream())
+             ptr(self.denc_tiles), ptr(self.table), ptr(self.offsets), ptr(self.gtables[self.parity]), ptr(self.opt_state), stream())
 
     def adam(self):
         call("n2m_s0_adam", ptr(self.table), ptr(self.color_master), ptr(self.gtable), ptr(self.m_table), ptr(self.v_table), self.rows,
@@ -250,58 +297,167 @@ class Stage0Trainer:
         self.mlp_bwd()
         self.encode_bwd()
 
+    def _compute(self):
+        """Everything after the march for the current slot."""
+        self.loss_acc.zero_()
+        self.encode_fwd()
+        self.mlp_fwd()
+        self.composite_loss()
+        self.mlp_bwd()
+        self.encode_bwd()
+
     def _step_body(self):
         self.forward_backward()
         self.adam()
 
     # -------------------------------------------------------------------------------------------
+    def _graph(self, name, fn):
+        """Capture-once CUDA graph of `fn` for the current (slot, shading, alpha) configuration."""
+        key = (name, self.cur, self.parity, int(self.params.shading_full), int(self.params.gt_has_alpha))
+        g = self._graphs.get(key)
+        if g is None:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            self._graphs[key] = g
+        return g
+
+    def _run(self, name, fn, use_graph):
+        if use_graph:
+            self._graph(name, fn).replay()
+        else:
+            fn()
+
     def step(self, rays_o=None, rays_d=None, gt=None, bg_color=None, noises=None, shading="full", lr=None, use_graph=True,
-             grad_sync=None):
-        """One optimizer step.  With tensors given, they are copied into the step buffers first
-        (pinned host tensors -> async H2D on the current stream).  Returns nothing; read
-        `loss_acc` / `counters` (device) afterwards -- no host sync happens here."""
-        has_alpha = bool(self.params.gt_has_alpha)
-        if rays_o is not None:
-            if gt.shape[-1] == 3:
-                self.gt.view(-1)[: self.N * 3].view(self.N, 3).copy_(gt, non_blocking=True)
-                has_alpha = False
-            else:
-                self.gt.copy_(gt, non_blocking=True)
-                has_alpha = True
-            self.rays_o.copy_(rays_o, non_blocking=True); self.rays_d.copy_(rays_d, non_blocking=True)
-            self.bg.copy_(bg_color, non_blocking=True)
-            if noises is not None:
-                self.noises.copy_(noises, non_blocking=True)
+             grad_sync=None, next_batch=None):
+        """One optimizer step on the batch (rays_o, rays_d, gt, bg_color[, noises]).
+
+        * tensors given: copied into the step buffers first (pinned host -> async H2D);
+          with rays_o=None the buffers of the current slot are used as they are.
+        * `next_batch=(rays_o, rays_d, gt, bg[, noises])`: the NEXT step's batch; its H2D copy and its march
+          (which do not depend on the parameters) are enqueued on a side stream and overlap this step's
+          compute.  The following step() call must then pass that same batch (its copy and march are skipped).
+        * `grad_sync`: callable run between backward and optimizer (data-parallel gradient all-reduce).
+        No host sync happens here; read `loss_acc` / `counters` afterwards."""
+        main = torch.cuda.current_stream()
+        if self._prefetched is not None:
+            self.cur = self._prefetched
+            self._prefetched = None
+            main.wait_event(self._ev_march[self.cur])
+            marched = True
+        else:
+            if rays_o is not None:
+                self.slots[self.cur].load(rays_o, rays_d, gt, bg_color, noises)
+            marched = False
         if lr is not None:
             self.opt_state[4:5].fill_(float(lr))
-        key = (shading == "full", has_alpha)
+        key = (shading == "full", self.slots[self.cur].has_alpha)
         if key != (bool(self.params.shading_full), bool(self.params.gt_has_alpha)):
             self._fill_params(*key)
-            self._graph = None
+
+        if next_batch is not None:
+            # side stream: stage + march the next batch into the other slot
+            nxt = 1 - self.cur
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.device)
+            side = self._side
+            if self._ev_done[nxt] is not None:
+                side.wait_event(self._ev_done[nxt])              # slot `nxt` was last read by the previous step
+            side.wait_stream(main)                               # (and after anything already queued on main, e.g. set_occupancy)
+            keep = self.cur
+            with torch.cuda.stream(side):
+                self.slots[nxt].load(*next_batch)
+                self.cur = nxt
+                self._run("march", self.march, use_graph)
+                self.cur = keep
+                ev = torch.cuda.Event(); ev.record(side)
+                self._ev_march[nxt] = ev
+            self._prefetched = nxt
+
+        if not marched:
+            self._run("march", self.march, use_graph)
         if grad_sync is None:
-            if not use_graph:
-                self._step_body()
-            else:
-                if self._graph is None:
-                    g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
-                        self._step_body()
-                    self._graph = g
-                self._graph.replay()
+            self._run("compute+adam", lambda: (self._compute(), self.adam()), use_graph)
+        elif getattr(grad_sync, "fused", False):
+            # data parallel, sharded optimizer fused with its collective over NVLink peer memory (parallel.PeerAdam)
+            self._run("compute", self._compute, use_graph)
+            p = self.parity
+            self._run("peer_adam", lambda: grad_sync.run(p), use_graph)
+            self.parity ^= 1
         else:
             # data parallel: [forward+backward] -> gradient all-reduce (NCCL) -> [optimizer]
-            if not use_graph:
-                self.forward_backward(); grad_sync(); self.adam()
-            else:
-                if self._graph is None:
-                    g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g1):
-                        self.forward_backward()
-                    with torch.cuda.graph(g2):
-                        self.adam()
-                    self._graph = (g1, g2)
-                self._graph[0].replay(); grad_sync(); self._graph[1].replay()
+            self._run("compute", self._compute, use_graph)
+            grad_sync()
+            self._run("adam", self.adam, use_graph)
+        ev = torch.cuda.Event(); ev.record(main)
+        self._ev_done[self.cur] = ev
         self.global_step += 1
+
+    # -------------------------------------------------------------------------------------------
+    # density grid / bitfield update and evaluation rendering
+    # -------------------------------------------------------------------------------------------
+    def update_density_grid(self, decay=0.95, density_thresh=10.0):
+        """NeRFRenderer.update_extra_state (renderer.py:1074-1149): evaluate the density field at one jittered
+        point per grid cell and cascade (hash gather + sigma_net on tensor cores), grid = max(grid * decay, sigma),
+        threshold = min(mean(clamp(grid, 0)), density_thresh), repack the bitfield.  Everything stays on the
+        device (the reference syncs for `mean_density.item()`)."""
+        c = self.cfg
+        H, cells = c.grid_size, c.grid_size ** 3
+        dev = self.device
+        if not hasattr(self, "_pts"):
+            self._pts = torch.zeros(self.Mcap, 3, device=dev)
+            self._pcount = torch.zeros(4, dtype=torch.int32, device=dev)
+            self._pparams = S0Params()
+        ctypes.memmove(ctypes.byref(self._pparams), ctypes.byref(self.params), ctypes.sizeof(S0Params))
+        self._pparams.shading_full = 0                       # sigma only: skip the specular rounds
+        pp = ctypes.byref(self._pparams)
+        for cas in range(c.cascade):
+            bound = float(min(2 ** cas, c.bound))
+            row = self.density_grid[cas]
+            for first in range(0, cells, self.Mcap):
+                cnt = min(self.Mcap, cells - first)
+                noise = torch.rand(cnt, 3, device=dev)
+                call("n2m_s0_grid_points", H, first, cnt, bound, ptr(noise), ptr(self._pts), stream())
+                self._pcount.fill_(cnt)
+                call("n2m_s0_encode_points", pp, ptr(self._pts), None, ptr(self._pcount), self.Mcap, ptr(self.table),
+                     ptr(self.offsets), ptr(self.enc_tiles), stream())
+                call("n2m_s0_mlp_fwd", pp, ptr(self.enc_tiles), ptr(self._pcount), self.Mcap, ptr(self.wpack), ptr(self.out),
+                     None, stream())
+                call("n2m_s0_grid_update", ptr(self.out), cnt, float(decay), row.data_ptr() + 4 * first, stream())
+        self.mean_density = self.density_grid.clamp(min=0).mean().reshape(1)
+        call("n2m_s0_packbits_dev", ptr(self.density_grid), self.density_bitfield.numel(), ptr(self.mean_density),
+             float(density_thresh), ptr(self.density_bitfield), stream())
+
+    @torch.no_grad()
+    def render(self, rays_o, rays_d, bg_color=1.0, shading="full"):
+        """Forward-only rendering of arbitrary many rays with the training kernels (march, gather, MLPs, composite),
+        in chunks of `num_rays`, no perturbation.  Returns (image [R,3], weights_sum [R], depth [R]) on the device."""
+        self.drop_prefetch()
+        R = rays_o.shape[0]
+        img = torch.empty(R, 3, device=self.device); ws = torch.empty(R, device=self.device); dep = torch.empty(R, device=self.device)
+        key = (shading == "full", False)
+        self._fill_params(*key)
+        slot = self.slots[self.cur]
+        zeros3 = torch.zeros(self.N, 3, device=self.device)
+        bg = torch.full((self.N, 3), float(bg_color), device=self.device) if not torch.is_tensor(bg_color) else None
+        for a in range(0, R, self.N):
+            b = min(R, a + self.N)
+            n = b - a
+            ro = torch.zeros(self.N, 3, device=self.device); rd = torch.ones(self.N, 3, device=self.device)
+            ro[:n] = rays_o[a:b]; rd[:n] = rays_d[a:b]
+            if n < self.N:
+                ro[n:] = 1e6            # padding rays miss the volume
+            slot.load(ro, rd, zeros3, bg if bg is not None else bg_color[a:b], torch.zeros(self.N, device=self.device))
+            self.loss_acc.zero_()
+            self.march(); self.encode_fwd(); self.mlp_fwd(); self.composite_loss()
+            img[a:b] = self.image[:n]; ws[a:b] = self.weights_sum[:n]; dep[a:b] = self.depth[:n]
+        return img, ws, dep
+
+    def drop_prefetch(self):
+        """Forget a batch staged by `next_batch=` (e.g. when the caller changes its batch sequence)."""
+        if self._side is not None:
+            self._side.synchronize()
+        self._prefetched = None
 
     def read_loss(self):
         """(host sync) loss of the last step as the reference reports it: rgb/mask part + specular regulariser."""

@@ -1,0 +1,68 @@
+"""GPU, >= 2 devices: the fused reduce-scatter + Adam + all-gather over NVLink peer memory (csrc/dp.cu,
+parallel.PeerAdam) against the library baseline (NCCL all-reduce + replicated Adam, parallel.GradSync):
+same parameters after several steps on every rank, ranks bit-identical among themselves."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, q):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root); sys.path.insert(0, os.path.join(root, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import cases
+    from nerf2mesh_b200 import synthetic as S
+    from nerf2mesh_b200.parallel import GradSync, PeerAdam
+    from nerf2mesh_b200.stage0 import Stage0Config, Stage0Trainer
+    N = 128
+    grid, bits, bricks = S.occupancy_regime("converged")
+    ro, rd = cases.rays(N, seed=10 + rank)                         # every rank its own rays
+    gt = S.render_bricks(ro, rd, bricks)
+    g = torch.Generator().manual_seed(rank)
+    bg = torch.rand(N, 3, generator=g); noises = torch.rand(N, generator=g)
+    out = {}
+    for mode in ("nccl", "peer"):
+        tr = Stage0Trainer(Stage0Config(bound=1.0, num_rays=N, max_samples=N * 256), seed=0)     # identical replicas
+        tr.set_occupancy(bits, grid)
+        sync = GradSync(tr) if mode == "nccl" else PeerAdam(tr)
+        for it in range(4):
+            tr.step(ro, rd, gt, bg, noises, grad_sync=sync, use_graph=(it > 0))
+        torch.cuda.synchronize()
+        st = tr.export_reference_state()
+        if mode == "peer":
+            st["encoder_color.embeddings"] = sync.gather_color_master()
+        out[mode] = {k: v.cpu() for k, v in st.items() if "density" not in k}
+        out[mode + "_loss"] = tr.read_loss()
+        dist.barrier()
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_peer_adam_matches_nccl_allreduce_world2():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = dict(q.get(timeout=600) for _ in range(2))
+    [p.join(120) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    for name in res[0]["peer"]:
+        a0, a1 = res[0]["peer"][name], res[1]["peer"][name]
+        assert torch.equal(a0, a1), f"ranks diverged on {name}"
+        b0 = res[0]["nccl"][name]
+        d = (a0 - b0).abs().max().item()
+        moved = (b0 - b0.mean()).abs().max().item()
+        assert d <= 2e-3 * max(moved, 1e-6) + 1e-7, f"{name}: peer vs nccl differ by {d}"
+    assert abs(res[0]["peer_loss"] - res[0]["nccl_loss"]) <= 1e-3 * abs(res[0]["nccl_loss"])

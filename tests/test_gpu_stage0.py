@@ -213,3 +213,28 @@ def test_warp_marcher_equals_serial_marcher(name):
     assert torch.equal(r0, r1)
     M = int(c0[1].item())
     assert torch.equal(s0[:M], s1[:M])
+
+
+def test_pipelined_mlp_backward_equals_single_tile_kernel():
+    """k_mlp_bwd2 (two tiles in flight, issuer warp, aliased smem) vs k_mlp_bwd: same feature gradients
+    bit for bit; weight gradients equal up to the order of the fp32 TMEM/atomic accumulation."""
+    from nerf2mesh_b200._lib import call
+    for shading in ("full", "diffuse"):
+        tr, b = make(shading, N=192)
+        stage(tr, b)
+        tr._fill_params(shading == "full", True)
+        tr.loss_acc.zero_(); tr.march(); tr.encode_fwd(); tr.mlp_fwd(); tr.composite_loss()
+        res = []
+        for mode in (0, 1):
+            call("n2m_s0_set_mlp_bwd_pipelined", mode)
+            tr.g_mlp.zero_(); tr.denc_tiles.zero_()
+            tr.mlp_bwd()
+            torch.cuda.synchronize()
+            res.append((tr.denc_tiles.clone(), tr.g_mlp.clone()))
+        call("n2m_s0_set_mlp_bwd_pipelined", 1)
+        M = int(tr.counters[1].item())
+        d0, d1 = untile(res[0][0], M), untile(res[1][0], M)
+        assert torch.equal(d0, d1), (d0 - d1).abs().max()
+        assert d0.abs().max() > 0
+        g0, g1 = res[0][1], res[1][1]
+        assert (g0 - g1).abs().max().item() <= 1e-4 * g0.abs().max().item()
