@@ -68,8 +68,12 @@ int n2m_s0_init(void);
 /* test hook: 1 = sequential one-thread-per-ray marcher, 0 = warp-per-ray marcher (default); same results */
 int n2m_s0_set_serial_march(int on);
 
-/* tuning hook: 1 = TV gradient in the forward gather kernel, 0 = in the backward scatter kernel (default) */
-int n2m_s0_set_tv_in_fwd(int on);
+/* tuning hook: where the TV gradient is evaluated: 0 = backward scatter kernel, 1 = forward gather kernel, 2 = own launch */
+int n2m_s0_set_tv_mode(int mode);
+/* the stand-alone TV launch (tv mode 2): reads recs/table, adds into gtable; independent of the MLP kernels */
+int n2m_s0_tv(const n2m_s0_params* p, const void* recs, const int32_t* counters, uint32_t Mcap, const float* rays_o,
+              const float* rays_d, const void* table, const int32_t* offsets, void* gtable, const float* loss_scale,
+              n2m_stream_t stream);
 
 /* test hook: MLP backward variant, 1 = two tiles in flight + issuer warp (default), 0 = one tile per CTA */
 int n2m_s0_set_mlp_bwd_pipelined(int on);
@@ -166,7 +170,7 @@ int n2m_dp_ctx_fill(void* host_ctx, uint32_t world, uint32_t rank, uint32_t rows
                     void* const* opt, void* const* flags, void* epoch);
 int n2m_dp_barrier(const void* ctx, n2m_stream_t stream);
 /* barrier -> reduce-scatter + Adam + all-gather on this rank's row slice -> MLP -> zero next-parity grads -> barrier.
- * color_master / m / v are slice-sized: ceil(rows / world) rows. */
+ * color_master / m / v are slice-sized: ceil(rows / world) rounded up to a multiple of 4 rows. */
 int n2m_dp_adam(const void* ctx, uint32_t parity, uint32_t world, uint32_t rows, uint32_t n_mlp, void* color_master_slice,
                 float* m_slice, float* v_slice, float* mlp_params, float* m_mlp, float* v_mlp, void* wpack,
                 void* gtab_next, float* gmlp_next, float* opt_state, float eps, n2m_stream_t stream);

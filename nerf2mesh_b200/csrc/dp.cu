@@ -89,14 +89,20 @@ __global__ void k_dp_prep(const DpCtx* __restrict__ ctx, uint32_t parity, float*
 
 constexpr int kRowsPerThread = 2;
 
+// rows owned by one rank: ceil(rows / world) rounded up to a multiple of 4, so that the float2 colour moments that
+// follow the `per` density moments in the slice-sized m / v arrays stay 8-byte aligned (764983 rows at world 8 is odd)
+__host__ __device__ __forceinline__ uint32_t slice_rows(uint32_t rows, uint32_t world) {
+    return ((rows + world - 1) / world + 3u) & ~3u;
+}
+
 // reduce-scatter + Adam + all-gather on this rank's row slice; also zeroes the local gradient table of the
 // other parity (the one the next step's backward accumulates into).
 __global__ void __launch_bounds__(256)
 k_dp_adam_tables(const DpCtx* __restrict__ ctx, uint32_t parity, float2* __restrict__ cmaster, float* __restrict__ m,
                  float* __restrict__ v, const float* __restrict__ st, float eps) {
     const uint32_t W = ctx->world, r = ctx->rank, rows = ctx->rows;
-    const uint32_t per = (rows + W - 1) / W;
-    const uint32_t lo = r * per, hi = min(rows, lo + per);
+    const uint32_t per = slice_rows(rows, W);
+    const uint32_t lo = min(rows, r * per), hi = min(rows, lo + per);
     const bool skip = st[3] != 0.f;
     const float inv = st[7];
     const float lr1 = __fdiv_rn(st[4], st[5]), bc2s = st[6];
@@ -263,7 +269,7 @@ int n2m_dp_adam(const void* ctx, uint32_t parity, uint32_t world, uint32_t rows,
     if (int e = check_launch("dp_adam(barrier A)")) return e;
     k_dp_prep<<<1, 32, 0, st>>>(c, parity, opt_state);
     if (int e = check_launch("dp_adam(prep)")) return e;
-    const uint32_t per = (rows + world - 1) / world;
+    const uint32_t per = slice_rows(rows, world);
     k_dp_adam_tables<<<div_up(per, 256u * kRowsPerThread), 256, 0, st>>>(c, parity, static_cast<float2*>(color_master_slice), m_slice, v_slice,
                                                                        opt_state, eps);
     if (int e = check_launch("dp_adam(tables)")) return e;

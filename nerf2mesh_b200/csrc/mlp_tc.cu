@@ -95,36 +95,45 @@ __device__ __forceinline__ void sync_before_mma() {
 
 // accumulator row (NCOL fp32 columns of this thread's TMEM lane) -> optional ReLU / mask -> fp16 row of a
 // 128-row chunk-major tile.  mask_tile != nullptr: zero where the fp16 activation stored there is <= 0.
+// Latency-tuned: all TMEM loads of the row are issued before one wait, ReLU and the mask are applied on packed
+// half2 values (HMNMX2 / HSETP-free multiply by __hgt2), half the instructions of the fp32 formulation and
+// bit-identical results (rounding to fp16 commutes with max(.,0) and with zeroing).
 template <int NCOL, bool RELU>
 __device__ __forceinline__ void epi_store_row(uint32_t taddr, uint8_t* tile, uint32_t r, const uint8_t* mask_tile) {
+    static_assert(NCOL == 32 || NCOL == 64, "row width");
+    uint32_t raw[NCOL];
+    {
+        uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&raw[0]);
+        tc::tmem_ld32(taddr, lo);
+        if (NCOL == 64) {
+            uint32_t (&hi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&raw[NCOL == 64 ? 32 : 0]);
+            tc::tmem_ld32(taddr + 32, hi);
+        }
+    }
+    uint4 msk[NCOL / 8];
+    if (mask_tile) {
 #pragma unroll
-    for (int c0 = 0; c0 < NCOL; c0 += 16) {
-        float v[16];
-        tc::tmem_ld16(taddr + c0, v);
-        if (RELU) {
+        for (int ch = 0; ch < NCOL / 8; ++ch) msk[ch] = *reinterpret_cast<const uint4*>(mask_tile + ch * kChunk + r * 16);
+    }
+    tc::tmem_ld_wait();
+    const __half2 zero2 = __float2half2_rn(0.f);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+    for (int ch = 0; ch < NCOL / 8; ++ch) {
+        __half2 h[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            h[i] = __floats2half2_rn(__uint_as_float(raw[8 * ch + 2 * i]), __uint_as_float(raw[8 * ch + 2 * i + 1]));
+            if (RELU) h[i] = __hmax2(h[i], zero2);
         }
         if (mask_tile) {
+            const uint32_t mm[4] = {msk[ch].x, msk[ch].y, msk[ch].z, msk[ch].w};
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const uint4 m = *reinterpret_cast<const uint4*>(mask_tile + (c0 / 8 + q) * kChunk + r * 16);
-                const uint32_t mm[4] = {m.x, m.y, m.z, m.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&mm[i]));
-                    if (!(f.x > 0.f)) v[8 * q + 2 * i] = 0.f;
-                    if (!(f.y > 0.f)) v[8 * q + 2 * i + 1] = 0.f;
-                }
-            }
+            for (int i = 0; i < 4; ++i) h[i] = __hmul2(h[i], __hgt2(*reinterpret_cast<const __half2*>(&mm[i]), zero2));
         }
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            uint4 o;
-            o.x = pack2(v[8 * q + 0], v[8 * q + 1]); o.y = pack2(v[8 * q + 2], v[8 * q + 3]);
-            o.z = pack2(v[8 * q + 4], v[8 * q + 5]); o.w = pack2(v[8 * q + 6], v[8 * q + 7]);
-            *reinterpret_cast<uint4*>(tile + (c0 / 8 + q) * kChunk + r * 16) = o;
-        }
+        uint4 o;
+        o.x = *reinterpret_cast<uint32_t*>(&h[0]); o.y = *reinterpret_cast<uint32_t*>(&h[1]);
+        o.z = *reinterpret_cast<uint32_t*>(&h[2]); o.w = *reinterpret_cast<uint32_t*>(&h[3]);
+        *reinterpret_cast<uint4*>(tile + ch * kChunk + r * 16) = o;
     }
 }
 
@@ -570,7 +579,7 @@ k_mlp_bwd(n2m_s0_params p, const uint8_t* __restrict__ enc_tiles, const float4* 
 // ================================================================================================
 // The single-tile kernel above is a chain of ten dependent [MMA -> commit -> wait -> TMEM load -> epilogue ->
 // smem store -> fence -> barrier] rounds per tile, and TMEM (368 of 512 columns) allows only one such CTA per
-// SM, so the tensor pipe idles during every epilogue and vice versa (profiles/r1_notes.md: 6 % issue
+// SM, so the tensor pipe idles during every epilogue and vice versa (profiles/r1_ncu_summary.md: 6 % issue
 // utilisation).  Here warps 0-3 and 4-7 each own one tile (same thread-per-sample epilogues), warp 8 issues all
 // tcgen05.mma for both: while one group runs an epilogue the other group's GEMMs execute.  The weight-gradient
 // accumulators are shared by both groups (one issuing thread => one program order), working columns are
@@ -596,6 +605,11 @@ __device__ __forceinline__ void group_wait(uint64_t* bar, uint32_t& ph) {
     tc::mbar_wait(bar, ph); ph ^= 1;
     tc::fence_after_sync();
 }
+
+// optional phase profiler (n2m_s0_set_prof): block 0 stamps clock64() at every hand-over of its first tile --
+// slots 0..31 tile group 0 (thread 0), 32..63 the issuer's view of group 0, 64..95 tile group 1.  Null => off.
+__device__ unsigned long long* g_prof = nullptr;
+#define PROF_STAMP() do { if (pf) { pf[ps++] = (unsigned long long)clock64(); } } while (0)
 
 __global__ void __launch_bounds__(288)
 k_mlp_bwd2(n2m_s0_params p, const uint8_t* __restrict__ enc_tiles, const float4* __restrict__ dout,
@@ -671,17 +685,31 @@ k_mlp_bwd2(n2m_s0_params p, const uint8_t* __restrict__ enc_tiles, const float4*
                 gd[g].Zm = tc::make_opdesc(opMN(sZ, 128));
                 gd[g].dOsm = tc::make_opdesc(opMN(sDY, 128)); gd[g].dO2m = tc::make_opdesc(opMN(sDY + 2 * kChunk, 128));
             }
-            const uint32_t n_it = max(n_g[0], n_g[1]);
-            for (uint32_t it = 0; it < n_it; ++it) {
-                for (int round = 0; round < 10; ++round) {
-                    if (!full && (round == 3 || round == 4)) continue;
+            // The issuer serves whichever group has handed over its operands: the two tiles drift apart by about half a
+            // round, so one group's GEMMs execute under the other group's epilogue (a fixed g0,g1,g0,... order would keep
+            // both groups in lockstep: both in their epilogues, then both waiting on the tensor pipe).
+            unsigned long long* pf0 = blockIdx.x == 0 ? g_prof : nullptr;
+            if (pf0) pf0 += 32;
+            uint32_t ps = 0;
+            uint32_t rd[2] = {0, 0}, itg[2] = {0, 0};
+            bool act[2] = {n_g[0] > 0, n_g[1] > 0};
+            uint32_t spins = 0;
+            while (act[0] || act[1]) {
 #pragma unroll
                     for (int g = 0; g < 2; ++g) {
-                        if (it >= n_g[g]) continue;
+                        if (!act[g]) continue;
+                        if (!tc::mbar_test_wait(&bar_ready[g], ph_ready[g])) {
+                            if (++spins > (1u << 28)) __trap();
+                            continue;
+                        }
+                        spins = 0;
+                        ph_ready[g] ^= 1;
+                        tc::fence_after_sync();
+                        const int round = (int)rd[g];
                         const GroupDesc& q = gd[g];
                         const uint32_t K0 = tmem + g * 128, K1 = K0 + 64;
-                        tc::mbar_wait(&bar_ready[g], ph_ready[g]); ph_ready[g] ^= 1;
-                        tc::fence_after_sync();
+                        unsigned long long* pf = (itg[g] == 0 && g == 0) ? pf0 : nullptr;
+                        PROF_STAMP();
                         switch (round) {
                             case 0:   // R1: first layers
                                 tc::gemm_issue_fast<64, 4, false, false>(K0, q.A, wC1k, false);
@@ -730,8 +758,11 @@ k_mlp_bwd2(n2m_s0_params p, const uint8_t* __restrict__ enc_tiles, const float4*
                                 break;
                         }
                         tc::mma_commit(&bar_done[g]);
+                        PROF_STAMP();
+                        ++rd[g];
+                        if (!full && rd[g] == 3) rd[g] = 5;             // no specular rounds in 'diffuse' shading
+                        if (rd[g] == 10) { rd[g] = 0; if (++itg[g] == n_g[g]) act[g] = false; }
                     }
-                }
             }
         }
     } else {
@@ -748,24 +779,29 @@ k_mlp_bwd2(n2m_s0_params p, const uint8_t* __restrict__ enc_tiles, const float4*
         const float ls = loss_scale[0];
         const float spec_reg = (M > 0) ? 2.0f * p.lambda_specular / (float)M * ls : 0.f;
 
+        unsigned long long* pfb = (blockIdx.x == 0 && tg == 0 && g_prof) ? g_prof + g * 64 : nullptr;
+        uint32_t ps = 0;
         for (uint32_t tile = blockIdx.x * 2 + g; tile < ntiles; tile += 2 * gridDim.x) {
+            unsigned long long* pf = (tile == blockIdx.x * 2 + g) ? pfb : nullptr;
+            PROF_STAMP();
             if (tg == 0) bulk_g2s(sA, enc_tiles + (size_t)tile * kTileBytes, kTileBytes, &bar_tma[g]);
             const uint32_t j = tile * kTile + tg;
             float4 dv = make_float4(0.f, 0.f, 0.f, 0.f);
             if (j < M) dv = dout[j];
             tc::mbar_wait(&bar_tma[g], ph_tma); ph_tma ^= 1;
-            group_ready(&bar_ready[g], g, tg);                                   // R1 may start
+            PROF_STAMP();
+            PROF_STAMP(); group_ready(&bar_ready[g], g, tg);                                   // R1 may start
             // ---- forward recompute ----
-            group_wait(&bar_done[g], ph_done);
+            group_wait(&bar_done[g], ph_done); PROF_STAMP();
             epi_store_row<64, true>(K0, sH1, tg, nullptr);
             epi_store_row<32, true>(K1, sS1, tg, nullptr);
-            group_ready(&bar_ready[g], g, tg);
-            group_wait(&bar_done[g], ph_done);
+            PROF_STAMP(); group_ready(&bar_ready[g], g, tg);
+            group_wait(&bar_done[g], ph_done); PROF_STAMP();
             float h_sig;
             { float v[8]; tc::tmem_ld8(K1, v); h_sig = round_h(v[0]); }
             epi_store_row<64, true>(K0, sH2, tg, nullptr);
-            group_ready(&bar_ready[g], g, tg);
-            group_wait(&bar_done[g], ph_done);
+            PROF_STAMP(); group_ready(&bar_ready[g], g, tg);
+            group_wait(&bar_done[g], ph_done); PROF_STAMP();
             float feat[6];
             { float v[8]; tc::tmem_ld8(K0, v);
 #pragma unroll
@@ -777,11 +813,11 @@ k_mlp_bwd2(n2m_s0_params p, const uint8_t* __restrict__ enc_tiles, const float4*
                 const __half2 d23 = *reinterpret_cast<const __half2*>(&dq.z);
                 const float in[8] = {__high2float(d01), __low2float(d23), __high2float(d23), feat[3], feat[4], feat[5], 0.f, 0.f};
                 store_chunk(sAs2, 0, tg, in);
-                group_ready(&bar_ready[g], g, tg);
-                group_wait(&bar_done[g], ph_done);
+                PROF_STAMP(); group_ready(&bar_ready[g], g, tg);
+                group_wait(&bar_done[g], ph_done); PROF_STAMP();
                 epi_store_row<32, true>(K1, sP1, tg, nullptr);
-                group_ready(&bar_ready[g], g, tg);
-                group_wait(&bar_done[g], ph_done);
+                PROF_STAMP(); group_ready(&bar_ready[g], g, tg);
+                group_wait(&bar_done[g], ph_done); PROF_STAMP();
                 float v[8];
                 tc::tmem_ld8(K0, v);
 #pragma unroll
@@ -808,14 +844,14 @@ k_mlp_bwd2(n2m_s0_params p, const uint8_t* __restrict__ enc_tiles, const float4*
                 store_chunk(sdOs, 0, tg, dOs);
                 if (full) store_chunk(sdO2, 0, tg, dO2);
             }
-            group_ready(&bar_ready[g], g, tg);
+            PROF_STAMP(); group_ready(&bar_ready[g], g, tg);
             // ---- B1 ----
-            group_wait(&bar_done[g], ph_done);
+            group_wait(&bar_done[g], ph_done); PROF_STAMP();
             epi_store_row<32, false>(K0, sS1, tg, sS1);                   // dS1 written over S1 (own row: read mask, then write)
             if (full) epi_store_row<32, false>(K1, sP1, tg, sP1);
-            group_ready(&bar_ready[g], g, tg);
+            PROF_STAMP(); group_ready(&bar_ready[g], g, tg);
             // ---- B2 ----
-            group_wait(&bar_done[g], ph_done);
+            group_wait(&bar_done[g], ph_done); PROF_STAMP();
             {
                 if (full) {
                     float v[8];
@@ -827,17 +863,17 @@ k_mlp_bwd2(n2m_s0_params p, const uint8_t* __restrict__ enc_tiles, const float4*
                 for (int i = 0; i < 6; ++i) dO[i] = dfeat[i] * feat[i] * (1.0f - feat[i]);
                 store_chunk(sdO, 0, tg, dO);
             }
-            group_ready(&bar_ready[g], g, tg);
+            PROF_STAMP(); group_ready(&bar_ready[g], g, tg);
             // ---- B3 ----
-            group_wait(&bar_done[g], ph_done);
+            group_wait(&bar_done[g], ph_done); PROF_STAMP();
             epi_store_row<64, false>(K1, sZ, tg, sH2);
-            group_ready(&bar_ready[g], g, tg);
+            PROF_STAMP(); group_ready(&bar_ready[g], g, tg);
             // ---- B4 ----
-            group_wait(&bar_done[g], ph_done);
+            group_wait(&bar_done[g], ph_done); PROF_STAMP();
             epi_store_row<64, false>(K1, sZ, tg, sH1);
-            group_ready(&bar_ready[g], g, tg);
+            PROF_STAMP(); group_ready(&bar_ready[g], g, tg);
             // ---- B5 ----
-            group_wait(&bar_done[g], ph_done);
+            group_wait(&bar_done[g], ph_done); PROF_STAMP();
             {
                 uint8_t* img = denc_tiles + (size_t)tile * kTileBytes + tg * 16;
 #pragma unroll
@@ -853,6 +889,7 @@ k_mlp_bwd2(n2m_s0_params p, const uint8_t* __restrict__ enc_tiles, const float4*
                     }
                 }
             }
+            PROF_STAMP();
             // the group's smem / TMEM working columns are free again: the next tile's bulk copy and R1 may proceed
             // (every MMA of this tile has completed, all TMEM loads above have been waited for)
         }
@@ -928,6 +965,15 @@ k_mlp_bwd2(n2m_s0_params p, const uint8_t* __restrict__ enc_tiles, const float4*
 using namespace n2m;
 
 extern "C" {
+
+/* debug: device buffer of >= 128 uint64 that block 0 of the pipelined MLP backward stamps with clock64(); NULL = off */
+int n2m_s0_set_prof(void* buf) {
+    unsigned long long* b = static_cast<unsigned long long*>(buf);
+    cudaError_t e = cudaMemcpyToSymbol(g_prof, &b, sizeof(b));
+    if (e != cudaSuccess) return fail("s0_set_prof", cudaGetErrorString(e));
+    return 0;
+}
+
 
 uint32_t n2m_s0_wpack_bytes(void) { return W_BYTES; }
 uint32_t n2m_s0_mlp_param_count(void) { return P_COUNT; }

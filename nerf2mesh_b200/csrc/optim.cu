@@ -50,7 +50,7 @@ __device__ __forceinline__ float adam_update(float p, float g, float& m, float& 
 // fp16 copy in the table)}.  m/v: [rows] density then [rows][2] colour.  Pure streaming (112 B/row, ~0.7 GB per
 // step): each thread handles kRowsPerThread rows, block-strided so every access stays coalesced, and issues ALL
 // of its loads before the first dependent instruction -- with one row per thread the kernel was latency bound
-// at 1.6 TB/s (profiles/r1_notes.md).
+// at 1.6 TB/s (profiles/r1_ncu_summary.md).
 constexpr int kRowsPerThread = 4;
 
 __global__ void __launch_bounds__(256)

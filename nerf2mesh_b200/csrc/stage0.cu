@@ -446,12 +446,12 @@ k_s0_encode_fwd(n2m_s0_params p, const float4* __restrict__ recs, const int32_t*
 
 // ------------------------------------------------------------------------------------------------
 // encode backward: scatter the (loss-scaled, fp16) feature gradients (the TV gradient is added by the forward kernel).
-// L2 atomic throughput bounds this kernel (profiles/r1_notes.md), so at the coarse levels -- where the
+// L2 atomic throughput bounds this kernel (profiles/r1_ncu_summary.md), so at the coarse levels -- where the
 // consecutive samples of a ray (= consecutive lanes) sit in the same lattice cell -- the 8 corner
 // contributions are first summed across each run of same-cell lanes with a segmented warp scan and only the
 // last lane of a run issues the red.global.add.v4.f32.  Fine levels (every lane its own cell) go straight to the atomics.
 // ------------------------------------------------------------------------------------------------
-template <bool TV>
+template <bool SCATTER, bool TV>
 __global__ void __launch_bounds__(kTile)
 k_s0_encode_bwd(n2m_s0_params p, const float4* __restrict__ recs, const int32_t* __restrict__ counters,
                 const float* __restrict__ rays_o, const float* __restrict__ rays_d,
@@ -477,7 +477,7 @@ k_s0_encode_bwd(n2m_s0_params p, const float4* __restrict__ recs, const int32_t*
 #pragma unroll
     for (uint32_t ch = 0; ch < 7; ++ch) {
         uint4 q = make_uint4(0, 0, 0, 0);
-        if (active) q = *reinterpret_cast<const uint4*>(img + ch * kChunkBytes);
+        if (SCATTER && active) q = *reinterpret_cast<const uint4*>(img + ch * kChunkBytes);
         const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -489,7 +489,7 @@ k_s0_encode_bwd(n2m_s0_params p, const float4* __restrict__ recs, const int32_t*
         bool bad = false;
 #pragma unroll
         for (int i = (int)kColDens; i < (int)kColDir; ++i) bad |= !isfinite(g[i]);
-        if (bad) loss_scale[3] = 1.f;
+        if (SCATTER && bad) loss_scale[3] = 1.f;
     }
     // TV weight: lambda inside the unit cube, 10 lambda outside when bound > 1 (utils.py:815-821); w = weight / (2 D),
     // kept in the loss-scaled domain
@@ -515,18 +515,20 @@ k_s0_encode_bwd(n2m_s0_params p, const float4* __restrict__ recs, const int32_t*
         const uint32_t key = active ? (base[0] | (base[1] << 10) | (base[2] << 20)) : 0xffffffffu;
         const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
         const uint32_t heads = __ballot_sync(0xffffffffu, lane == 0 || key != prev);
-        const bool merge = lg.res < 1023u && __popc(heads) <= 20;
+        const bool merge = lg.res < 1023u && (SCATTER ? __popc(heads) <= 20 : heads != 0xffffffffu);
         bool issue = active;
         if (merge) {
             const uint32_t run_start = 31u - __clz(heads & (0xffffffffu >> (31u - lane)));
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const bool take = lane >= run_start + (uint32_t)o;
+                if (SCATTER) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const float a = __shfl_up_sync(0xffffffffu, vd[k], o), b = __shfl_up_sync(0xffffffffu, v0[k], o),
-                                cc = __shfl_up_sync(0xffffffffu, v1[k], o);
-                    if (take) { vd[k] += a; v0[k] += b; v1[k] += cc; }
+                    for (int k = 0; k < 8; ++k) {
+                        const float a = __shfl_up_sync(0xffffffffu, vd[k], o), b = __shfl_up_sync(0xffffffffu, v0[k], o),
+                                    cc = __shfl_up_sync(0xffffffffu, v1[k], o);
+                        if (take) { vd[k] += a; v0[k] += b; v1[k] += cc; }
+                    }
                 }
                 if (TV) {
                     const float t = __shfl_up_sync(0xffffffffu, tvw, o);
@@ -537,8 +539,10 @@ k_s0_encode_bwd(n2m_s0_params p, const float4* __restrict__ recs, const int32_t*
             issue = active && tail;
         }
         if (issue) {
+            if (SCATTER) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) atomicAdd(gt + c.row[k], make_float4(vd[k], v0[k], v1[k], 0.f));
+                for (int k = 0; k < 8; ++k) atomicAdd(gt + c.row[k], make_float4(vd[k], v0[k], v1[k], 0.f));
+            }
             if (TV) {        // gridencoder.cu:506-609 on the density feature: centre, +1 neighbours = corners 1,2,4, -1 = left[]
                 const TableEntry* tab = table + lg.row0;
                 const int right_corner[3] = {1, 2, 4};
@@ -773,14 +777,15 @@ k_s0_unpack_grads(const float4* __restrict__ gtable, uint32_t rows, const float*
 using namespace n2m;
 
 static bool g_serial_march = false;
-static bool g_tv_in_fwd = false;     // where the TV gradient is evaluated (measured: cheaper in the scatter kernel)
+static int g_tv_mode = 0;            // TV gradient: 0 = inside the scatter kernel, 1 = inside the gather kernel, 2 = own launch (n2m_s0_tv)
 
 extern "C" {
 
 /* test hook: 1 = one-thread-per-ray sequential marcher (the reference's structure), 0 = warp-per-ray (default) */
 int n2m_s0_set_serial_march(int on) { g_serial_march = on != 0; return 0; }
-/* test / tuning hook: 1 = TV gradient evaluated by the forward gather kernel, 0 = by the backward scatter kernel (default) */
-int n2m_s0_set_tv_in_fwd(int on) { g_tv_in_fwd = on != 0; return 0; }
+/* tuning hook: TV gradient evaluated 0 = by the backward scatter kernel, 1 = by the forward gather kernel, 2 = by its own
+ * launch n2m_s0_tv (which the host overlaps with the tensor-core MLP kernels on a forked stream) */
+int n2m_s0_set_tv_mode(int mode) { g_tv_mode = mode; return 0; }
 
 int n2m_s0_pack_tables(const float* emb_density, const float* emb_color, uint32_t rows, void* table, void* color_master,
                        n2m_stream_t stream) {
@@ -834,7 +839,7 @@ int n2m_s0_encode_fwd(const n2m_s0_params* p, const void* recs, const int32_t* c
     N2M_REQUIRE(!gtable || loss_scale, "s0_encode_fwd", "gtable given but loss_scale null");
     N2M_REQUIRE(p->num_levels == kLevels, "s0_encode_fwd", "fused path supports num_levels == 16");
     N2M_REQUIRE(Mcap % kTile == 0 && Mcap > 0, "s0_encode_fwd", "Mcap must be a positive multiple of 128");
-    if (g_tv_in_fwd && gtable && p->lambda_tv > 0)
+    if (g_tv_mode == 1 && gtable && p->lambda_tv > 0)
         k_s0_encode_fwd<false, true><<<Mcap / kTile, kTile, 0, as_stream(stream)>>>(*p, static_cast<const float4*>(recs), counters, rays_o, rays_d,
                                                                                    static_cast<const TableEntry*>(table), offsets,
                                                                                    static_cast<uint8_t*>(enc_tiles), static_cast<float4*>(gtable), loss_scale);
@@ -886,18 +891,26 @@ int n2m_s0_encode_bwd(const n2m_s0_params* p, const void* recs, const int32_t* c
                 "s0_encode_bwd", "null pointer");
     N2M_REQUIRE(p->num_levels == kLevels, "s0_encode_bwd", "fused path supports num_levels == 16");
     N2M_REQUIRE(Mcap % kTile == 0 && Mcap > 0, "s0_encode_bwd", "Mcap must be a positive multiple of 128");
-    // the TV gradient is added here unless the forward kernel was asked to do it (g_tv_in_fwd)
-    if (p->lambda_tv > 0 && !g_tv_in_fwd)
-        k_s0_encode_bwd<true><<<Mcap / kTile, kTile, 0, as_stream(stream)>>>(*p, static_cast<const float4*>(recs), counters, rays_o, rays_d,
-                                                                             static_cast<const uint8_t*>(denc_tiles),
-                                                                             static_cast<const TableEntry*>(table), offsets,
-                                                                             static_cast<float4*>(gtable), const_cast<float*>(loss_scale));
+    // the TV gradient is added here unless the forward kernel or the stand-alone TV launch does it (g_tv_mode)
+#define N2M_BWD_ARGS *p, static_cast<const float4*>(recs), counters, rays_o, rays_d, static_cast<const uint8_t*>(denc_tiles), \
+                     static_cast<const TableEntry*>(table), offsets, static_cast<float4*>(gtable), const_cast<float*>(loss_scale)
+    if (p->lambda_tv > 0 && g_tv_mode == 0)
+        k_s0_encode_bwd<true, true><<<Mcap / kTile, kTile, 0, as_stream(stream)>>>(N2M_BWD_ARGS);
     else
-        k_s0_encode_bwd<false><<<Mcap / kTile, kTile, 0, as_stream(stream)>>>(*p, static_cast<const float4*>(recs), counters, rays_o, rays_d,
-                                                                              static_cast<const uint8_t*>(denc_tiles),
-                                                                              static_cast<const TableEntry*>(table), offsets,
-                                                                              static_cast<float4*>(gtable), const_cast<float*>(loss_scale));
+        k_s0_encode_bwd<true, false><<<Mcap / kTile, kTile, 0, as_stream(stream)>>>(N2M_BWD_ARGS);
     return check_launch("s0_encode_bwd");
+}
+
+/* stand-alone TV-gradient launch (same arithmetic as inside the scatter kernel); only meaningful with tv mode 2 */
+int n2m_s0_tv(const n2m_s0_params* p, const void* recs, const int32_t* counters, uint32_t Mcap, const float* rays_o,
+              const float* rays_d, const void* table, const int32_t* offsets, void* gtable, const float* loss_scale,
+              n2m_stream_t stream) {
+    N2M_REQUIRE(p && recs && counters && rays_o && rays_d && table && offsets && gtable && loss_scale, "s0_tv", "null pointer");
+    N2M_REQUIRE(Mcap % kTile == 0 && Mcap > 0, "s0_tv", "Mcap must be a positive multiple of 128");
+    if (!(p->lambda_tv > 0)) return 0;
+    const void* denc_tiles = nullptr;
+    k_s0_encode_bwd<false, true><<<Mcap / kTile, kTile, 0, as_stream(stream)>>>(N2M_BWD_ARGS);
+    return check_launch("s0_tv");
 }
 
 int n2m_s0_composite_loss(const n2m_s0_params* p, const void* out, const void* recs, const int32_t* rays,

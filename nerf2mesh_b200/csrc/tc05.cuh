@@ -90,6 +90,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
+// non-blocking probe (try_wait may suspend the thread for a hardware-defined time; a poller of several barriers must not)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
 // bounded wait: a protocol bug traps (launch error) instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
@@ -120,6 +130,18 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 32 columns in one instruction (one wait instead of two): the epilogues are latency bound on LDTM round trips
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // ---- helpers for issuing a whole GEMM over K ------------------------------------------------------
 // A tile: rows_a rows (chunk-major), B tile: rows_b rows.  K-major operand: M/N = rows, K = cols.
 // MN-major operand: M/N = cols, K = rows.  k_total multiple of 16.
@@ -145,7 +167,7 @@ __device__ __forceinline__ void gemm_issue(uint32_t d_tmem, const Operand& a, co
 
 // ---- cheap issue path ------------------------------------------------------------------------------
 // A single thread issues every tcgen05.mma of a CTA, so descriptor arithmetic is on the critical path
-// (profiles/r1_notes.md: ~125 cycles per MMA with smem_desc() rebuilt each time).  The descriptor of k-step
+// (profiles/r1_ncu_summary.md: ~125 cycles per MMA with smem_desc() rebuilt each time).  The descriptor of k-step
 // `s` differs from that of k-step 0 only in the 14-bit start-address field (low word), by a constant:
 //   K-major : 16 k = 2 chunks          -> += 2 * chunk_bytes / 16 = rows * 2
 //   MN-major: 16 k = 2 groups of 8 rows -> += 256 / 16 = 16

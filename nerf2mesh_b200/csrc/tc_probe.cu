@@ -64,33 +64,37 @@ template <uint32_t N, uint32_t KSTEPS, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(128)
 k_tc_bench(uint32_t reps, int mode, unsigned long long* __restrict__ out) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bar[2];
     __shared__ uint32_t tmem_base_s;
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
-    if (tid == 0) { tc::mbar_init(&bar, 1); tc::mbar_init_fence(); }
-    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 64);
+    if (tid == 0) { tc::mbar_init(&bar[0], 1); tc::mbar_init(&bar[1], 1); tc::mbar_init_fence(); }
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 128);
     for (uint32_t i = tid; i < 49152 / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     tc::fence_async_smem(); tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = tmem_base_s;
-    if (tid == 0) {
+    // mode 2: threads 0 and 32 (two warps) issue concurrently into disjoint TMEM columns -- is the 59-cycle
+    // pace per issuing thread or per SM?
+    const bool issuer = tid == 0 || (mode == 2 && tid == 32);
+    if (issuer) {
+        const uint32_t w = tid >> 5;
         const tc::OpDesc a = tc::make_opdesc(tc::Operand{tc::smem_u32(smem), 128, A_MN});
         const tc::OpDesc b = tc::make_opdesc(tc::Operand{tc::smem_u32(smem + 32768), B_MN ? 128u : N, B_MN});
         uint32_t ph = 0;
         const long long t0 = clock64();
         for (uint32_t r = 0; r < reps; ++r) {
-            tc::gemm_issue_fast<N, KSTEPS, A_MN, B_MN>(tmem, a, b, r > 0);
-            if (mode == 1) { tc::mma_commit(&bar); tc::mbar_wait(&bar, ph); ph ^= 1; }
+            tc::gemm_issue_fast<N, KSTEPS, A_MN, B_MN>(tmem + w * 64, a, b, r > 0);
+            if (mode == 1) { tc::mma_commit(&bar[w]); tc::mbar_wait(&bar[w], ph); ph ^= 1; }
         }
-        if (mode == 0) { tc::mma_commit(&bar); tc::mbar_wait(&bar, ph); }
+        if (mode != 1) { tc::mma_commit(&bar[w]); tc::mbar_wait(&bar[w], ph); }
         const long long t1 = clock64();
-        out[0] = (unsigned long long)(t1 - t0);
-        out[1] = (unsigned long long)reps * KSTEPS;
+        out[2 * w] = (unsigned long long)(t1 - t0);
+        out[2 * w + 1] = (unsigned long long)reps * KSTEPS;
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem, 64);
+    if (warp == 0) tc::tmem_dealloc(tmem, 128);
 }
 
 }  // namespace

@@ -54,9 +54,15 @@ _lib.register({
 _lib.lib.n2m_dp_ctx_bytes.restype = ctypes.c_uint32
 
 
+def slice_rows(rows, world):
+    """Rows owned by one rank: ceil(rows / world) rounded up to a multiple of 4 (csrc/dp.cu slice_rows(): the float2
+    colour moments follow `per` density moments in the slice-sized m / v arrays and must stay 8-byte aligned)."""
+    return ((rows + world - 1) // world + 3) // 4 * 4
+
+
 class PeerAdam:
     """Sharded optimizer for data-parallel training of a Stage0Trainer: each rank owns rows
-    [r*ceil(R/W), (r+1)*ceil(R/W)) of the hash tables.  After the backward pass one kernel per rank reads its
+    [r*per, (r+1)*per), per = ceil(R/W) rounded up to 4, of the hash tables.  After the backward pass one kernel per rank reads its
     slice of every peer's gradient table over NVLink, applies Adam to the slice and stores the refreshed table
     entries into every peer's table (include/n2m_b200_fused.h, "Data-parallel optimizer").  Replaces
     GradSync + Stage0Trainer.adam(); the fp32 colour masters and Adam moments exist only for the owned slice."""
@@ -71,8 +77,8 @@ class PeerAdam:
         assert W <= 8, "PeerAdam supports up to 8 ranks (one NVSwitch domain)"
         dev = t.device
         R = t.rows
-        self.per = per = (R + W - 1) // W
-        lo, hi = r * per, min(R, (r + 1) * per)
+        self.per = per = slice_rows(R, W)
+        lo, hi = min(R, r * per), min(R, (r + 1) * per)
         # second-parity gradient buffers (peers may still be reading parity p while parity p^1 is being zeroed)
         t.gtables = [t.gtable, torch.zeros_like(t.gtable)]
         t.g_mlps = [t.g_mlp, torch.zeros_like(t.g_mlp)]

@@ -37,7 +37,8 @@ _lib.register({
     "n2m_s0_init": [],
     "n2m_s0_set_serial_march": [I],
     "n2m_s0_set_mlp_bwd_pipelined": [I],
-    "n2m_s0_set_tv_in_fwd": [I],
+    "n2m_s0_set_tv_mode": [I],
+    "n2m_s0_tv": [PP, P, P, U, P, P, P, P, P, P, P],
     "n2m_s0_pack_weights": [P, P, P],
     "n2m_s0_pack_tables": [P, P, U, P, P, P],
     "n2m_s0_unpack_tables": [P, P, U, P, P, P],
@@ -166,6 +167,9 @@ class Stage0Trainer:
         self.loss_acc = torch.zeros(4, device=dev)          # [0] rgb(+mask) loss, [1] sum |spec|^2
         self.params = S0Params()
         self._fill_params(shading_full=True, gt_has_alpha=True)
+        self.tv_overlap = True              # TV gradient as its own launch overlapped with the MLP kernels (tv mode 2)
+        self._tv_stream = None
+        call("n2m_s0_set_tv_mode", 2 if self.tv_overlap else 0)
         self.gtables = [self.gtable]        # PeerAdam adds a second parity (parallel.py)
         self.g_mlps = [self.g_mlp]
         self.parity = 0
@@ -282,6 +286,10 @@ class Stage0Trainer:
         call("n2m_s0_encode_bwd", self._pp(), ptr(self.recs), ptr(self.counters), self.Mcap, ptr(self.rays_o), ptr(self.rays_d),
              ptr(self.denc_tiles), ptr(self.table), ptr(self.offsets), ptr(self.gtables[self.parity]), ptr(self.opt_state), stream())
 
+    def tv(self):
+        call("n2m_s0_tv", self._pp(), ptr(self.recs), ptr(self.counters), self.Mcap, ptr(self.rays_o), ptr(self.rays_d),
+             ptr(self.table), ptr(self.offsets), ptr(self.gtables[self.parity]), ptr(self.opt_state), stream())
+
     def adam(self):
         call("n2m_s0_adam", ptr(self.table), ptr(self.color_master), ptr(self.gtable), ptr(self.m_table), ptr(self.v_table), self.rows,
              ptr(self.mlp), ptr(self.g_mlp), ptr(self.m_mlp), ptr(self.v_mlp), ptr(self.wpack), ptr(self.opt_state), self.cfg.eps, stream())
@@ -289,21 +297,28 @@ class Stage0Trainer:
     def forward_backward(self):
         """march -> encode -> MLP -> composite+loss -> MLP backward -> scatter(+TV); gradients stay in
         gtable / g_mlp (loss-scaled)."""
-        self.loss_acc.zero_()
         self.march()
-        self.encode_fwd()
-        self.mlp_fwd()
-        self.composite_loss()
-        self.mlp_bwd()
-        self.encode_bwd()
+        self._compute()
 
     def _compute(self):
-        """Everything after the march for the current slot."""
+        """Everything after the march for the current slot.  With tv_overlap the TV-gradient kernel (memory
+        bound, independent of the MLPs) runs on a forked stream underneath the latency-bound tensor-core MLP
+        kernels and is joined before the scatter."""
         self.loss_acc.zero_()
         self.encode_fwd()
+        fork = self.tv_overlap and self.cfg.lambda_tv > 0
+        if fork:
+            main = torch.cuda.current_stream()
+            if self._tv_stream is None:
+                self._tv_stream = torch.cuda.Stream(device=self.device)
+            self._tv_stream.wait_stream(main)
+            with torch.cuda.stream(self._tv_stream):
+                self.tv()
         self.mlp_fwd()
         self.composite_loss()
         self.mlp_bwd()
+        if fork:
+            main.wait_stream(self._tv_stream)
         self.encode_bwd()
 
     def _step_body(self):
@@ -313,7 +328,13 @@ class Stage0Trainer:
     # -------------------------------------------------------------------------------------------
     def _graph(self, name, fn):
         """Capture-once CUDA graph of `fn` for the current (slot, shading, alpha) configuration."""
-        key = (name, self.cur, self.parity, int(self.params.shading_full), int(self.params.gt_has_alpha))
+        # only what the captured launches actually depend on goes into the key (fewer captures)
+        if name == "march":
+            key = (name, self.cur)
+        elif name in ("adam", "peer_adam"):
+            key = (name, self.parity)
+        else:
+            key = (name, self.cur, self.parity, int(self.params.shading_full), int(self.params.gt_has_alpha))
         g = self._graphs.get(key)
         if g is None:
             g = torch.cuda.CUDAGraph()
@@ -457,6 +478,8 @@ class Stage0Trainer:
         """Forget a batch staged by `next_batch=` (e.g. when the caller changes its batch sequence)."""
         if self._side is not None:
             self._side.synchronize()
+        if self._prefetched is not None:
+            self.cur = self._prefetched      # keep the slot alternation in phase (graphs are captured per slot)
         self._prefetched = None
 
     def read_loss(self):

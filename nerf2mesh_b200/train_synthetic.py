@@ -45,6 +45,8 @@ def main(argv=None):
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--update_interval", type=int, default=16)
     ap.add_argument("--diffuse_step", type=int, default=1000)
+    ap.add_argument("--samples_per_ray", type=int, default=512,
+                    help="sample-slab capacity per ray; the cold-start occupancy grid marches far more samples than a converged one")
     args = ap.parse_args(argv)
 
     torch.manual_seed(args.seed)
@@ -53,7 +55,7 @@ def main(argv=None):
     poses = S.orbit_cameras(100, seed=0)
     test_poses = S.orbit_cameras(args.eval_views, seed=12345)
     intr = S.lego_intrinsics()
-    cfg = Stage0Config(bound=1.0, num_rays=args.num_rays, max_samples=args.num_rays * 192)
+    cfg = Stage0Config(bound=1.0, num_rays=args.num_rays, max_samples=args.num_rays * args.samples_per_ray)
     tr = Stage0Trainer(cfg, seed=args.seed)
     # cold start as the reference: empty density grid => first update marks everything with sigma > mean
     tr.density_grid.zero_()

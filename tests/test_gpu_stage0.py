@@ -238,3 +238,58 @@ def test_pipelined_mlp_backward_equals_single_tile_kernel():
         assert d0.abs().max() > 0
         g0, g1 = res[0][1], res[1][1]
         assert (g0 - g1).abs().max().item() <= 1e-4 * g0.abs().max().item()
+
+
+def test_update_density_grid_matches_reference_composition():
+    """Stage0Trainer.update_density_grid vs the reference's update_extra_state arithmetic (renderer.py:1074-1149)
+    composed from torch + the (bit-exact) operator-level encoder, same random jitter."""
+    import torch.nn.functional as Fnn
+    from nerf2mesh_b200 import raymarching as rm
+    tr, b = make()
+    c = tr.cfg
+    H = c.grid_size
+    st = tr.export_reference_state()
+    tr.density_grid.zero_()
+    torch.manual_seed(123)
+    tr.update_density_grid(decay=0.95, density_thresh=10.0)
+    torch.cuda.synchronize()
+    # reference composition
+    torch.manual_seed(123)
+    ax = torch.arange(H, dtype=torch.int32, device="cuda")
+    grid = torch.zeros(1, H ** 3, device="cuda")
+    cells = H ** 3
+    for first in range(0, cells, tr.Mcap):
+        cnt = min(tr.Mcap, cells - first)
+        noise = torch.rand(cnt, 3, device="cuda")
+        idx = torch.arange(first, first + cnt, dtype=torch.int32, device="cuda")
+        coords = rm.morton3D_invert(idx)
+        xyz = 2 * coords.float() / (H - 1) - 1
+        hgs = 1.0 / H
+        xyz = xyz * (1.0 - hgs) + (noise * 2 - 1) * hgs
+        enc = grid_encode((xyz + 1) / 2, st["encoder.embeddings"], tr.offsets, c.per_level_scale, 16)
+        with torch.autocast("cuda", dtype=torch.float16):
+            h = Fnn.linear(torch.cat([xyz, enc], -1), st["sigma_net.net.0.weight"]).relu()
+            h = Fnn.linear(h, st["sigma_net.net.1.weight"])
+        sigma = torch.exp(h[:, 0].float())
+        grid[0, first:first + cnt] = torch.maximum(grid[0, first:first + cnt] * 0.95, sigma)
+    assert (tr.density_grid - grid).abs().max().item() <= 2e-3 * grid.abs().max().item()
+    mean = tr.density_grid.clamp(min=0).mean().item()
+    assert abs(tr.mean_density.item() - mean) < 1e-6
+    assert torch.equal(tr.density_bitfield, rm.packbits(tr.density_grid, min(mean, 10.0)))
+    occ = (tr.density_grid > min(mean, 10.0)).float().mean().item()
+    assert 0.05 < occ < 0.95
+
+
+def test_render_equals_training_forward():
+    tr, b = make()
+    stage(tr, b)
+    tr.noises.zero_()
+    tr.forward_backward()
+    img0 = tr.image.clone(); ws0 = tr.weights_sum.clone()
+    img, ws, dep = tr.render(b["ro"].cuda(), b["rd"].cuda(), bg_color=b["bg"].cuda())
+    assert torch.equal(img, img0) and torch.equal(ws, ws0)
+    # ragged call: more rays than one chunk, white background
+    ro2 = torch.cat([b["ro"], b["ro"][:10]]).cuda(); rd2 = torch.cat([b["rd"], b["rd"][:10]]).cuda()
+    img2, ws2, _ = tr.render(ro2, rd2, bg_color=1.0)
+    assert img2.shape == (N + 10, 3) and torch.equal(img2[:10], img2[N:])
+    assert torch.isfinite(img2).all()

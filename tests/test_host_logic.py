@@ -107,3 +107,18 @@ def test_drop_in_module_names():
               "march_rays_train", "composite_rays_train", "march_rays", "composite_rays"):
         assert callable(getattr(raymarching, n))
     assert gridencoder.GridEncoder is ge.GridEncoder and shencoder.SHEncoder is sh.SHEncoder
+
+
+def test_peer_adam_slices_cover_rows_and_stay_aligned():
+    """PeerAdam row slices: disjoint cover of the table, slice length a multiple of 4 so that the float2 colour
+    moments stored behind the density moments are 8-byte aligned (6119864 rows / 8 ranks = 764983 is odd)."""
+    from nerf2mesh_b200.parallel import slice_rows
+    from nerf2mesh_b200.gridencoder.grid import level_offsets
+    rows = int(level_offsets(3, 16, float(np.exp2(np.log2(2048 / 16) / 15)), 16, 19, False)[-1])
+    for R in (rows, 1, 7, 1000003):
+        for W in range(1, 9):
+            per = slice_rows(R, W)
+            assert per % 4 == 0 and per * W >= R
+            lo = [min(R, r * per) for r in range(W)]
+            hi = [min(R, (r + 1) * per) for r in range(W)]
+            assert lo[0] == 0 and hi[-1] == R and all(hi[r] == lo[r + 1] for r in range(W - 1))
