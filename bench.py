@@ -144,6 +144,8 @@ def run_ours(args):
 
     cfg = Stage0Config(bound=1.0, num_rays=NUM_RAYS, max_samples=NUM_RAYS * 128)
     tr = Stage0Trainer(cfg, seed=0)
+    tr.nparts = args.parts
+    tr.part_mode = args.part_mode
     sync = None
     dp_used = args.dp
     if world > 1:
@@ -225,7 +227,7 @@ def run_ours(args):
     e2e_samples = 0
     for it in range(K):
         one_step(host_batches, it)
-        loss_host.copy_(tr.loss_acc, non_blocking=True); cnt_host.copy_(tr.counters, non_blocking=True)
+        loss_host.copy_(tr.loss_acc, non_blocking=True); cnt_host.copy_(tr.counters[:4], non_blocking=True)
         torch.cuda.current_stream().synchronize()            # the user-visible result of the step
         e2e_samples += int(cnt_host[1])
     f1.record()
@@ -273,7 +275,7 @@ def run_ours(args):
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16",
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "rays_per_batch": NUM_RAYS, "global_rays": NUM_RAYS * world,
-                           "samples_per_step": samples_total / K, "parallelism": f"dp{world}" + ("" if world == 1 else f"-{dp_used}"), "cuda_graph": not args.no_graph, "march_prefetch": not args.no_prefetch,
+                           "samples_per_step": samples_total / K, "parallelism": f"dp{world}" + ("" if world == 1 else f"-{dp_used}"), "cuda_graph": not args.no_graph, "ray_range_parts": args.parts, "part_mode": args.part_mode, "march_prefetch": not args.no_prefetch,
                            "l2": "inputs cycle over 8 batches; tables+grads+Adam state (0.6 GB touched per step) exceed the 126 MB L2"},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -294,6 +296,9 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-prefetch", action="store_true", help="do not overlap the next batch's march with this step")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--part-mode", default="chains", choices=["pipeline", "chains"])
+    ap.add_argument("--parts", type=int, default=1, choices=[1, 2, 4, 8],
+                    help="ray-range parts run as concurrent gather->MLP->composite->MLP'->scatter chains on forked streams")
     ap.add_argument("--dp", default="peer", choices=["peer", "nccl"],
                     help="N > 1: 'peer' = fused reduce-scatter+Adam+all-gather over NVLink peer memory, 'nccl' = all-reduce + replicated Adam")
     args = ap.parse_args()

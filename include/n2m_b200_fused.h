@@ -29,7 +29,10 @@
  *              51-53 unit view direction, 54-63 zero.  It is the A operand of every first-layer GEMM and is
  *              staged global->shared with a single bulk async copy.
  *   recs       [Mcap] float4 {t_before, dt, t_after, ray_id (bits)} per sample, ray order.
- *   counters   int32 [4]: [0] M (total samples marched), [1] min(M, Mcap), [2] overflow flag, [3] unused.
+ *   counters   int32 [16]: [0] M (total samples marched), [1] min(M, Mcap), [2] overflow flag, [3] unused,
+ *              [4..12] sample offset of the first ray of every eighth of the batch (ray N*e/8, e = 0..8; [4] = 0,
+ *              [12] = [1]): the boundaries of the ray-range parts of the *_part entry points below.
+ *              Entry points without parts (and nparts == 1) read only [1], so hand-filled 4-entry arrays keep working.
  *   wpack      packed fp16 MLP weights in tensor-core tile layout (n2m_s0_pack_weights).
  */
 #ifndef N2M_B200_FUSED_H
@@ -70,13 +73,18 @@ int n2m_s0_set_serial_march(int on);
 
 /* tuning hook: where the TV gradient is evaluated: 0 = backward scatter kernel, 1 = forward gather kernel, 2 = own launch */
 int n2m_s0_set_tv_mode(int mode);
+/* tuning hook: preferred shared-memory carve-out (percent, -1 = driver default) of the gather / scatter / composite / march
+ * kernels; an SM holds one carve-out configuration at a time, so co-residency with the MLP kernels needs a matching one */
+int n2m_s0_set_gather_carveout(int percent);
 /* the stand-alone TV launch (tv mode 2): reads recs/table, adds into gtable; independent of the MLP kernels */
 int n2m_s0_tv(const n2m_s0_params* p, const void* recs, const int32_t* counters, uint32_t Mcap, const float* rays_o,
               const float* rays_d, const void* table, const int32_t* offsets, void* gtable, const float* loss_scale,
               n2m_stream_t stream);
 
-/* test hook: MLP backward variant, 1 = two tiles in flight + issuer warp (default), 0 = one tile per CTA */
+/* tuning hook: MLP backward variant, 0 = one tile per CTA (default), 1 = two tiles in flight + issuer warp */
 int n2m_s0_set_mlp_bwd_pipelined(int on);
+/* debug: device buffer (>= 128 uint64) that block 0 of the pipelined MLP backward stamps with clock64(); NULL = off */
+int n2m_s0_set_prof(void* buf);
 
 /* sizes of the packed weight blob (bytes) and of the flat fp32 MLP parameter / gradient vector (floats) */
 uint32_t n2m_s0_wpack_bytes(void);
@@ -144,6 +152,32 @@ int n2m_s0_encode_bwd(const n2m_s0_params* p, const void* recs, const int32_t* c
                       const float* rays_o, const float* rays_d, const void* denc_tiles, const void* table,
                       const int32_t* offsets, void* gtable, const float* loss_scale, n2m_stream_t stream);
 
+/* Ray-range parts.  The stages between march and optimizer can be run on `nparts` (1, 2, 4 or 8) contiguous ray ranges
+ * of the batch -- part k covers rays [N*k/nparts, N*(k+1)/nparts) and their (contiguous, ray-ordered) samples -- so that
+ * independent chains  gather -> MLP -> composite -> MLP backward -> scatter  of different parts can be in flight on
+ * different streams: the latency-bound tensor-core MLP kernels of one part then share the SMs with the memory-bound
+ * gather / scatter kernels of another.  A 128-sample tile that straddles a part boundary is computed by both parts,
+ * each one reading / writing only its own rows (rows are masked by the [lo, hi) sample range taken from counters[4..12]);
+ * losses, weight gradients and table gradients accumulate atomically, so the union of all parts equals the un-split call
+ * up to fp32 summation order.  The entry points above are the nparts == 1 case. */
+int n2m_s0_encode_fwd_part(const n2m_s0_params* p, const void* recs, const int32_t* counters, uint32_t Mcap,
+                           const float* rays_o, const float* rays_d, const void* table, const int32_t* offsets,
+                           void* enc_tiles, void* gtable, const float* loss_scale, uint32_t part, uint32_t nparts,
+                           n2m_stream_t stream);
+int n2m_s0_mlp_fwd_part(const n2m_s0_params* p, const void* enc_tiles, const int32_t* counters, uint32_t Mcap,
+                        const void* wpack, void* out, float* spec_sq_sum, uint32_t part, uint32_t nparts, n2m_stream_t stream);
+int n2m_s0_composite_loss_part(const n2m_s0_params* p, const void* out, const void* recs, const int32_t* rays,
+                               const int32_t* counters, uint32_t N, uint32_t Mcap, const float* gt, const float* bg,
+                               const float* loss_scale, void* dout, float* image, float* weights_sum, float* depth,
+                               float* loss_out, uint32_t part, uint32_t nparts, n2m_stream_t stream);
+int n2m_s0_mlp_bwd_part(const n2m_s0_params* p, const void* enc_tiles, const void* dout, const int32_t* counters,
+                        uint32_t Mcap, const void* wpack, void* denc_tiles, float* g_mlp, const float* loss_scale,
+                        uint32_t part, uint32_t nparts, n2m_stream_t stream);
+int n2m_s0_encode_bwd_part(const n2m_s0_params* p, const void* recs, const int32_t* counters, uint32_t Mcap,
+                           const float* rays_o, const float* rays_d, const void* denc_tiles, const void* table,
+                           const int32_t* offsets, void* gtable, const float* loss_scale, uint32_t part, uint32_t nparts,
+                           n2m_stream_t stream);
+
 /* optimizer state block (device, float[8]): [0] loss_scale, [1] growth_tracker, [2] adam step t,
  * [3] found_inf, [4] lr (host-written each step), [5] 1-beta1^t, [6] sqrt(1-beta2^t), [7] 1/loss_scale.
  * Every `loss_scale` pointer argument above is the base of this block: the kernels read [0] and set [3]
@@ -154,6 +188,16 @@ int n2m_s0_encode_bwd(const n2m_s0_params* p, const void* recs, const int32_t* c
 int n2m_s0_adam(void* table, void* color_master, void* gtable, float* m_table, float* v_table, uint32_t rows,
                 float* mlp_params, float* g_mlp, float* m_mlp, float* v_mlp, void* wpack,
                 float* opt_state, float eps, n2m_stream_t stream);
+
+/* the same stage as four launches: head (MLP-gradient inf scan + step constants), tables, mlp (+ weight repack), post
+ * (GradScaler update).  `tables` and `mlp` only read opt_state and touch disjoint buffers: a host may run them on two
+ * streams between head and post (nerf2mesh_b200/stage0.py does). */
+int n2m_s0_adam_head(const float* g_mlp, float* opt_state, n2m_stream_t stream);
+int n2m_s0_adam_tables(void* table, void* color_master, void* gtable, float* m_table, float* v_table, uint32_t rows,
+                       const float* opt_state, float eps, n2m_stream_t stream);
+int n2m_s0_adam_mlp(float* mlp_params, float* g_mlp, float* m_mlp, float* v_mlp, void* wpack, const float* opt_state, float eps,
+                    n2m_stream_t stream);
+int n2m_s0_adam_post(float* opt_state, n2m_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Data-parallel optimizer fused with its collective over NVLink peer memory (csrc/dp.cu).

@@ -154,15 +154,18 @@ constexpr uint32_t F_W = 0, F_A = F_W + W_BYTES, F_H = F_A + kTileBytes, F_S1 = 
 
 __global__ void __launch_bounds__(128)
 k_mlp_fwd(n2m_s0_params p, const uint8_t* __restrict__ enc_tiles, const int32_t* __restrict__ counters,
-          const uint8_t* __restrict__ wpack, float4* __restrict__ out, float* __restrict__ spec_sq_sum) {
+          const uint8_t* __restrict__ wpack, float4* __restrict__ out, float* __restrict__ spec_sq_sum,
+          uint32_t part, uint32_t nparts) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar_mma, bar_tma;
     __shared__ uint32_t tmem_s;
     __shared__ float red[4];
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
-    const uint32_t M = (uint32_t)counters[1];
-    const uint32_t ntiles = (M + kTile - 1) / kTile;
-    if (blockIdx.x >= ntiles) return;
+    // samples [lo, hi) of this part: tiles [t0, t1); the boundary tiles are also computed by the neighbouring parts,
+    // every part writes only its own rows
+    const PartRange pr = part_range(counters, part, nparts);
+    const uint32_t t0 = pr.lo / kTile, t1 = (pr.hi + kTile - 1) / kTile;
+    if (pr.hi <= pr.lo || t0 + blockIdx.x >= t1) return;
 
     if (tid == 0) { tc::mbar_init(&bar_mma, 1); tc::mbar_init(&bar_tma, 1); tc::mbar_init_fence(); }
     if (warp == 0) tc::tmem_alloc(&tmem_s, 128);
@@ -186,7 +189,7 @@ k_mlp_fwd(n2m_s0_params p, const uint8_t* __restrict__ enc_tiles, const int32_t*
                      wS2 = tc::make_opdesc(opK(sW + W_S2, 16)), wP1 = tc::make_opdesc(opK(sW + W_P1, 32)),
                      wP2 = tc::make_opdesc(opK(sW + W_P2, 16));
 
-    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (uint32_t tile = t0 + blockIdx.x; tile < t1; tile += gridDim.x) {
         if (tid == 0) bulk_g2s(sA, enc_tiles + (size_t)tile * kTileBytes, kTileBytes, &bar_tma);
         tc::mbar_wait(&bar_tma, ph_tma); ph_tma ^= 1;
 
@@ -262,7 +265,7 @@ k_mlp_fwd(n2m_s0_params p, const uint8_t* __restrict__ enc_tiles, const int32_t*
             cb = fminf(fmaxf(round_h(sp[2] + cb), 0.f), 1.f);
         }
         const uint32_t j = tile * kTile + tid;
-        if (j < M) {
+        if (j >= pr.lo && j < pr.hi) {
             out[j] = make_float4(sigma, cr, cg, cb);
             spec_sq += sp[0] * sp[0] + sp[1] * sp[1] + sp[2] * sp[2];
         }
@@ -292,14 +295,17 @@ constexpr uint32_t T_K0 = 0, T_K1 = 64, T_C1 = 128, T_C2 = 192, T_S1 = 256, T_P1
 __global__ void __launch_bounds__(128)
 k_mlp_bwd(n2m_s0_params p, const uint8_t* __restrict__ enc_tiles, const float4* __restrict__ dout,
           const int32_t* __restrict__ counters, const uint8_t* __restrict__ wpack, uint8_t* __restrict__ denc_tiles,
-          float* __restrict__ g_mlp, const float* __restrict__ loss_scale) {
+          float* __restrict__ g_mlp, const float* __restrict__ loss_scale, uint32_t part, uint32_t nparts) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar_mma, bar_tma;
     __shared__ uint32_t tmem_s;
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
-    const uint32_t M = (uint32_t)counters[1];
-    const uint32_t ntiles = (M + kTile - 1) / kTile;
-    if (blockIdx.x >= ntiles) return;
+    // rows outside [lo, hi) of a boundary tile belong to a neighbouring part: zero upstream gradient (so they add
+    // nothing to the weight gradients; their activations are whatever finite values the tile holds) and no store
+    const PartRange pr = part_range(counters, part, nparts);
+    const uint32_t M = pr.M;
+    const uint32_t t0 = pr.lo / kTile, t1 = (pr.hi + kTile - 1) / kTile;
+    if (pr.hi <= pr.lo || t0 + blockIdx.x >= t1) return;
 
     if (tid == 0) { tc::mbar_init(&bar_mma, 1); tc::mbar_init(&bar_tma, 1); tc::mbar_init_fence(); }
     if (warp == 0) tc::tmem_alloc(&tmem_s, 512);
@@ -336,11 +342,12 @@ k_mlp_bwd(n2m_s0_params p, const uint8_t* __restrict__ enc_tiles, const float4* 
     const tc::Operand G2 = opMN(sH2, 128);              // [H2 | H1]
     const tc::Operand G3 = opMN(sS1, 128);              // [S1 | P1 | As2 | (don't care)]
 
-    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (uint32_t tile = t0 + blockIdx.x; tile < t1; tile += gridDim.x) {
         if (tid == 0) bulk_g2s(sA, enc_tiles + (size_t)tile * kTileBytes, kTileBytes, &bar_tma);
         const uint32_t j = tile * kTile + tid;
         float4 dv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (j < M) dv = dout[j];
+        const bool own = j >= pr.lo && j < pr.hi;
+        if (own) dv = dout[j];
         tc::mbar_wait(&bar_tma, ph_tma); ph_tma ^= 1;
 
         // ---------------- forward recompute ----------------
@@ -409,7 +416,7 @@ k_mlp_bwd(n2m_s0_params p, const uint8_t* __restrict__ enc_tiles, const float4* 
                 if (full) {
                     const float cs = round_h(sp[c] + feat[c]);
                     if (!(cs >= 0.f && cs <= 1.f)) g = 0.f;            // clamp(0,1) backward
-                    const float dsp = (j < M) ? g + spec_reg * sp[c] : 0.f;
+                    const float dsp = own ? g + spec_reg * sp[c] : 0.f;
                     dO2[c] = dsp * sp[c] * (1.0f - sp[c]);            // sigmoid backward
                 }
                 dfeat[c] = g;
@@ -498,7 +505,7 @@ k_mlp_bwd(n2m_s0_params p, const uint8_t* __restrict__ enc_tiles, const float4* 
                     uint4 o;
                     o.x = pack2(v[8 * q + 0], v[8 * q + 1]); o.y = pack2(v[8 * q + 2], v[8 * q + 3]);
                     o.z = pack2(v[8 * q + 4], v[8 * q + 5]); o.w = pack2(v[8 * q + 6], v[8 * q + 7]);
-                    *reinterpret_cast<uint4*>(img + (c0 / 8 + q) * kChunk) = o;
+                    if (own || nparts == 1) *reinterpret_cast<uint4*>(img + (c0 / 8 + q) * kChunk) = o;
                 }
             }
         }
@@ -609,19 +616,21 @@ __device__ __forceinline__ void group_wait(uint64_t* bar, uint32_t& ph) {
 // optional phase profiler (n2m_s0_set_prof): block 0 stamps clock64() at every hand-over of its first tile --
 // slots 0..31 tile group 0 (thread 0), 32..63 the issuer's view of group 0, 64..95 tile group 1.  Null => off.
 __device__ unsigned long long* g_prof = nullptr;
+constexpr uint32_t kProfIter = 3;                 // which of block 0's tile iterations is stamped (steady state, not the cold first one)
 #define PROF_STAMP() do { if (pf) { pf[ps++] = (unsigned long long)clock64(); } } while (0)
 
 __global__ void __launch_bounds__(288)
 k_mlp_bwd2(n2m_s0_params p, const uint8_t* __restrict__ enc_tiles, const float4* __restrict__ dout,
            const int32_t* __restrict__ counters, const uint8_t* __restrict__ wpack, uint8_t* __restrict__ denc_tiles,
-           float* __restrict__ g_mlp, const float* __restrict__ loss_scale) {
+           float* __restrict__ g_mlp, const float* __restrict__ loss_scale, uint32_t part, uint32_t nparts) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar_ready[2], bar_done[2], bar_tma[2];
     __shared__ uint32_t tmem_s;
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t M = (uint32_t)counters[1];
-    const uint32_t ntiles = (M + kTile - 1) / kTile;
-    if (blockIdx.x * 2 >= ntiles) return;
+    const PartRange pr = part_range(counters, part, nparts);
+    const uint32_t M = pr.M;
+    const uint32_t t0 = pr.lo / kTile, ntiles = (pr.hi + kTile - 1) / kTile;       // tiles [t0, ntiles)
+    if (pr.hi <= pr.lo || t0 + blockIdx.x * 2 >= ntiles) return;
     const bool full = p.shading_full != 0;
 
     if (tid == 0) {
@@ -652,7 +661,7 @@ k_mlp_bwd2(n2m_s0_params p, const uint8_t* __restrict__ enc_tiles, const float4*
             uint32_t ph_ready[2] = {0, 0};
             uint32_t n_g[2];
             for (int g = 0; g < 2; ++g) {
-                const uint32_t first_tile = blockIdx.x * 2 + g;
+                const uint32_t first_tile = t0 + blockIdx.x * 2 + g;
                 n_g[g] = first_tile < ntiles ? (ntiles - first_tile + 2 * gridDim.x - 1) / (2 * gridDim.x) : 0;
             }
             bool f_c1 = false, f_c2 = false, f_s1 = false, f_p1 = false, f_c3 = false, f_s2 = false, f_p2 = false;   // accumulator initialised?
@@ -708,7 +717,7 @@ k_mlp_bwd2(n2m_s0_params p, const uint8_t* __restrict__ enc_tiles, const float4*
                         const int round = (int)rd[g];
                         const GroupDesc& q = gd[g];
                         const uint32_t K0 = tmem + g * 128, K1 = K0 + 64;
-                        unsigned long long* pf = (itg[g] == 0 && g == 0) ? pf0 : nullptr;
+                        unsigned long long* pf = (itg[g] == kProfIter && g == 0) ? pf0 : nullptr;
                         PROF_STAMP();
                         switch (round) {
                             case 0:   // R1: first layers
@@ -781,13 +790,14 @@ k_mlp_bwd2(n2m_s0_params p, const uint8_t* __restrict__ enc_tiles, const float4*
 
         unsigned long long* pfb = (blockIdx.x == 0 && tg == 0 && g_prof) ? g_prof + g * 64 : nullptr;
         uint32_t ps = 0;
-        for (uint32_t tile = blockIdx.x * 2 + g; tile < ntiles; tile += 2 * gridDim.x) {
-            unsigned long long* pf = (tile == blockIdx.x * 2 + g) ? pfb : nullptr;
+        for (uint32_t tile = t0 + blockIdx.x * 2 + g; tile < ntiles; tile += 2 * gridDim.x) {
+            unsigned long long* pf = (tile == t0 + blockIdx.x * 2 + g + kProfIter * 2 * gridDim.x) ? pfb : nullptr;
             PROF_STAMP();
             if (tg == 0) bulk_g2s(sA, enc_tiles + (size_t)tile * kTileBytes, kTileBytes, &bar_tma[g]);
             const uint32_t j = tile * kTile + tg;
             float4 dv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (j < M) dv = dout[j];
+            const bool own = j >= pr.lo && j < pr.hi;
+            if (own) dv = dout[j];
             tc::mbar_wait(&bar_tma[g], ph_tma); ph_tma ^= 1;
             PROF_STAMP();
             PROF_STAMP(); group_ready(&bar_ready[g], g, tg);                                   // R1 may start
@@ -834,7 +844,7 @@ k_mlp_bwd2(n2m_s0_params p, const uint8_t* __restrict__ enc_tiles, const float4*
                     if (full) {
                         const float cs = round_h(sp[c] + feat[c]);
                         if (!(cs >= 0.f && cs <= 1.f)) gg = 0.f;
-                        const float dsp = (j < M) ? gg + spec_reg * sp[c] : 0.f;
+                        const float dsp = own ? gg + spec_reg * sp[c] : 0.f;
                         dO2[c] = dsp * sp[c] * (1.0f - sp[c]);
                     }
                     dfeat[c] = gg;
@@ -885,7 +895,7 @@ k_mlp_bwd2(n2m_s0_params p, const uint8_t* __restrict__ enc_tiles, const float4*
                         uint4 o;
                         o.x = pack2(v[8 * q + 0], v[8 * q + 1]); o.y = pack2(v[8 * q + 2], v[8 * q + 3]);
                         o.z = pack2(v[8 * q + 4], v[8 * q + 5]); o.w = pack2(v[8 * q + 6], v[8 * q + 7]);
-                        *reinterpret_cast<uint4*>(img + (c0 / 8 + q) * kChunk) = o;
+                        if (own || nparts == 1) *reinterpret_cast<uint4*>(img + (c0 / 8 + q) * kChunk) = o;
                     }
                 }
             }
@@ -990,8 +1000,9 @@ static int num_sms() {
     return n;
 }
 
-static bool g_bwd_pipelined = true;
-/* test hook: 0 = single-tile backward kernel, 1 = two-tile pipelined kernel with issuer warp (default) */
+static bool g_bwd_pipelined = false;
+/* 0 = single-tile backward kernel (default: measured faster, and it leaves room on the SM for a co-resident gather /
+ * scatter kernel), 1 = two-tile pipelined kernel with issuer warp */
 int n2m_s0_set_mlp_bwd_pipelined(int on) { g_bwd_pipelined = on != 0; return 0; }
 
 /* one-time function attributes (dynamic shared memory opt-in); safe to call repeatedly */
@@ -1004,32 +1015,46 @@ int n2m_s0_init(void) {
     return 0;
 }
 
-int n2m_s0_mlp_fwd(const n2m_s0_params* p, const void* enc_tiles, const int32_t* counters, uint32_t Mcap, const void* wpack,
-                   void* out, float* spec_sq_sum, n2m_stream_t stream) {
+int n2m_s0_mlp_fwd_part(const n2m_s0_params* p, const void* enc_tiles, const int32_t* counters, uint32_t Mcap, const void* wpack,
+                        void* out, float* spec_sq_sum, uint32_t part, uint32_t nparts, n2m_stream_t stream) {
     N2M_REQUIRE(p && enc_tiles && counters && wpack && out, "s0_mlp_fwd", "null pointer");
     N2M_REQUIRE(Mcap % kTile == 0 && Mcap > 0, "s0_mlp_fwd", "Mcap must be a positive multiple of 128");
+    N2M_REQUIRE(valid_parts(part, nparts), "s0_mlp_fwd", "nparts must be 1, 2, 4 or 8 and part < nparts");
     const uint32_t grid = min(Mcap / kTile, (uint32_t)(2 * num_sms()));
     k_mlp_fwd<<<grid, 128, F_BYTES, as_stream(stream)>>>(*p, static_cast<const uint8_t*>(enc_tiles), counters,
-                                                         static_cast<const uint8_t*>(wpack), static_cast<float4*>(out), spec_sq_sum);
+                                                         static_cast<const uint8_t*>(wpack), static_cast<float4*>(out), spec_sq_sum,
+                                                         part, nparts);
     return check_launch("s0_mlp_fwd");
 }
 
-int n2m_s0_mlp_bwd(const n2m_s0_params* p, const void* enc_tiles, const void* dout, const int32_t* counters, uint32_t Mcap,
-                   const void* wpack, void* denc_tiles, float* g_mlp, const float* loss_scale, n2m_stream_t stream) {
+int n2m_s0_mlp_fwd(const n2m_s0_params* p, const void* enc_tiles, const int32_t* counters, uint32_t Mcap, const void* wpack,
+                   void* out, float* spec_sq_sum, n2m_stream_t stream) {
+    return n2m_s0_mlp_fwd_part(p, enc_tiles, counters, Mcap, wpack, out, spec_sq_sum, 0, 1, stream);
+}
+
+int n2m_s0_mlp_bwd_part(const n2m_s0_params* p, const void* enc_tiles, const void* dout, const int32_t* counters, uint32_t Mcap,
+                        const void* wpack, void* denc_tiles, float* g_mlp, const float* loss_scale, uint32_t part, uint32_t nparts,
+                        n2m_stream_t stream) {
     N2M_REQUIRE(p && enc_tiles && dout && counters && wpack && denc_tiles && g_mlp && loss_scale, "s0_mlp_bwd", "null pointer");
     N2M_REQUIRE(Mcap % kTile == 0 && Mcap > 0, "s0_mlp_bwd", "Mcap must be a positive multiple of 128");
+    N2M_REQUIRE(valid_parts(part, nparts), "s0_mlp_bwd", "nparts must be 1, 2, 4 or 8 and part < nparts");
     if (g_bwd_pipelined) {
         const uint32_t grid2 = min((Mcap / kTile + 1) / 2, (uint32_t)num_sms());
         k_mlp_bwd2<<<grid2, 288, P_BYTES, as_stream(stream)>>>(*p, static_cast<const uint8_t*>(enc_tiles), static_cast<const float4*>(dout),
                                                                counters, static_cast<const uint8_t*>(wpack), static_cast<uint8_t*>(denc_tiles),
-                                                               g_mlp, loss_scale);
+                                                               g_mlp, loss_scale, part, nparts);
         return check_launch("s0_mlp_bwd(pipelined)");
     }
     const uint32_t grid = min(Mcap / kTile, (uint32_t)num_sms());
     k_mlp_bwd<<<grid, 128, B_BYTES, as_stream(stream)>>>(*p, static_cast<const uint8_t*>(enc_tiles), static_cast<const float4*>(dout),
                                                          counters, static_cast<const uint8_t*>(wpack), static_cast<uint8_t*>(denc_tiles),
-                                                         g_mlp, loss_scale);
+                                                         g_mlp, loss_scale, part, nparts);
     return check_launch("s0_mlp_bwd");
+}
+
+int n2m_s0_mlp_bwd(const n2m_s0_params* p, const void* enc_tiles, const void* dout, const int32_t* counters, uint32_t Mcap,
+                   const void* wpack, void* denc_tiles, float* g_mlp, const float* loss_scale, n2m_stream_t stream) {
+    return n2m_s0_mlp_bwd_part(p, enc_tiles, dout, counters, Mcap, wpack, denc_tiles, g_mlp, loss_scale, 0, 1, stream);
 }
 
 }  // extern "C"

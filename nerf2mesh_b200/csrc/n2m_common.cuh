@@ -62,4 +62,27 @@ __host__ __device__ __forceinline__ uint32_t compact3(uint32_t x) {
     return x;
 }
 
+
+// ---- ray-range parts of a batch (fused stage-0 path) ----------------------------------------------
+// The march leaves the sample offsets of rays N*e/8 (e = 0..8) in counters[4..12] (clamped to counters[1]).
+// Part `part` of `nparts` (1, 2, 4 or 8) covers rays [N*e0/8, N*e1/8) with e0 = part*8/nparts, e1 = (part+1)*8/nparts,
+// i.e. the contiguous samples [counters[4+e0], counters[4+e1]).  nparts == 1 reads only counters[1] (callers that
+// fill counters by hand, e.g. the explicit-point gather, keep working with a 4-entry array).
+constexpr uint32_t kPartSlots = 8;
+struct PartRange { uint32_t lo, hi, M; };
+__device__ __forceinline__ PartRange part_range(const int32_t* __restrict__ counters, uint32_t part, uint32_t nparts) {
+    PartRange r;
+    r.M = (uint32_t)counters[1];
+    if (nparts <= 1) { r.lo = 0; r.hi = r.M; return r; }
+    r.lo = (uint32_t)counters[4 + part * kPartSlots / nparts];
+    r.hi = (uint32_t)counters[4 + (part + 1) * kPartSlots / nparts];
+    return r;
+}
+__host__ __device__ __forceinline__ uint32_t part_first_ray(uint32_t N, uint32_t eighth) {
+    return (uint32_t)(((unsigned long long)N * eighth) / kPartSlots);
+}
+__host__ inline bool valid_parts(uint32_t part, uint32_t nparts) {
+    return (nparts == 1 || nparts == 2 || nparts == 4 || nparts == 8) && part < nparts;
+}
+
 }  // namespace n2m

@@ -18,16 +18,6 @@ constexpr float kGrowthInterval = 2000.f;
 
 struct __align__(8) TableEntry { float d; __half2 c; };
 
-__global__ void k_adam_prep(float* __restrict__ st) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const bool skip = st[3] != 0.f;
-    if (!skip) st[2] += 1.f;
-    const float t = fmaxf(st[2], 1.f);
-    st[5] = 1.f - powf(kBeta1, t);
-    st[6] = sqrtf(1.f - powf(kBeta2, t));
-    st[7] = 1.f / st[0];
-}
-
 __global__ void k_adam_post(float* __restrict__ st) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     // torch.amp.GradScaler.update: back off on inf, otherwise grow every growth_interval clean steps
@@ -109,11 +99,21 @@ k_adam_mlp(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, 
     m[i] = mi; v[i] = vi;
 }
 
-// non-finite scan of the MLP gradient vector (the table gradients are checked where they are produced)
-__global__ void __launch_bounds__(256)
-k_check_mlp(const float* __restrict__ g, uint32_t n, float* __restrict__ st) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && !isfinite(g[i])) st[3] = 1.f;
+// head of the optimizer stage, one block: non-finite scan of the MLP gradient vector (the table gradients are checked
+// where they are produced) OR-ed into found_inf, then the per-step constants (bias corrections, 1 / loss_scale)
+__global__ void __launch_bounds__(1024)
+k_adam_head(const float* __restrict__ g, uint32_t n, float* __restrict__ st) {
+    int bad = 0;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) bad |= !isfinite(g[i]);
+    bad = __syncthreads_or(bad);
+    if (threadIdx.x != 0) return;
+    if (bad) st[3] = 1.f;
+    const bool skip = st[3] != 0.f;
+    if (!skip) st[2] += 1.f;
+    const float t = fmaxf(st[2], 1.f);
+    st[5] = 1.f - powf(kBeta1, t);
+    st[6] = sqrtf(1.f - powf(kBeta2, t));
+    st[7] = 1.f / st[0];
 }
 
 }  // namespace
@@ -124,23 +124,46 @@ using namespace n2m;
 extern "C" int n2m_s0_pack_weights(const float* mlp_params, void* wpack, n2m_stream_t stream);
 extern "C" uint32_t n2m_s0_mlp_param_count(void);
 
+/* The optimizer stage in four launches.  adam_mlp (+ weight repack) and adam_tables are independent of each other (both only
+ * READ opt_state), so a host may run them on two streams between head and post; n2m_s0_adam is the serial composition. */
+extern "C" int n2m_s0_adam_head(const float* g_mlp, float* opt_state, n2m_stream_t stream) {
+    N2M_REQUIRE(g_mlp && opt_state, "s0_adam_head", "null pointer");
+    k_adam_head<<<1, 1024, 0, as_stream(stream)>>>(g_mlp, n2m_s0_mlp_param_count(), opt_state);
+    return check_launch("s0_adam(head)");
+}
+
+extern "C" int n2m_s0_adam_tables(void* table, void* color_master, void* gtable, float* m_table, float* v_table, uint32_t rows,
+                                  const float* opt_state, float eps, n2m_stream_t stream) {
+    N2M_REQUIRE(table && color_master && gtable && m_table && v_table && opt_state, "s0_adam_tables", "null pointer");
+    if (rows == 0) return 0;
+    k_adam_tables<<<div_up(rows, 256u * kRowsPerThread), 256, 0, as_stream(stream)>>>(
+        static_cast<TableEntry*>(table), static_cast<float2*>(color_master), static_cast<float4*>(gtable), m_table, v_table, rows,
+        opt_state, eps);
+    return check_launch("s0_adam(tables)");
+}
+
+extern "C" int n2m_s0_adam_mlp(float* mlp_params, float* g_mlp, float* m_mlp, float* v_mlp, void* wpack, const float* opt_state,
+                               float eps, n2m_stream_t stream) {
+    N2M_REQUIRE(mlp_params && g_mlp && m_mlp && v_mlp && wpack && opt_state, "s0_adam_mlp", "null pointer");
+    const uint32_t n = n2m_s0_mlp_param_count();
+    k_adam_mlp<<<div_up(n, 256u), 256, 0, as_stream(stream)>>>(mlp_params, g_mlp, m_mlp, v_mlp, n, opt_state, eps);
+    if (int e = check_launch("s0_adam(mlp)")) return e;
+    return n2m_s0_pack_weights(mlp_params, wpack, stream);
+}
+
+extern "C" int n2m_s0_adam_post(float* opt_state, n2m_stream_t stream) {
+    N2M_REQUIRE(opt_state, "s0_adam_post", "null pointer");
+    k_adam_post<<<1, 32, 0, as_stream(stream)>>>(opt_state);
+    return check_launch("s0_adam(post)");
+}
+
 extern "C" int n2m_s0_adam(void* table, void* color_master, void* gtable, float* m_table, float* v_table, uint32_t rows,
                            float* mlp_params, float* g_mlp, float* m_mlp, float* v_mlp, void* wpack, float* opt_state,
                            float eps, n2m_stream_t stream) {
     N2M_REQUIRE(table && color_master && gtable && m_table && v_table && mlp_params && g_mlp && m_mlp && v_mlp && wpack && opt_state,
                 "s0_adam", "null pointer");
-    cudaStream_t st = as_stream(stream);
-    const uint32_t n = n2m_s0_mlp_param_count();
-    k_check_mlp<<<div_up(n, 256u), 256, 0, st>>>(g_mlp, n, opt_state);
-    if (int e = check_launch("s0_adam(check)")) return e;
-    k_adam_prep<<<1, 32, 0, st>>>(opt_state);
-    if (int e = check_launch("s0_adam(prep)")) return e;
-    k_adam_tables<<<div_up(rows, 256u * kRowsPerThread), 256, 0, st>>>(static_cast<TableEntry*>(table), static_cast<float2*>(color_master),
-                                                      static_cast<float4*>(gtable), m_table, v_table, rows, opt_state, eps);
-    if (int e = check_launch("s0_adam(tables)")) return e;
-    k_adam_mlp<<<div_up(n, 256u), 256, 0, st>>>(mlp_params, g_mlp, m_mlp, v_mlp, n, opt_state, eps);
-    if (int e = check_launch("s0_adam(mlp)")) return e;
-    if (int e = n2m_s0_pack_weights(mlp_params, wpack, stream)) return e;
-    k_adam_post<<<1, 32, 0, st>>>(opt_state);
-    return check_launch("s0_adam(post)");
+    if (int e = n2m_s0_adam_head(g_mlp, opt_state, stream)) return e;
+    if (int e = n2m_s0_adam_tables(table, color_master, gtable, m_table, v_table, rows, opt_state, eps, stream)) return e;
+    if (int e = n2m_s0_adam_mlp(mlp_params, g_mlp, m_mlp, v_mlp, wpack, opt_state, eps, stream)) return e;
+    return n2m_s0_adam_post(opt_state, stream);
 }

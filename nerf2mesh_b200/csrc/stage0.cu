@@ -181,12 +181,19 @@ k_s0_scan(int32_t* __restrict__ rays, uint32_t N, uint32_t Mcap, int32_t* __rest
         if (threadIdx.x == 1023) carry_s = carry + warp_tot[31];
         __syncthreads();
     }
+    const uint32_t M = carry_s;
     if (threadIdx.x == 0) {
-        const uint32_t M = carry_s;
         counters[0] = (int32_t)M;
         counters[1] = (int32_t)min(M, Mcap);
         counters[2] = M > Mcap ? 1 : 0;
         counters[3] = 0;
+    }
+    // part boundaries (n2m_common.cuh part_range): sample offset of the first ray of every eighth of the batch
+    if (threadIdx.x <= kPartSlots) {
+        const uint32_t e = threadIdx.x;
+        const uint32_t first = part_first_ray(N, e);
+        const uint32_t off = (e == kPartSlots || first >= N) ? M : (uint32_t)rays[2 * first];
+        counters[4 + e] = (int32_t)min(min(off, M), Mcap);
     }
 }
 
@@ -327,14 +334,13 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 // POINTS = true : explicit positions xyz [P,3] (rays_o) and optional directions [P,3] (rays_d) -- used for the
 //                 density-grid update (renderer.py:1112-1113 evaluates self.density on cell centres) and tests.
 template <bool POINTS, bool TV>
-__global__ void __launch_bounds__(kTile)
-k_s0_encode_fwd(n2m_s0_params p, const float4* __restrict__ recs, const int32_t* __restrict__ counters,
+__device__ __forceinline__ void
+encode_fwd_tile(const n2m_s0_params& p, const float4* __restrict__ recs,
                 const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                 const TableEntry* __restrict__ table, const int32_t* __restrict__ offsets,
-                uint8_t* __restrict__ enc_tiles, float4* __restrict__ gtable, const float* __restrict__ loss_scale) {
-    const uint32_t M = (uint32_t)counters[1];
-    const uint32_t tile = blockIdx.x, r = threadIdx.x;
-    if (tile * kTile >= M) return;
+                uint8_t* __restrict__ enc_tiles, float4* __restrict__ gtable, const float* __restrict__ loss_scale,
+                const PartRange pr, uint32_t nparts, uint32_t tile) {
+    const uint32_t r = threadIdx.x;
     const uint32_t lane = r & 31;
     const uint32_t j = tile * kTile + r;
     float feat[kTileCols];
@@ -342,8 +348,9 @@ k_s0_encode_fwd(n2m_s0_params p, const float4* __restrict__ recs, const int32_t*
     for (uint32_t i = 0; i < kTileCols; ++i) feat[i] = 0.f;
 
     Sample s;
-    bool active = j < M;
-    if (j < M) {
+    const bool own = j >= pr.lo && j < pr.hi;        // rows of a boundary tile outside [lo, hi) belong to another part
+    bool active = own;
+    if (own) {
         if (POINTS) {
             s.x = rays_o[3 * j]; s.y = rays_o[3 * j + 1]; s.z = rays_o[3 * j + 2];
             s.u = __fmul_rn(__fadd_rn(s.x, p.grid_bound), p.inv_2gb);
@@ -432,6 +439,7 @@ k_s0_encode_fwd(n2m_s0_params p, const float4* __restrict__ recs, const int32_t*
         }
     }
     // write this row of the tile image: 8 chunks of 16 bytes, each chunk 2 KiB apart
+    if (nparts > 1 && !own) return;                  // (whole-batch mode also zero-fills the rows past M of the last tile)
     uint8_t* img = enc_tiles + (size_t)tile * kTileBytes + r * 16;
 #pragma unroll
     for (uint32_t ch = 0; ch < 8; ++ch) {
@@ -444,6 +452,23 @@ k_s0_encode_fwd(n2m_s0_params p, const float4* __restrict__ recs, const int32_t*
     }
 }
 
+// one block per 128-sample tile of the part's range [lo, hi) (grid-stride, so any grid size is correct: the host sizes
+// the grid for the expected share of the part and the loop covers an unbalanced one)
+template <bool POINTS, bool TV>
+__global__ void __launch_bounds__(kTile, 6)
+k_s0_encode_fwd(n2m_s0_params p, const float4* __restrict__ recs, const int32_t* __restrict__ counters,
+                const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                const TableEntry* __restrict__ table, const int32_t* __restrict__ offsets,
+                uint8_t* __restrict__ enc_tiles, float4* __restrict__ gtable, const float* __restrict__ loss_scale,
+                uint32_t part, uint32_t nparts) {
+    const PartRange pr = part_range(counters, part, nparts);
+    if (pr.hi <= pr.lo) return;
+    const uint32_t t1 = (pr.hi + kTile - 1) / kTile;
+#pragma unroll 1
+    for (uint32_t tile = pr.lo / kTile + blockIdx.x; tile < t1; tile += gridDim.x)
+        encode_fwd_tile<POINTS, TV>(p, recs, rays_o, rays_d, table, offsets, enc_tiles, gtable, loss_scale, pr, nparts, tile);
+}
+
 // ------------------------------------------------------------------------------------------------
 // encode backward: scatter the (loss-scaled, fp16) feature gradients (the TV gradient is added by the forward kernel).
 // L2 atomic throughput bounds this kernel (profiles/r1_ncu_summary.md), so at the coarse levels -- where the
@@ -452,18 +477,17 @@ k_s0_encode_fwd(n2m_s0_params p, const float4* __restrict__ recs, const int32_t*
 // last lane of a run issues the red.global.add.v4.f32.  Fine levels (every lane its own cell) go straight to the atomics.
 // ------------------------------------------------------------------------------------------------
 template <bool SCATTER, bool TV>
-__global__ void __launch_bounds__(kTile)
-k_s0_encode_bwd(n2m_s0_params p, const float4* __restrict__ recs, const int32_t* __restrict__ counters,
+__device__ __forceinline__ void
+encode_bwd_tile(const n2m_s0_params& p, const float4* __restrict__ recs,
                 const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                 const uint8_t* __restrict__ denc_tiles, const TableEntry* __restrict__ table,
-                const int32_t* __restrict__ offsets, float4* __restrict__ gtable, float* __restrict__ loss_scale) {
-    const uint32_t M = (uint32_t)counters[1];
-    const uint32_t tile = blockIdx.x, r = threadIdx.x;
-    if (tile * kTile >= M) return;                       // whole block idle
+                const int32_t* __restrict__ offsets, float4* __restrict__ gtable, float* __restrict__ loss_scale,
+                const PartRange pr, uint32_t tile) {
+    const uint32_t r = threadIdx.x;
     const uint32_t lane = r & 31;
     const uint32_t j = tile * kTile + r;
     Sample s;
-    bool active = j < M;
+    bool active = j >= pr.lo && j < pr.hi;
     if (active) {
         s = sample_of(recs[j], rays_o, rays_d, p);
         active = !((s.u < 0 || s.u > 1) || (s.v < 0 || s.v > 1) || (s.w < 0 || s.w > 1));
@@ -564,6 +588,28 @@ k_s0_encode_bwd(n2m_s0_params p, const float4* __restrict__ recs, const int32_t*
     }
 }
 
+// LOOP = false: the grid covers every tile of the slab (whole-batch launch), one tile per block, straight-line code
+// (measured 10 us faster than the looping form); LOOP = true: grid-stride over the part's tiles.
+template <bool SCATTER, bool TV, bool LOOP>
+__global__ void __launch_bounds__(kTile)
+k_s0_encode_bwd(n2m_s0_params p, const float4* __restrict__ recs, const int32_t* __restrict__ counters,
+                const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                const uint8_t* __restrict__ denc_tiles, const TableEntry* __restrict__ table,
+                const int32_t* __restrict__ offsets, float4* __restrict__ gtable, float* __restrict__ loss_scale,
+                uint32_t part, uint32_t nparts) {
+    const PartRange pr = part_range(counters, part, nparts);
+    if (pr.hi <= pr.lo) return;
+    const uint32_t t1 = (pr.hi + kTile - 1) / kTile;
+    if (!LOOP) {
+        const uint32_t tile = pr.lo / kTile + blockIdx.x;
+        if (tile < t1) encode_bwd_tile<SCATTER, TV>(p, recs, rays_o, rays_d, denc_tiles, table, offsets, gtable, loss_scale, pr, tile);
+        return;
+    }
+#pragma unroll 1
+    for (uint32_t tile = pr.lo / kTile + blockIdx.x; tile < t1; tile += gridDim.x)
+        encode_bwd_tile<SCATTER, TV>(p, recs, rays_o, rays_d, denc_tiles, table, offsets, gtable, loss_scale, pr, tile);
+}
+
 // ------------------------------------------------------------------------------------------------
 // composite forward + loss + composite backward: one WARP per ray.
 // The reference walks each ray sequentially in one thread (raymarching.cu:541-568, 651-693); here the
@@ -593,10 +639,11 @@ k_s0_composite_loss(n2m_s0_params p, const float4* __restrict__ out, const float
                     const int32_t* __restrict__ rays, const int32_t* __restrict__ counters, uint32_t N,
                     const float* __restrict__ gt, const float* __restrict__ bg, const float* __restrict__ loss_scale,
                     float4* __restrict__ dout, float* __restrict__ image, float* __restrict__ weights_sum,
-                    float* __restrict__ depth, float* __restrict__ loss_out) {
-    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+                    float* __restrict__ depth, float* __restrict__ loss_out, uint32_t ray_lo, uint32_t ray_hi) {
+    // rays [ray_lo, ray_hi) of the N-ray batch (a part of the batch, n2m_common.cuh part_range); all means stay over N
+    const uint32_t n = ray_lo + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const uint32_t lane = threadIdx.x & 31;
-    if (n >= N) return;
+    if (n >= ray_hi) return;
     const uint32_t M = (uint32_t)counters[1];
     const uint32_t off = rays[2 * n], cnt = rays[2 * n + 1];
     const bool live = cnt != 0 && off + cnt <= M;
@@ -779,6 +826,12 @@ using namespace n2m;
 static bool g_serial_march = false;
 static int g_tv_mode = 0;            // TV gradient: 0 = inside the scatter kernel, 1 = inside the gather kernel, 2 = own launch (n2m_s0_tv)
 
+// blocks for one part's gather / scatter launch: the part's expected share of the sample slab plus one boundary tile
+// (the kernels are grid-stride over the part's tiles, so an unbalanced part is still covered)
+static inline uint32_t part_grid(uint32_t Mcap, uint32_t nparts) {
+    return nparts <= 1 ? Mcap / kTile : div_up(Mcap / kTile, nparts) + 1;
+}
+
 extern "C" {
 
 /* test hook: 1 = one-thread-per-ray sequential marcher (the reference's structure), 0 = warp-per-ray (default) */
@@ -786,6 +839,20 @@ int n2m_s0_set_serial_march(int on) { g_serial_march = on != 0; return 0; }
 /* tuning hook: TV gradient evaluated 0 = by the backward scatter kernel, 1 = by the forward gather kernel, 2 = by its own
  * launch n2m_s0_tv (which the host overlaps with the tensor-core MLP kernels on a forked stream) */
 int n2m_s0_set_tv_mode(int mode) { g_tv_mode = mode; return 0; }
+/* tuning hook: preferred shared-memory carve-out (percent of the SM's unified L1/shared storage, -1 = driver default) of the
+ * gather / scatter / composite kernels.  An SM runs one carve-out configuration at a time: kernels that want the default
+ * (L1-heavy) split cannot be co-resident with the tensor-core MLP kernels, which need 79-140 KB of shared memory. */
+int n2m_s0_set_gather_carveout(int percent) {
+    cudaError_t e = cudaSuccess;
+#define N2M_CARVE(K) if (e == cudaSuccess) e = cudaFuncSetAttribute(K, cudaFuncAttributePreferredSharedMemoryCarveout, percent)
+    N2M_CARVE((k_s0_encode_fwd<false, false>)); N2M_CARVE((k_s0_encode_fwd<false, true>)); N2M_CARVE((k_s0_encode_fwd<true, false>));
+    N2M_CARVE((k_s0_encode_bwd<true, true, false>)); N2M_CARVE((k_s0_encode_bwd<true, false, false>)); N2M_CARVE((k_s0_encode_bwd<false, true, false>));
+    N2M_CARVE((k_s0_encode_bwd<true, true, true>)); N2M_CARVE((k_s0_encode_bwd<true, false, true>));
+    N2M_CARVE(k_s0_composite_loss); N2M_CARVE(k_s0_count_warp); N2M_CARVE(k_s0_records);
+#undef N2M_CARVE
+    if (e != cudaSuccess) return fail("s0_set_gather_carveout", cudaGetErrorString(e));
+    return 0;
+}
 
 int n2m_s0_pack_tables(const float* emb_density, const float* emb_color, uint32_t rows, void* table, void* color_master,
                        n2m_stream_t stream) {
@@ -832,22 +899,30 @@ int n2m_s0_march(const n2m_s0_params* p, const float* rays_o, const float* rays_
     return check_launch("s0_march(records)");
 }
 
-int n2m_s0_encode_fwd(const n2m_s0_params* p, const void* recs, const int32_t* counters, uint32_t Mcap,
-                      const float* rays_o, const float* rays_d, const void* table, const int32_t* offsets, void* enc_tiles,
-                      void* gtable, const float* loss_scale, n2m_stream_t stream) {
+int n2m_s0_encode_fwd_part(const n2m_s0_params* p, const void* recs, const int32_t* counters, uint32_t Mcap,
+                           const float* rays_o, const float* rays_d, const void* table, const int32_t* offsets, void* enc_tiles,
+                           void* gtable, const float* loss_scale, uint32_t part, uint32_t nparts, n2m_stream_t stream) {
     N2M_REQUIRE(p && recs && counters && rays_o && rays_d && table && offsets && enc_tiles, "s0_encode_fwd", "null pointer");
     N2M_REQUIRE(!gtable || loss_scale, "s0_encode_fwd", "gtable given but loss_scale null");
     N2M_REQUIRE(p->num_levels == kLevels, "s0_encode_fwd", "fused path supports num_levels == 16");
     N2M_REQUIRE(Mcap % kTile == 0 && Mcap > 0, "s0_encode_fwd", "Mcap must be a positive multiple of 128");
+    N2M_REQUIRE(valid_parts(part, nparts), "s0_encode_fwd", "nparts must be 1, 2, 4 or 8 and part < nparts");
     if (g_tv_mode == 1 && gtable && p->lambda_tv > 0)
-        k_s0_encode_fwd<false, true><<<Mcap / kTile, kTile, 0, as_stream(stream)>>>(*p, static_cast<const float4*>(recs), counters, rays_o, rays_d,
+        k_s0_encode_fwd<false, true><<<part_grid(Mcap, nparts), kTile, 0, as_stream(stream)>>>(*p, static_cast<const float4*>(recs), counters, rays_o, rays_d,
                                                                                    static_cast<const TableEntry*>(table), offsets,
-                                                                                   static_cast<uint8_t*>(enc_tiles), static_cast<float4*>(gtable), loss_scale);
+                                                                                   static_cast<uint8_t*>(enc_tiles), static_cast<float4*>(gtable), loss_scale,
+                                                                                   part, nparts);
     else
-        k_s0_encode_fwd<false, false><<<Mcap / kTile, kTile, 0, as_stream(stream)>>>(*p, static_cast<const float4*>(recs), counters, rays_o, rays_d,
+        k_s0_encode_fwd<false, false><<<part_grid(Mcap, nparts), kTile, 0, as_stream(stream)>>>(*p, static_cast<const float4*>(recs), counters, rays_o, rays_d,
                                                                                     static_cast<const TableEntry*>(table), offsets,
-                                                                                    static_cast<uint8_t*>(enc_tiles), nullptr, nullptr);
+                                                                                    static_cast<uint8_t*>(enc_tiles), nullptr, nullptr, part, nparts);
     return check_launch("s0_encode_fwd");
+}
+
+int n2m_s0_encode_fwd(const n2m_s0_params* p, const void* recs, const int32_t* counters, uint32_t Mcap,
+                      const float* rays_o, const float* rays_d, const void* table, const int32_t* offsets, void* enc_tiles,
+                      void* gtable, const float* loss_scale, n2m_stream_t stream) {
+    return n2m_s0_encode_fwd_part(p, recs, counters, Mcap, rays_o, rays_d, table, offsets, enc_tiles, gtable, loss_scale, 0, 1, stream);
 }
 
 int n2m_s0_encode_points(const n2m_s0_params* p, const float* xyz, const float* dirs, const int32_t* counters, uint32_t Pcap,
@@ -857,7 +932,7 @@ int n2m_s0_encode_points(const n2m_s0_params* p, const float* xyz, const float* 
     N2M_REQUIRE(Pcap % kTile == 0 && Pcap > 0, "s0_encode_points", "Pcap must be a positive multiple of 128");
     k_s0_encode_fwd<true, false><<<Pcap / kTile, kTile, 0, as_stream(stream)>>>(*p, nullptr, counters, xyz, dirs,
                                                                         static_cast<const TableEntry*>(table), offsets,
-                                                                        static_cast<uint8_t*>(enc_tiles), nullptr, nullptr);
+                                                                        static_cast<uint8_t*>(enc_tiles), nullptr, nullptr, 0, 1);
     return check_launch("s0_encode_points");
 }
 
@@ -884,21 +959,33 @@ int n2m_s0_packbits_dev(const float* grid, uint32_t nbytes, const float* mean_de
     return check_launch("s0_packbits_dev");
 }
 
-int n2m_s0_encode_bwd(const n2m_s0_params* p, const void* recs, const int32_t* counters, uint32_t Mcap,
-                      const float* rays_o, const float* rays_d, const void* denc_tiles, const void* table,
-                      const int32_t* offsets, void* gtable, const float* loss_scale, n2m_stream_t stream) {
+int n2m_s0_encode_bwd_part(const n2m_s0_params* p, const void* recs, const int32_t* counters, uint32_t Mcap,
+                           const float* rays_o, const float* rays_d, const void* denc_tiles, const void* table,
+                           const int32_t* offsets, void* gtable, const float* loss_scale, uint32_t part, uint32_t nparts,
+                           n2m_stream_t stream) {
     N2M_REQUIRE(p && recs && counters && rays_o && rays_d && denc_tiles && table && offsets && gtable && loss_scale,
                 "s0_encode_bwd", "null pointer");
     N2M_REQUIRE(p->num_levels == kLevels, "s0_encode_bwd", "fused path supports num_levels == 16");
     N2M_REQUIRE(Mcap % kTile == 0 && Mcap > 0, "s0_encode_bwd", "Mcap must be a positive multiple of 128");
+    N2M_REQUIRE(valid_parts(part, nparts), "s0_encode_bwd", "nparts must be 1, 2, 4 or 8 and part < nparts");
     // the TV gradient is added here unless the forward kernel or the stand-alone TV launch does it (g_tv_mode)
 #define N2M_BWD_ARGS *p, static_cast<const float4*>(recs), counters, rays_o, rays_d, static_cast<const uint8_t*>(denc_tiles), \
-                     static_cast<const TableEntry*>(table), offsets, static_cast<float4*>(gtable), const_cast<float*>(loss_scale)
-    if (p->lambda_tv > 0 && g_tv_mode == 0)
-        k_s0_encode_bwd<true, true><<<Mcap / kTile, kTile, 0, as_stream(stream)>>>(N2M_BWD_ARGS);
-    else
-        k_s0_encode_bwd<true, false><<<Mcap / kTile, kTile, 0, as_stream(stream)>>>(N2M_BWD_ARGS);
+                     static_cast<const TableEntry*>(table), offsets, static_cast<float4*>(gtable), const_cast<float*>(loss_scale), part, nparts
+    const bool tv_here = p->lambda_tv > 0 && g_tv_mode == 0;
+    if (nparts == 1) {
+        if (tv_here) k_s0_encode_bwd<true, true, false><<<Mcap / kTile, kTile, 0, as_stream(stream)>>>(N2M_BWD_ARGS);
+        else k_s0_encode_bwd<true, false, false><<<Mcap / kTile, kTile, 0, as_stream(stream)>>>(N2M_BWD_ARGS);
+    } else {
+        if (tv_here) k_s0_encode_bwd<true, true, true><<<part_grid(Mcap, nparts), kTile, 0, as_stream(stream)>>>(N2M_BWD_ARGS);
+        else k_s0_encode_bwd<true, false, true><<<part_grid(Mcap, nparts), kTile, 0, as_stream(stream)>>>(N2M_BWD_ARGS);
+    }
     return check_launch("s0_encode_bwd");
+}
+
+int n2m_s0_encode_bwd(const n2m_s0_params* p, const void* recs, const int32_t* counters, uint32_t Mcap,
+                      const float* rays_o, const float* rays_d, const void* denc_tiles, const void* table,
+                      const int32_t* offsets, void* gtable, const float* loss_scale, n2m_stream_t stream) {
+    return n2m_s0_encode_bwd_part(p, recs, counters, Mcap, rays_o, rays_d, denc_tiles, table, offsets, gtable, loss_scale, 0, 1, stream);
 }
 
 /* stand-alone TV-gradient launch (same arithmetic as inside the scatter kernel); only meaningful with tv mode 2 */
@@ -909,22 +996,34 @@ int n2m_s0_tv(const n2m_s0_params* p, const void* recs, const int32_t* counters,
     N2M_REQUIRE(Mcap % kTile == 0 && Mcap > 0, "s0_tv", "Mcap must be a positive multiple of 128");
     if (!(p->lambda_tv > 0)) return 0;
     const void* denc_tiles = nullptr;
-    k_s0_encode_bwd<false, true><<<Mcap / kTile, kTile, 0, as_stream(stream)>>>(N2M_BWD_ARGS);
+    const uint32_t part = 0, nparts = 1;
+    k_s0_encode_bwd<false, true, false><<<Mcap / kTile, kTile, 0, as_stream(stream)>>>(N2M_BWD_ARGS);
     return check_launch("s0_tv");
+}
+
+int n2m_s0_composite_loss_part(const n2m_s0_params* p, const void* out, const void* recs, const int32_t* rays,
+                               const int32_t* counters, uint32_t N, uint32_t Mcap, const float* gt, const float* bg,
+                               const float* loss_scale, void* dout, float* image, float* weights_sum, float* depth,
+                               float* loss_out, uint32_t part, uint32_t nparts, n2m_stream_t stream) {
+    (void)Mcap;
+    if (N == 0) return 0;
+    N2M_REQUIRE(p && out && recs && rays && counters && gt && bg && loss_scale && dout && image && weights_sum && depth && loss_out,
+                "s0_composite_loss", "null pointer");
+    N2M_REQUIRE(valid_parts(part, nparts), "s0_composite_loss", "nparts must be 1, 2, 4 or 8 and part < nparts");
+    const uint32_t ray_lo = part_first_ray(N, part * kPartSlots / nparts), ray_hi = part_first_ray(N, (part + 1) * kPartSlots / nparts);
+    if (ray_hi == ray_lo) return 0;
+    k_s0_composite_loss<<<div_up((ray_hi - ray_lo) * 32u, 128u), 128, 0, as_stream(stream)>>>(
+        *p, static_cast<const float4*>(out), static_cast<const float4*>(recs), rays, counters, N, gt, bg, loss_scale,
+        static_cast<float4*>(dout), image, weights_sum, depth, loss_out, ray_lo, ray_hi);
+    return check_launch("s0_composite_loss");
 }
 
 int n2m_s0_composite_loss(const n2m_s0_params* p, const void* out, const void* recs, const int32_t* rays,
                           const int32_t* counters, uint32_t N, uint32_t Mcap, const float* gt, const float* bg,
                           const float* loss_scale, void* dout, float* image, float* weights_sum, float* depth,
                           float* loss_out, n2m_stream_t stream) {
-    (void)Mcap;
-    if (N == 0) return 0;
-    N2M_REQUIRE(p && out && recs && rays && counters && gt && bg && loss_scale && dout && image && weights_sum && depth && loss_out,
-                "s0_composite_loss", "null pointer");
-    k_s0_composite_loss<<<div_up(N * 32u, 128u), 128, 0, as_stream(stream)>>>(*p, static_cast<const float4*>(out), static_cast<const float4*>(recs),
-                                                                        rays, counters, N, gt, bg, loss_scale, static_cast<float4*>(dout),
-                                                                        image, weights_sum, depth, loss_out);
-    return check_launch("s0_composite_loss");
+    return n2m_s0_composite_loss_part(p, out, recs, rays, counters, N, Mcap, gt, bg, loss_scale, dout, image, weights_sum, depth,
+                                      loss_out, 0, 1, stream);
 }
 
 }  // extern "C"

@@ -54,6 +54,17 @@ _lib.register({
     "n2m_s0_mlp_bwd": [PP, P, P, P, U, P, P, P, P, P],
     "n2m_s0_encode_bwd": [PP, P, P, U, P, P, P, P, P, P, P, P],
     "n2m_s0_adam": [P, P, P, P, P, U, P, P, P, P, P, P, F, P],
+    "n2m_s0_encode_fwd_part": [PP, P, P, U, P, P, P, P, P, P, P, U, U, P],
+    "n2m_s0_mlp_fwd_part": [PP, P, P, U, P, P, P, U, U, P],
+    "n2m_s0_composite_loss_part": [PP, P, P, P, P, U, U, P, P, P, P, P, P, P, P, U, U, P],
+    "n2m_s0_mlp_bwd_part": [PP, P, P, P, U, P, P, P, P, U, U, P],
+    "n2m_s0_encode_bwd_part": [PP, P, P, U, P, P, P, P, P, P, P, U, U, P],
+    "n2m_s0_adam_head": [P, P, P],
+    "n2m_s0_adam_tables": [P, P, P, P, P, U, P, F, P],
+    "n2m_s0_adam_mlp": [P, P, P, P, P, P, F, P],
+    "n2m_s0_adam_post": [P, P],
+    "n2m_s0_set_prof": [P],
+    "n2m_s0_set_gather_carveout": [I],
 })
 _lib.lib.n2m_s0_wpack_bytes.restype = c_uint32
 _lib.lib.n2m_s0_mlp_param_count.restype = c_uint32
@@ -100,7 +111,7 @@ class _Slot:
         self.gt = torch.zeros(N, 4, device=dev); self.bg = torch.zeros(N, 3, device=dev)
         self.noises = torch.zeros(N, device=dev)
         self.rays = torch.zeros(N, 2, dtype=torch.int32, device=dev)
-        self.counters = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.counters = torch.zeros(16, dtype=torch.int32, device=dev)    # include/n2m_b200_fused.h: [4..12] part boundaries
         self.tbuf = torch.empty(N * max_steps * 2, device=dev)
         self.recs = torch.zeros(Mc, 4, device=dev)
         self.has_alpha = True
@@ -169,6 +180,11 @@ class Stage0Trainer:
         self._fill_params(shading_full=True, gt_has_alpha=True)
         self.tv_overlap = True              # TV gradient as its own launch overlapped with the MLP kernels (tv mode 2)
         self._tv_stream = None
+        self.nparts = 1                     # ray-range parts run as concurrent chains on forked streams (1, 2, 4 or 8)
+        self._part_streams = []
+        self.part_mode = "chains"           # "pipeline": gathers/scatters on one stream, MLPs on a high-priority one; "chains": a stream per part
+        self._mlp_stream = None
+        self._adam_stream = None
         call("n2m_s0_set_tv_mode", 2 if self.tv_overlap else 0)
         self.gtables = [self.gtable]        # PeerAdam adds a second parity (parallel.py)
         self.g_mlps = [self.g_mlp]
@@ -265,34 +281,49 @@ class Stage0Trainer:
         call("n2m_s0_march", self._pp(), ptr(self.rays_o), ptr(self.rays_d), ptr(self.aabb), None, ptr(self.density_bitfield),
              ptr(self.noises), self.N, ptr(self.rays), ptr(self.counters), ptr(self.tbuf), ptr(self.recs), self.Mcap, stream())
 
-    def encode_fwd(self):
-        call("n2m_s0_encode_fwd", self._pp(), ptr(self.recs), ptr(self.counters), self.Mcap, ptr(self.rays_o), ptr(self.rays_d),
-             ptr(self.table), ptr(self.offsets), ptr(self.enc_tiles), ptr(self.gtables[self.parity]), ptr(self.opt_state), stream())
+    def encode_fwd(self, part=0, nparts=1):
+        call("n2m_s0_encode_fwd_part", self._pp(), ptr(self.recs), ptr(self.counters), self.Mcap, ptr(self.rays_o), ptr(self.rays_d),
+             ptr(self.table), ptr(self.offsets), ptr(self.enc_tiles), ptr(self.gtables[self.parity]), ptr(self.opt_state),
+             part, nparts, stream())
 
-    def mlp_fwd(self):
-        call("n2m_s0_mlp_fwd", self._pp(), ptr(self.enc_tiles), ptr(self.counters), self.Mcap, ptr(self.wpack), ptr(self.out),
-             self.loss_acc.data_ptr() + 4, stream())
+    def mlp_fwd(self, part=0, nparts=1):
+        call("n2m_s0_mlp_fwd_part", self._pp(), ptr(self.enc_tiles), ptr(self.counters), self.Mcap, ptr(self.wpack), ptr(self.out),
+             self.loss_acc.data_ptr() + 4, part, nparts, stream())
 
-    def composite_loss(self):
-        call("n2m_s0_composite_loss", self._pp(), ptr(self.out), ptr(self.recs), ptr(self.rays), ptr(self.counters), self.N, self.Mcap,
+    def composite_loss(self, part=0, nparts=1):
+        call("n2m_s0_composite_loss_part", self._pp(), ptr(self.out), ptr(self.recs), ptr(self.rays), ptr(self.counters), self.N, self.Mcap,
              ptr(self.gt), ptr(self.bg), ptr(self.opt_state), ptr(self.dout), ptr(self.image), ptr(self.weights_sum), ptr(self.depth),
-             ptr(self.loss_acc), stream())
+             ptr(self.loss_acc), part, nparts, stream())
 
-    def mlp_bwd(self):
-        call("n2m_s0_mlp_bwd", self._pp(), ptr(self.enc_tiles), ptr(self.dout), ptr(self.counters), self.Mcap, ptr(self.wpack),
-             ptr(self.denc_tiles), ptr(self.g_mlps[self.parity]), ptr(self.opt_state), stream())
+    def mlp_bwd(self, part=0, nparts=1):
+        call("n2m_s0_mlp_bwd_part", self._pp(), ptr(self.enc_tiles), ptr(self.dout), ptr(self.counters), self.Mcap, ptr(self.wpack),
+             ptr(self.denc_tiles), ptr(self.g_mlps[self.parity]), ptr(self.opt_state), part, nparts, stream())
 
-    def encode_bwd(self):
-        call("n2m_s0_encode_bwd", self._pp(), ptr(self.recs), ptr(self.counters), self.Mcap, ptr(self.rays_o), ptr(self.rays_d),
-             ptr(self.denc_tiles), ptr(self.table), ptr(self.offsets), ptr(self.gtables[self.parity]), ptr(self.opt_state), stream())
+    def encode_bwd(self, part=0, nparts=1):
+        call("n2m_s0_encode_bwd_part", self._pp(), ptr(self.recs), ptr(self.counters), self.Mcap, ptr(self.rays_o), ptr(self.rays_d),
+             ptr(self.denc_tiles), ptr(self.table), ptr(self.offsets), ptr(self.gtables[self.parity]), ptr(self.opt_state),
+             part, nparts, stream())
 
     def tv(self):
         call("n2m_s0_tv", self._pp(), ptr(self.recs), ptr(self.counters), self.Mcap, ptr(self.rays_o), ptr(self.rays_d),
              ptr(self.table), ptr(self.offsets), ptr(self.gtables[self.parity]), ptr(self.opt_state), stream())
 
     def adam(self):
-        call("n2m_s0_adam", ptr(self.table), ptr(self.color_master), ptr(self.gtable), ptr(self.m_table), ptr(self.v_table), self.rows,
-             ptr(self.mlp), ptr(self.g_mlp), ptr(self.m_mlp), ptr(self.v_mlp), ptr(self.wpack), ptr(self.opt_state), self.cfg.eps, stream())
+        """Optimizer stage: head -> [table rows || MLP parameters + weight repack] -> GradScaler update.  The MLP branch
+        (three tiny launches) runs on a forked stream underneath the 0.7 GB table sweep."""
+        main = torch.cuda.current_stream()
+        call("n2m_s0_adam_head", ptr(self.g_mlp), ptr(self.opt_state), stream())
+        if self._adam_stream is None:
+            self._adam_stream = torch.cuda.Stream(device=self.device)
+        side = self._adam_stream
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            call("n2m_s0_adam_mlp", ptr(self.mlp), ptr(self.g_mlp), ptr(self.m_mlp), ptr(self.v_mlp), ptr(self.wpack),
+                 ptr(self.opt_state), self.cfg.eps, stream())
+        call("n2m_s0_adam_tables", ptr(self.table), ptr(self.color_master), ptr(self.gtable), ptr(self.m_table), ptr(self.v_table),
+             self.rows, ptr(self.opt_state), self.cfg.eps, stream())
+        main.wait_stream(side)
+        call("n2m_s0_adam_post", ptr(self.opt_state), stream())
 
     def forward_backward(self):
         """march -> encode -> MLP -> composite+loss -> MLP backward -> scatter(+TV); gradients stay in
@@ -301,25 +332,80 @@ class Stage0Trainer:
         self._compute()
 
     def _compute(self):
-        """Everything after the march for the current slot.  With tv_overlap the TV-gradient kernel (memory
-        bound, independent of the MLPs) runs on a forked stream underneath the latency-bound tensor-core MLP
-        kernels and is joined before the scatter."""
+        """Everything after the march for the current slot.
+
+        * `nparts` > 1: the batch is cut into ray-range parts (include/n2m_b200_fused.h "Ray-range parts"); the chain
+          gather -> MLP -> composite -> MLP backward -> scatter of every part runs on its own stream, so the
+          latency-bound tensor-core MLP kernels of one part share the SMs with the memory-bound gather / scatter
+          kernels of another (measured in profiles/overlap_probe.py).
+        * `tv_overlap`: the TV-gradient kernel (memory bound, independent of the MLPs) runs on a forked stream as well.
+        All forks are joined before returning (and they are graph-capturable: fork/join by events only)."""
         self.loss_acc.zero_()
-        self.encode_fwd()
-        fork = self.tv_overlap and self.cfg.lambda_tv > 0
-        if fork:
-            main = torch.cuda.current_stream()
-            if self._tv_stream is None:
-                self._tv_stream = torch.cuda.Stream(device=self.device)
-            self._tv_stream.wait_stream(main)
-            with torch.cuda.stream(self._tv_stream):
-                self.tv()
-        self.mlp_fwd()
-        self.composite_loss()
-        self.mlp_bwd()
-        if fork:
+        main = torch.cuda.current_stream()
+        P_ = int(self.nparts)
+        fork_tv = self.tv_overlap and self.cfg.lambda_tv > 0
+
+        def launch_tv():
+            if fork_tv:
+                if self._tv_stream is None:
+                    self._tv_stream = torch.cuda.Stream(device=self.device)
+                self._tv_stream.wait_stream(main)
+                with torch.cuda.stream(self._tv_stream):
+                    self.tv()
+
+        if P_ <= 1:
+            self.encode_fwd()
+            launch_tv()
+            self.mlp_fwd()
+            self.composite_loss()
+            self.mlp_bwd()
+            if fork_tv:
+                main.wait_stream(self._tv_stream)
+            self.encode_bwd()
+            return
+        if self.part_mode == "pipeline":
+            # two-stream software pipeline: gathers then scatters of all parts in order on this (normal-priority) stream,
+            # MLP forward -> composite -> MLP backward of each part on ONE high-priority stream.  The tensor-core kernels
+            # are few persistent CTAs with long dependent chains: dispatched first (priority) they leave most of every SM
+            # to the gather / scatter blocks of the neighbouring parts, which fill in around them.
+            if self._mlp_stream is None:
+                self._mlp_stream = torch.cuda.Stream(device=self.device, priority=-1)
+            H = self._mlp_stream
+            H.wait_stream(main)
+            done = []
+            for k in range(P_):
+                self.encode_fwd(k, P_)
+                ev = torch.cuda.Event(); ev.record(main)
+                with torch.cuda.stream(H):
+                    H.wait_event(ev)
+                    self.mlp_fwd(k, P_)
+                    self.composite_loss(k, P_)
+                    self.mlp_bwd(k, P_)
+                    evb = torch.cuda.Event(); evb.record(H)
+                    done.append(evb)
+            launch_tv()                      # behind the gathers: fills the wait for the first MLP chain
+            for k in range(P_):
+                main.wait_event(done[k])
+                self.encode_bwd(k, P_)
+        else:
+            # independent chains, one stream per part
+            launch_tv()
+            while len(self._part_streams) < P_ - 1:
+                self._part_streams.append(torch.cuda.Stream(device=self.device))
+            streams = [main] + self._part_streams[:P_ - 1]
+            for st in streams[1:]:
+                st.wait_stream(main)
+            for k, st in enumerate(streams):
+                with torch.cuda.stream(st):
+                    self.encode_fwd(k, P_)
+                    self.mlp_fwd(k, P_)
+                    self.composite_loss(k, P_)
+                    self.mlp_bwd(k, P_)
+                    self.encode_bwd(k, P_)
+            for st in streams[1:]:
+                main.wait_stream(st)
+        if fork_tv:
             main.wait_stream(self._tv_stream)
-        self.encode_bwd()
 
     def _step_body(self):
         self.forward_backward()
@@ -334,7 +420,8 @@ class Stage0Trainer:
         elif name in ("adam", "peer_adam"):
             key = (name, self.parity)
         else:
-            key = (name, self.cur, self.parity, int(self.params.shading_full), int(self.params.gt_has_alpha))
+            key = (name, self.cur, self.parity, int(self.params.shading_full), int(self.params.gt_has_alpha), int(self.nparts),
+                   bool(self.tv_overlap), self.part_mode)
         g = self._graphs.get(key)
         if g is None:
             g = torch.cuda.CUDAGraph()

@@ -113,7 +113,7 @@ class _GridEncode(Function):
         _, ge = backends()
         inputs, embeddings, offsets = ctx.saved_tensors
         B, D, C, L, S, H = ctx.dims
-        grad = grad.view(B, L, C).permute(1, 0, 2).contiguous()
+        grad = grad.reshape(B, L, C).permute(1, 0, 2).contiguous()
         gemb = torch.zeros_like(embeddings)
         ge.grid_encode_backward(grad, inputs, embeddings, offsets, gemb, B, D, C, L, L, S, H, None, None, 0, False, 0)
         return None, gemb, None, None, None

@@ -293,3 +293,49 @@ def test_render_equals_training_forward():
     img2, ws2, _ = tr.render(ro2, rd2, bg_color=1.0)
     assert img2.shape == (N + 10, 3) and torch.equal(img2[:10], img2[N:])
     assert torch.isfinite(img2).all()
+
+
+@pytest.mark.parametrize("nparts", [2, 4, 8])
+def test_ray_range_parts_equal_whole_batch(nparts):
+    """include/n2m_b200_fused.h "Ray-range parts": the per-part chains (concurrent streams, boundary tiles computed by
+    both neighbours with row masks) give the same forward values exactly and the same loss / gradients up to fp32
+    atomic summation order."""
+    tr, b = make()
+    stage(tr, b)
+    tr.forward_backward()
+    torch.cuda.synchronize()
+    M = int(tr.counters[1].item())
+    bounds = tr.counters[4:13].cpu().tolist()
+    assert bounds[0] == 0 and bounds[8] == M and all(bounds[i] <= bounds[i + 1] for i in range(8))
+    for e in range(8):
+        assert bounds[e] == int(tr.rays[N * e // 8, 0].item())
+    assert any(x % 128 for x in bounds[1:8])                 # boundaries really fall inside tiles
+    ref = dict(out=tr.out[:M].clone(), dout=tr.dout[:M].clone(), image=tr.image.clone(), ws=tr.weights_sum.clone(),
+               loss=tr.read_loss(), enc=untile(tr.enc_tiles, M), denc=untile(tr.denc_tiles, M))
+    g_ref = tr.export_reference_grads()
+    tr.gtable.zero_(); tr.g_mlp.zero_()
+    tr.enc_tiles.zero_(); tr.denc_tiles.zero_(); tr.out.zero_(); tr.dout.zero_()
+    tr.nparts = nparts
+    tr.forward_backward()
+    torch.cuda.synchronize()
+    assert torch.equal(untile(tr.enc_tiles, M), ref["enc"])
+    assert torch.equal(tr.out[:M], ref["out"])
+    assert torch.equal(tr.image, ref["image"]) and torch.equal(tr.weights_sum, ref["ws"])
+    assert torch.equal(tr.dout[:M], ref["dout"])
+    assert torch.equal(untile(tr.denc_tiles, M), ref["denc"])
+    assert abs(tr.read_loss() - ref["loss"]) <= 1e-5 * abs(ref["loss"])
+    g = tr.export_reference_grads()
+    for name in g_ref:
+        a, r = g[name].double(), g_ref[name].double()
+        assert (a - r).abs().max().item() <= 1e-4 * r.abs().max().item() + 1e-12, name
+    # and a graph-captured multi-stream step trains like the single-stream one
+    losses = []
+    for P_ in (1, nparts):
+        t2, b2 = make(seed=1)
+        t2.nparts = P_
+        ls = []
+        for it in range(3):
+            t2.step(b2["ro"], b2["rd"], b2["gt"], b2["bg"], b2["noises"], use_graph=True)
+            ls.append(t2.read_loss())
+        losses.append(ls)
+    assert np.allclose(losses[0], losses[1], rtol=1e-3), losses
