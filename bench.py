@@ -45,32 +45,71 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md recipe).  NVML is polled in-process about every
+    millisecond (a timed region of a few dozen sub-millisecond steps is shorter than one `nvidia-smi -lms 100` period); if NVML
+    cannot be loaded the nvidia-smi loop is the fallback."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.sm, self.mx, self.reasons, self.proc = index, [], [], set(), None
+        self._stop_evt = threading.Event()
+        self._nv = None
+        try:                                   # NVML start-up (tens of ms) happens here, before the timed region
+            import pynvml as nv
+            nv.nvmlInit()
+            self._h = nv.nvmlDeviceGetHandleByIndex(index)
+            self.mx.append(int(nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM)))
+            self._nv = nv
+        except Exception:
+            self._nv = None
 
-    def run(self):
+    def _run_nvml(self):
+        nv, h = self._nv, self._h
+        if nv is None:
+            raise RuntimeError("NVML unavailable")
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop_evt.is_set():
+            self.sm.append(int(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            mask = int(get_reasons(h))
+            for bit, name in self.REASONS.items():
+                if mask & bit:
+                    self.reasons.add(name)
+            time.sleep(0.001)
+
+    def _run_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                      "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+        for line in self.proc.stdout:
+            r = [x.strip() for x in line.split(",")]
+            if r and r[0].isdigit():
+                self.sm.append(int(r[0]))
+            if len(r) > 1 and r[1].isdigit():
+                self.mx.append(int(r[1]))
+            for i in range(4):
+                if len(r) >= 6 and r[2 + i].lower().startswith("active"):
+                    self.reasons.add(names[i])
+
+    def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
-            for line in self.proc.stdout:
-                self.rows.append([x.strip() for x in line.split(",")])
+            self._run_nvml()
         except Exception:
-            pass
+            try:
+                self._run_smi()
+            except Exception:
+                pass
 
     def stop(self):
+        self._stop_evt.set()
         if self.proc:
             self.proc.terminate()
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+        self.join(timeout=2.0)
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(sm)}
 
 
 def make_batches(n_batches, seed, pin):
