@@ -55,6 +55,7 @@ typedef struct {
     float lambda_mask;
     float lambda_specular;
     float lambda_tv;
+    float lambda_entropy;   /* utils.py:728-733: entropy of the per-sample weights and of weights_sum (0 = off) */
     uint32_t contract;
     uint32_t max_steps;
     uint32_t cascades;
@@ -136,7 +137,9 @@ int n2m_s0_mlp_fwd(const n2m_s0_params* p, const void* enc_tiles, const int32_t*
 
 /* per ray: composite, loss, composite backward.  gt [N,4] (rgba) or [N,3]; bg [N,3].
  * dout [Mcap] float4 {dL/dsigma, dL/dr, dL/dg, dL/db} * loss_scale (zero beyond each ray's break).
- * loss_out float[4]: [0] += sum_rays per-ray loss / N, [1] += mask term; image/ws/depth [N] outputs. */
+ * loss_out float[4]: [0] += sum_rays per-ray loss / N (rgb + mask + ray-level entropy), [1] is the MLP forward's sum |spec|^2,
+ * [2] += sum of H(weights_k) over the weights the compositor touched, [3] += their count (lambda_entropy > 0 only);
+ * image/ws/depth [N] outputs. */
 int n2m_s0_composite_loss(const n2m_s0_params* p, const void* out, const void* recs, const int32_t* rays,
                           const int32_t* counters, uint32_t N, uint32_t Mcap, const float* gt, const float* bg,
                           const float* loss_scale, void* dout, float* image, float* weights_sum, float* depth,

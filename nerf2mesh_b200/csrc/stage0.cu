@@ -634,6 +634,14 @@ __device__ __forceinline__ float warp_incl_scan_mul(float v, uint32_t lane) {
     return v;
 }
 
+// binary entropy in bits of w clamped to [1e-5, 1 - 1e-5] and its derivative (zero where the clamp is active), utils.py:729-732
+__device__ __forceinline__ float entropy_bits(float w, float& dH) {
+    const float wc = fminf(fmaxf(w, 1e-5f), 1.0f - 1e-5f);
+    const float l1 = __log2f(wc), l0 = __log2f(1.0f - wc);
+    dH = (w > 1e-5f && w < 1.0f - 1e-5f) ? l0 - l1 : 0.f;
+    return -wc * l1 - (1.0f - wc) * l0;
+}
+
 __global__ void __launch_bounds__(128)
 k_s0_composite_loss(n2m_s0_params p, const float4* __restrict__ out, const float4* __restrict__ recs,
                     const int32_t* __restrict__ rays, const int32_t* __restrict__ counters, uint32_t N,
@@ -651,6 +659,8 @@ k_s0_composite_loss(n2m_s0_params p, const float4* __restrict__ out, const float
     // ---- forward ----
     float T_in = 1.0f, r = 0, g = 0, b = 0, ws = 0, d = 0;
     uint32_t n_used = 0;                 // samples up to and including the one that crossed T_thresh
+    const bool ent = p.lambda_entropy > 0.f;
+    float ent_sum = 0.f;                 // per lane: entropy of the weights this ray's loop touched
     if (live) {
         for (uint32_t base = 0; base < cnt; base += 32) {
             const uint32_t k = base + lane;
@@ -667,6 +677,7 @@ k_s0_composite_loss(n2m_s0_params p, const float4* __restrict__ out, const float
             const float w = use ? alpha * Tpre : 0.f;
             r += warp_sum(w * o.y); g += warp_sum(w * o.z); b += warp_sum(w * o.w);
             ws += warp_sum(w); d += warp_sum(w * rc.z);
+            if (ent) { float dH; ent_sum += use ? entropy_bits(w, dH) : 0.f; }
             n_used = base + min(last + 1u, cnt - base);
             if (stop) break;
             T_in = __shfl_sync(0xffffffffu, Tpost, 31);
@@ -695,6 +706,18 @@ k_s0_composite_loss(n2m_s0_params p, const float4* __restrict__ out, const float
         const float em = ws - mask;
         my_loss += p.lambda_mask * em * em;
         gws += sc * p.lambda_mask * 2.0f * em;
+    }
+    // entropy regulariser (utils.py:728-733): lambda * (mean_k H(weights_k) + mean_n H(weights_sum_n)).  The ray-level term
+    // joins this ray's loss; the sample-level sum goes to loss_out[2] (+ the count of touched weights in [3], the untouched
+    // entries of `weights` are 0 and contribute the constant H(1e-5)); gw_scale feeds grad_weights below.
+    float gw_scale = 0.f;
+    if (ent) {
+        float dH2;
+        my_loss += p.lambda_entropy * entropy_bits(ws, dH2);
+        gws += sc * p.lambda_entropy * dH2;
+        gw_scale = M > 0 ? loss_scale[0] * p.lambda_entropy / (float)M : 0.f;
+        ent_sum = warp_sum(ent_sum);
+        if (lane == 0 && live) { atomicAdd(loss_out + 2, ent_sum); atomicAdd(loss_out + 3, (float)n_used); }
     }
     if (lane == 0) {
         image[3 * n] = pr; image[3 * n + 1] = pg; image[3 * n + 2] = pb;
@@ -725,8 +748,11 @@ k_s0_composite_loss(n2m_s0_params p, const float4* __restrict__ out, const float
             if (k < cnt) {
                 float4 gq = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (use) {
+                    // grad_weights_k rides with grad_weights_sum exactly as in raymarching.cu:676
+                    float gwk = 0.f;
+                    if (ent) { float dH; entropy_bits(w, dH); gwk = gw_scale * dH; }
                     gq.x = dtk * (gi0 * (Tpost * o.y - (r - sr)) + gi1 * (Tpost * o.z - (g - sg)) +
-                                  gi2 * (Tpost * o.w - (b - sb)) + gws * (Tpost - (ws - sw)));
+                                  gi2 * (Tpost * o.w - (b - sb)) + (gws + gwk) * (Tpost - (ws - sw)));
                     gq.y = gi0 * w; gq.z = gi1 * w; gq.w = gi2 * w;
                 }
                 dout[off + k] = gq;

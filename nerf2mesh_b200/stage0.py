@@ -26,7 +26,7 @@ from .gridencoder.grid import level_offsets
 
 class S0Params(ctypes.Structure):
     _fields_ = [(n, c_float) for n in ("bound", "grid_bound", "inv_2gb", "dt_gamma", "min_near", "T_thresh", "S",
-                                       "lambda_mask", "lambda_specular", "lambda_tv")] + \
+                                       "lambda_mask", "lambda_specular", "lambda_tv", "lambda_entropy")] + \
                [(n, c_uint32) for n in ("contract", "max_steps", "cascades", "grid_size", "num_levels", "base_res",
                                         "shading_full", "gt_has_alpha")]
 
@@ -82,7 +82,7 @@ class Stage0Config:
 
     def __init__(self, bound=1.0, contract=False, dt_gamma=0.0, max_steps=1024, grid_size=128, min_near=0.05,
                  T_thresh=1e-4, num_levels=16, base_resolution=16, log2_hashmap_size=19, lambda_mask=0.1,
-                 lambda_specular=1e-5, lambda_tv=1e-8, lr=1e-2, eps=1e-15, max_samples=None, num_rays=4096,
+                 lambda_specular=1e-5, lambda_tv=1e-8, lambda_entropy=0.0, lr=1e-2, eps=1e-15, max_samples=None, num_rays=4096,
                  loss_scale=65536.0):
         self.real_bound = float(bound)
         self.contract = bool(contract)
@@ -94,6 +94,7 @@ class Stage0Config:
         desired = 2048 * self.bound                             # network.py:66,71
         self.per_level_scale = float(np.exp2(np.log2(desired / base_resolution) / (num_levels - 1)))
         self.lambda_mask, self.lambda_specular, self.lambda_tv = float(lambda_mask), float(lambda_specular), float(lambda_tv)
+        self.lambda_entropy = float(lambda_entropy)          # main.py --lambda_entropy (garden recipe: 1e-3)
         self.lr, self.eps = float(lr), float(eps)
         self.num_rays = int(num_rays)
         # sample capacity of the per-step buffers; rays whose samples do not fit are dropped for the
@@ -212,6 +213,7 @@ class Stage0Trainer:
         p.dt_gamma, p.min_near, p.T_thresh = c.dt_gamma, c.min_near, c.T_thresh
         p.S = float(np.float32(np.log2(c.per_level_scale)))
         p.lambda_mask, p.lambda_specular, p.lambda_tv = c.lambda_mask, c.lambda_specular, c.lambda_tv
+        p.lambda_entropy = c.lambda_entropy
         p.contract, p.max_steps, p.cascades, p.grid_size = int(c.contract), c.max_steps, c.cascade, c.grid_size
         p.num_levels, p.base_res = c.num_levels, c.base_resolution
         p.shading_full, p.gt_has_alpha = int(shading_full), int(gt_has_alpha)
@@ -576,4 +578,11 @@ class Stage0Trainer:
         loss = acc[0]
         if self.params.shading_full and self.cfg.lambda_specular > 0:
             loss += self.cfg.lambda_specular * acc[1] / M
+        if self.cfg.lambda_entropy > 0:
+            # acc[2]: sum of the entropies of the weights the compositor touched; every other entry of `weights` is 0,
+            # clamped to 1e-5 by the loss (utils.py:729)
+            w0 = 1e-5
+            h0 = -w0 * math.log2(w0) - (1 - w0) * math.log2(1 - w0)
+            touched = acc[3]
+            loss += self.cfg.lambda_entropy * ((acc[2] + (M - touched) * h0) / M)
         return loss

@@ -186,6 +186,29 @@ def composite_train(sigmas, rgbs, ts, rays, T_thresh=1e-4):
     return weights, ws, depth, image
 
 
+class _CompositeRef(torch.autograd.Function):
+    """composite_rays_train with the REFERENCE's backward (raymarching.py:248-302 -> raymarching.cu:605-694), which adds
+    grad_weights[k] to grad_weights_sum in sample k's own term instead of differentiating the weights exactly.  Needed
+    whenever a loss touches `weights` (the entropy regulariser); identical to autograd when grad_weights == 0."""
+
+    @staticmethod
+    def forward(ctx, sigmas, rgbs, ts, rays, T_thresh):
+        w, ws, depth, image = R.composite_rays_train_forward(sigmas.detach().numpy(), rgbs.detach().numpy(), ts.numpy(),
+                                                             np.asarray(rays), T_thresh)
+        out = [torch.from_numpy(np.ascontiguousarray(a)) for a in (w, ws, depth, image)]
+        ctx.save_for_backward(sigmas.detach(), rgbs.detach(), ts, *out[1:])
+        ctx.rays, ctx.T = np.asarray(rays), T_thresh
+        return tuple(out)
+
+    @staticmethod
+    def backward(ctx, gw, gws, gd, gi):
+        sigmas, rgbs, ts, ws, depth, image = ctx.saved_tensors
+        g_sig, g_rgb = R.composite_rays_train_backward(gw.numpy(), gws.numpy(), gd.numpy(), gi.numpy(), sigmas.numpy(),
+                                                       rgbs.numpy(), ts.numpy(), ctx.rays, ws.numpy(), depth.numpy(),
+                                                       image.numpy(), ctx.T)
+        return torch.from_numpy(g_sig), torch.from_numpy(g_rgb), None, None, None
+
+
 # ------------------------------------------------------------------------------------------------
 # one train step
 # ------------------------------------------------------------------------------------------------
@@ -200,7 +223,10 @@ def render_train(field, rays_o, rays_d, bits, cfg, noises, bg_color, shading="fu
     xyzs = torch.from_numpy(xyzs); dirs = torch.from_numpy(dirs); ts = torch.from_numpy(ts)
     dirs = dirs / torch.sqrt(torch.clamp((dirs * dirs).sum(-1, keepdim=True), min=1e-20))      # safe_normalize
     sigmas, rgbs, specs = field(xyzs, dirs, shading, amp)
-    weights, ws, depth, image = composite_train(sigmas, rgbs.float(), ts, rays, cfg.get("T_thresh", 1e-4))
+    if cfg.get("ref_composite", False):
+        weights, ws, depth, image = _CompositeRef.apply(sigmas.float(), rgbs.float(), ts, rays, cfg.get("T_thresh", 1e-4))
+    else:
+        weights, ws, depth, image = composite_train(sigmas, rgbs.float(), ts, rays, cfg.get("T_thresh", 1e-4))
     image = image + (1 - ws).unsqueeze(-1) * bg_color
     return dict(image=image, weights_sum=ws, depth=depth, weights=weights, xyzs=xyzs, dirs=dirs, ts=ts, rays=rays,
                 sigmas=sigmas, rgbs=rgbs, speculars=specs, num_points=xyzs.shape[0])

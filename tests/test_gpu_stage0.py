@@ -43,9 +43,9 @@ def untile(t, M):
     return x[:M].float()
 
 
-def oracle_field(tr):
+def oracle_field(tr, bound=1.0):
     from oracle import train_oracle as T
-    f = T.OracleField(1.0)
+    f = T.OracleField(bound)
     st = tr.export_reference_state()
     with torch.no_grad():
         f.encoder.embeddings.copy_(st["encoder.embeddings"].cpu())
@@ -339,3 +339,94 @@ def test_ray_range_parts_equal_whole_batch(nparts):
             ls.append(t2.read_loss())
         losses.append(ls)
     assert np.allclose(losses[0], losses[1], rtol=1e-3), losses
+
+
+def _operator_march(tr, Nr):
+    """xyzs, dirs, ts, rays of the operator-level marcher (bit-exact vs the reference kernel, test_gpu_raymarching) on the
+    trainer's staged rays / noises / bitfield."""
+    from nerf2mesh_b200._lib import call, ptr, stream
+    c = tr.cfg
+    nears, fars = rm.near_far_from_aabb(tr.rays_o, tr.rays_d, tr.aabb, c.min_near)
+    counter = torch.zeros(1, dtype=torch.int32, device="cuda"); rays = torch.empty(Nr, 2, dtype=torch.int32, device="cuda")
+    tbuf = torch.empty(Nr * c.max_steps * 2, device="cuda")
+    args = (ptr(tr.rays_o), ptr(tr.rays_d), ptr(tr.density_bitfield), c.real_bound, int(c.contract), c.dt_gamma, c.max_steps, Nr,
+            c.cascade, c.grid_size, ptr(nears), ptr(fars))
+    call("n2m_march_rays_train", *args, None, None, None, ptr(rays), ptr(counter), ptr(tr.noises), ptr(tbuf), stream())
+    M = int(counter.item())
+    xyzs = torch.zeros(M, 3, device="cuda"); dirs = torch.zeros(M, 3, device="cuda"); ts = torch.zeros(M, 2, device="cuda")
+    call("n2m_march_rays_train", *args, ptr(xyzs), ptr(dirs), ptr(ts), ptr(rays), ptr(counter), ptr(tr.noises), ptr(tbuf), stream())
+    torch.cuda.synchronize()
+    return xyzs, dirs, ts, rays, M
+
+
+@pytest.mark.parametrize("name,lambda_entropy", [("lego_converged", 1e-2), ("garden_cascades", 1e-3)])
+def test_entropy_and_cascades_through_the_fused_step(name, lambda_entropy):
+    """The garden recipe's extras through the fused path (scripts/runall_360_outdoor.sh):
+    bound 16 => 5 cascades and a 32768-resolution grid, dt_gamma 1/256, entropy regulariser on weights and weights_sum
+    (utils.py:728-733, with the reference's grad_weights folding, raymarching.cu:676), TV weight x10 outside the unit cube
+    (utils.py:815-821).  Samples are taken from the operator-level marcher (asserted identical to the fused one), everything
+    behind it is checked against the train oracle."""
+    c = cases.march_case(name)
+    Nr = 96
+    cfg = Stage0Config(bound=c["bound"], dt_gamma=c["dt_gamma"], num_rays=Nr, max_samples=Nr * 1024, lambda_entropy=lambda_entropy)
+    assert cfg.cascade == c["C"]
+    tr = Stage0Trainer(cfg, seed=2)
+    tr.set_occupancy(c["bits"])
+    ro, rd = c["rays_o"][:Nr].contiguous(), c["rays_d"][:Nr].contiguous()
+    gt = S.render_bricks(ro, rd, c["bricks"])
+    g = torch.Generator().manual_seed(11)
+    bg = torch.rand(Nr, 3, generator=g)
+    stage(tr, dict(ro=ro, rd=rd, gt=gt, bg=bg, noises=c["noises"][:Nr]))
+    st = tr.export_reference_state()
+    # some opacity, so that rays terminate and the weights spread over (0, 1); |x| reaches `bound`, keep exp() in range
+    st["sigma_net.net.1.weight"] = st["sigma_net.net.1.weight"] * (30.0 if c["bound"] <= 1 else 4.0)
+    tr.load_reference_state(st)
+    tr._fill_params(True, True)
+    tr.forward_backward()
+    torch.cuda.synchronize()
+    M = int(tr.counters[1].item())
+    xyzs, dirs, ts, rays, M_op = _operator_march(tr, Nr)
+    assert M_op == M and tr.counters[2].item() == 0 and M > 1000
+    assert torch.equal(tr.rays, rays) and torch.equal(tr.recs[:M, 2], ts[:, 0]) and torch.equal(tr.recs[:M, 1], ts[:, 1])
+
+    f, T = oracle_field(tr, c["bound"])
+    d = dirs / torch.sqrt(torch.clamp((dirs * dirs).sum(-1, keepdim=True), min=1e-20))
+    sigmas, rgbs, specs = f(xyzs.cpu(), d.cpu(), "full", True)
+    weights, ws, depth, image = T._CompositeRef.apply(sigmas.float(), rgbs.float(), ts.cpu(), rays.cpu().numpy(), 1e-4)
+    image = image + (1 - ws).unsqueeze(-1) * bg
+    out = dict(image=image, weights_sum=ws, weights=weights, speculars=specs)
+    loss = T.train_loss(out, gt, bg, cfg.lambda_mask, cfg.lambda_specular, lambda_entropy=lambda_entropy)
+    loss.backward()
+    assert (tr.out[:M, 0].cpu() - sigmas.detach()).abs().max().item() <= 2e-3 * sigmas.abs().max().item()
+    assert (tr.image.cpu() - image.detach()).abs().max().item() <= 1e-3
+    assert (tr.weights_sum.cpu() - ws.detach()).abs().max().item() <= 1e-3
+    assert 0.05 < ws.mean().item() < 0.99
+    assert abs(tr.read_loss() - loss.item()) <= 1e-3 * abs(loss.item())
+    # gradients; TV on the density table: weight inside the unit cube, 10 x outside when bound > 1
+    from oracle import grid_oracle
+    ref = {"encoder.embeddings": f.encoder.embeddings.grad.clone(), "encoder_color.embeddings": f.encoder_color.embeddings.grad}
+    for nm, _ in MLP_LAYOUT:
+        mod, _, idx, _ = nm.split(".")
+        ref[nm] = getattr(f, mod).net[int(idx)].weight.grad
+    xc = xyzs.cpu()
+    inner = xc.abs().amax(-1) <= 1
+    groups = [(xc, cfg.lambda_tv)] if c["bound"] <= 1 else [(xc[inner], cfg.lambda_tv), (xc[~inner], cfg.lambda_tv * 10)]
+    for pts, lam in groups:
+        if pts.shape[0]:
+            x01 = (pts + c["bound"]) / (2 * c["bound"])
+            ref["encoder.embeddings"] += grid_oracle.grad_total_variation(x01, f.encoder.embeddings.detach(), f.offsets, lam, f.S, f.H).float()
+    gq = tr.export_reference_grads()
+    for nm, r in ref.items():
+        a = gq[nm].cpu().double().flatten(); r = r.double().flatten()
+        scale = r.abs().max().item()
+        assert scale > 0, nm
+        err = (a - r).abs().max().item()
+        cos = torch.dot(a, r) / (a.norm() * r.norm() + 1e-300)
+        assert err <= 3e-2 * scale and cos > 0.999, f"{nm}: err {err:.3e} scale {scale:.3e} cos {cos:.6f}"
+    # the entropy term is really in there: without it the sigma_net gradient differs
+    tr.gtable.zero_(); tr.g_mlp.zero_()
+    tr.cfg.lambda_entropy = 0.0
+    tr._fill_params(True, True)
+    tr.forward_backward()
+    g0 = tr.export_reference_grads()["sigma_net.net.0.weight"].cpu()
+    assert (g0 - gq["sigma_net.net.0.weight"].cpu()).abs().max().item() > 1e-3 * g0.abs().max().item()

@@ -49,3 +49,36 @@ def test_train_oracle_step_decreases_loss():
     bg = torch.rand(48, 3)
     losses = [T.train_step(f, opt, ro, rd, gt, bits, cfg, torch.zeros(48), bg)[0] for _ in range(3)]
     assert losses[-1] < losses[0]
+
+
+def test_reference_backward_compositor_matches_autograd_without_weight_losses():
+    """oracle/train_oracle._CompositeRef (reference backward formula, used when the entropy regulariser is on) gives the
+    autograd gradients of the padded-tensor compositor as long as no loss touches `weights`; with lambda_entropy > 0 it
+    follows the reference's folding of grad_weights (raymarching.cu:676) and therefore differs from autograd."""
+    from nerf2mesh_b200 import synthetic as S
+    from oracle import train_oracle as T
+    torch.manual_seed(0)
+    ro, rd = cases.rays(24, 1)
+    grid, bits, bricks = S.occupancy_regime("converged")
+    gt = S.render_bricks(ro, rd, bricks)
+    bg = torch.rand(24, 3)
+    grads = {}
+    for ref in (False, True):
+        for lam in (0.0, 1e-2):
+            torch.manual_seed(1)
+            f = T.OracleField(1.0)
+            with torch.no_grad():
+                f.sigma_net.net[1].weight.mul_(30.0)           # some opacity, so that rays terminate and weights spread
+            cfg = dict(bound=1.0, C=1, H=128, ref_composite=ref)
+            out = T.render_train(f, ro, rd, bits, cfg, torch.zeros(24), bg, "full", True)
+            loss = T.train_loss(out, gt, bg, 0.1, 1e-5, lambda_entropy=lam)
+            loss.backward()
+            grads[(ref, lam)] = (loss.item(), f.sigma_net.net[0].weight.grad.clone(), f.color_net.net[0].weight.grad.clone())
+    for i in (1, 2):
+        a, b = grads[(False, 0.0)][i], grads[(True, 0.0)][i]
+        assert (a - b).abs().max() <= 2e-3 * a.abs().max()
+    assert abs(grads[(False, 0.0)][0] - grads[(True, 0.0)][0]) <= 1e-5 * abs(grads[(False, 0.0)][0])
+    assert abs(grads[(False, 1e-2)][0] - grads[(True, 1e-2)][0]) <= 1e-5 * abs(grads[(True, 1e-2)][0])      # same loss value
+    assert grads[(True, 1e-2)][0] > grads[(True, 0.0)][0]
+    d = (grads[(True, 1e-2)][1] - grads[(True, 0.0)][1]).abs().max()
+    assert d > 0                                                                                      # the term reaches sigma_net
