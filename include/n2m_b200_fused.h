@@ -131,6 +131,14 @@ int n2m_s0_grid_update(const void* out, uint32_t count, float decay, float* grid
 int n2m_s0_packbits_dev(const float* grid, uint32_t nbytes, const float* mean_density, float density_thresh, uint8_t* bitfield,
                         n2m_stream_t stream);
 
+/* batch sampling on the device = get_rays (nerf/utils.py:236-290) + the stage-0 training collate (nerf/provider.py:300-331)
+ * for N random (image, pixel) pairs: poses [num_poses,4,4] (device), intrinsics_host float[4] {fx, fy, cx, cy} (HOST),
+ * img_idx / pix_idx int32 [N] (device; pix = j * W + i), images uint8 [num_poses, H, W, C] (device, nullable with gt).
+ * Writes rays_o, rays_d [N,3] (unnormalised directions) and gt [N,C] = pixel / 255.  Indices are not range-checked. */
+int n2m_s0_gen_rays(const float* poses, uint32_t num_poses, const float* intrinsics_host, uint32_t H, uint32_t W,
+                    const int32_t* img_idx, const int32_t* pix_idx, const uint8_t* images, uint32_t C, uint32_t N,
+                    float* rays_o, float* rays_d, float* gt, n2m_stream_t stream);
+
 /* out [Mcap] float4 {sigma, r, g, b}; spec_sq_sum: += sum over samples of |specular|^2 (for the loss value) */
 int n2m_s0_mlp_fwd(const n2m_s0_params* p, const void* enc_tiles, const int32_t* counters, uint32_t Mcap,
                    const void* wpack, void* out, float* spec_sq_sum, n2m_stream_t stream);

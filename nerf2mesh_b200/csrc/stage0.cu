@@ -812,6 +812,34 @@ k_s0_packbits_dev(const float* __restrict__ grid, uint32_t nbytes, const float* 
 }
 
 // ------------------------------------------------------------------------------------------------
+// batch sampling on the device: get_rays (utils.py:236-290) + the training collate of the provider
+// (provider.py:300-331) for random (image, pixel) pairs over a device-resident pose / image set.
+// One thread per ray: pixel centre (+0.5), camera-space direction ((i-cx)/fx, -(j-cy)/fy, -1), rotated by the
+// pose (row-times-R^T == R times column), origin = pose translation, ground truth = images[idx, j, i] / 255.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_s0_gen_rays(const float* __restrict__ poses, float fx, float fy, float cx, float cy, uint32_t W,
+              const int32_t* __restrict__ img_idx, const int32_t* __restrict__ pix_idx, const uint8_t* __restrict__ images,
+              uint32_t HW, uint32_t C, uint32_t N, float* __restrict__ rays_o, float* __restrict__ rays_d, float* __restrict__ gt) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const uint32_t b = (uint32_t)img_idx[n], pix = (uint32_t)pix_idx[n];
+    const float i = __fadd_rn((float)(pix % W), 0.5f), j = __fadd_rn((float)(pix / W), 0.5f);
+    const float x = __fdiv_rn(__fsub_rn(i, cx), fx), y = -__fdiv_rn(__fsub_rn(j, cy), fy), z = -1.0f;
+    const float* P = poses + (size_t)b * 16;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        // fp32 dot product in index order, no FMA contraction (as a reference matmul of a [1,3] row does on CUDA cores)
+        rays_d[3 * n + r] = __fadd_rn(__fadd_rn(__fmul_rn(P[4 * r], x), __fmul_rn(P[4 * r + 1], y)), __fmul_rn(P[4 * r + 2], z));
+        rays_o[3 * n + r] = P[4 * r + 3];
+    }
+    if (gt) {
+        const uint8_t* px = images + ((size_t)b * HW + pix) * C;
+        for (uint32_t c = 0; c < C; ++c) gt[(size_t)n * C + c] = __fdiv_rn((float)px[c], 255.0f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // table (de)interleave
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -983,6 +1011,19 @@ int n2m_s0_packbits_dev(const float* grid, uint32_t nbytes, const float* mean_de
     if (nbytes == 0) return 0;
     k_s0_packbits_dev<<<div_up(nbytes, 256u), 256, 0, as_stream(stream)>>>(grid, nbytes, mean_density, density_thresh, bitfield);
     return check_launch("s0_packbits_dev");
+}
+
+int n2m_s0_gen_rays(const float* poses, uint32_t num_poses, const float* intrinsics_host, uint32_t H, uint32_t W,
+                    const int32_t* img_idx, const int32_t* pix_idx, const uint8_t* images, uint32_t C, uint32_t N,
+                    float* rays_o, float* rays_d, float* gt, n2m_stream_t stream) {
+    if (N == 0) return 0;
+    N2M_REQUIRE(poses && intrinsics_host && img_idx && pix_idx && rays_o && rays_d, "s0_gen_rays", "null pointer");
+    N2M_REQUIRE(num_poses > 0 && H > 0 && W > 0, "s0_gen_rays", "empty pose set or image");
+    N2M_REQUIRE(!gt || (images && (C == 3 || C == 4)), "s0_gen_rays", "gt requested without images, or channels not 3 / 4");
+    k_s0_gen_rays<<<div_up(N, 256u), 256, 0, as_stream(stream)>>>(poses, intrinsics_host[0], intrinsics_host[1], intrinsics_host[2],
+                                                                 intrinsics_host[3], W, img_idx, pix_idx, images, H * W, C, N,
+                                                                 rays_o, rays_d, gt);
+    return check_launch("s0_gen_rays");
 }
 
 int n2m_s0_encode_bwd_part(const n2m_s0_params* p, const void* recs, const int32_t* counters, uint32_t Mcap,

@@ -45,6 +45,10 @@ def main(argv=None):
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--update_interval", type=int, default=16)
     ap.add_argument("--diffuse_step", type=int, default=1000)
+    ap.add_argument("--device_dataset", action="store_true",
+                    help="render the training views once into a device-resident uint8 image set and sample the batches with the "
+                         "on-device sampler (nerf2mesh_b200/sampler.py) instead of synthesising every batch on the host")
+    ap.add_argument("--train_res", type=int, default=400, help="resolution of the device-resident training views")
     ap.add_argument("--samples_per_ray", type=int, default=512,
                     help="sample-slab capacity per ray; the cold-start occupancy grid marches far more samples than a converged one")
     args = ap.parse_args(argv)
@@ -61,12 +65,31 @@ def main(argv=None):
     tr.density_grid.zero_()
     g = torch.Generator().manual_seed(args.seed + 1)
 
-    def batch():
-        ro, rd, _, _ = S.sample_rays(poses, intr, 800, 800, args.num_rays, g)
-        gt = S.render_bricks(ro, rd, bricks)
-        bg = torch.rand(args.num_rays, 3, generator=g)
-        noises = torch.rand(args.num_rays, generator=g)
-        return tuple(t.pin_memory() for t in (ro, rd, gt, bg, noises))
+    if args.device_dataset:
+        from .sampler import DeviceRaySampler
+        R = args.train_res
+        bricks_d = tuple(t.to(dev) for t in bricks)
+        intr_t = intr * (R / 800.0)
+        imgs = torch.empty(poses.shape[0], R, R, 4, dtype=torch.uint8, device=dev)
+        for k in range(poses.shape[0]):
+            ro, rd = full_image_rays(poses[k], intr_t, R, R)
+            rgba = S.render_bricks(ro.to(dev), rd.to(dev), bricks_d)
+            imgs[k] = (rgba * 255).round().clamp(0, 255).to(torch.uint8).view(R, R, 4)
+        sampler = DeviceRaySampler(poses, intr_t, R, R, imgs)
+        gd = torch.Generator(device=dev).manual_seed(args.seed + 1)
+
+        def batch():
+            ro, rd, gt = sampler.sample(args.num_rays, generator=gd)
+            bg = torch.rand(args.num_rays, 3, device=dev, generator=gd)
+            noises = torch.rand(args.num_rays, device=dev, generator=gd)
+            return ro, rd, gt, bg, noises
+    else:
+        def batch():
+            ro, rd, _, _ = S.sample_rays(poses, intr, 800, 800, args.num_rays, g)
+            gt = S.render_bricks(ro, rd, bricks)
+            bg = torch.rand(args.num_rays, 3, generator=g)
+            noises = torch.rand(args.num_rays, generator=g)
+            return tuple(t.pin_memory() for t in (ro, rd, gt, bg, noises))
 
     t0 = time.time()
     samples = 0
@@ -95,7 +118,7 @@ def main(argv=None):
         gt_rgb = gt[:, :3] * gt[:, 3:] + (1 - gt[:, 3:])
         img, ws, _ = tr.render(ro.to(dev), rd.to(dev), bg_color=1.0, shading="full" if args.iters > args.diffuse_step else "diffuse")
         vals.append(psnr(img.clamp(0, 1).cpu(), gt_rgb))
-    out = {"iters": args.iters, "train_seconds": train_s, "psnr_views": vals, "psnr_mean": sum(vals) / len(vals), "log": log}
+    out = {"iters": args.iters, "device_dataset": bool(args.device_dataset), "train_seconds": train_s, "psnr_views": vals, "psnr_mean": sum(vals) / len(vals), "log": log}
     print(json.dumps(out))
     return out
 
