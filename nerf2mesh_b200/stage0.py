@@ -465,24 +465,12 @@ class Stage0Trainer:
         if key != (bool(self.params.shading_full), bool(self.params.gt_has_alpha)):
             self._fill_params(*key)
 
+        ev_start = None
         if next_batch is not None:
-            # side stream: stage + march the next batch into the other slot
-            nxt = 1 - self.cur
-            if self._side is None:
-                self._side = torch.cuda.Stream(device=self.device)
-            side = self._side
-            if self._ev_done[nxt] is not None:
-                side.wait_event(self._ev_done[nxt])              # slot `nxt` was last read by the previous step
-            side.wait_stream(main)                               # (and after anything already queued on main, e.g. set_occupancy)
-            keep = self.cur
-            with torch.cuda.stream(side):
-                self.slots[nxt].load(*next_batch)
-                self.cur = nxt
-                self._run("march", self.march, use_graph)
-                self.cur = keep
-                ev = torch.cuda.Event(); ev.record(side)
-                self._ev_march[nxt] = ev
-            self._prefetched = nxt
+            # the prefetch below must come after whatever is already queued on this stream (e.g. set_occupancy), but NOT after
+            # this step's own compute: mark the spot now, enqueue the compute first (the GPU starts on it while the host is
+            # still enqueueing the prefetch -- matters when the caller synchronises every step), the prefetch afterwards
+            ev_start = torch.cuda.Event(); ev_start.record(main)
 
         if not marched:
             self._run("march", self.march, use_graph)
@@ -502,6 +490,25 @@ class Stage0Trainer:
         ev = torch.cuda.Event(); ev.record(main)
         self._ev_done[self.cur] = ev
         self.global_step += 1
+        if next_batch is not None:
+            # side stream: stage + march the next batch into the other slot
+            nxt = 1 - self.cur
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.device)
+            side = self._side
+            if self._ev_done[nxt] is not None:
+                side.wait_event(self._ev_done[nxt])              # slot `nxt` was last read by the previous step
+            side.wait_event(ev_start)
+            keep = self.cur
+            with torch.cuda.stream(side):
+                self.slots[nxt].load(*next_batch)
+                self.cur = nxt
+                self._run("march", self.march, use_graph)
+                self.cur = keep
+                ev = torch.cuda.Event(); ev.record(side)
+                self._ev_march[nxt] = ev
+            self._prefetched = nxt
+
 
     # -------------------------------------------------------------------------------------------
     # density grid / bitfield update and evaluation rendering
