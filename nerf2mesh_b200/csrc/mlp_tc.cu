@@ -592,6 +592,10 @@ k_mlp_bwd(n2m_s0_params p, const uint8_t* __restrict__ enc_tiles, const float4* 
 // accumulators are shared by both groups (one issuing thread => one program order), working columns are
 // per group: 2 x 128 + 240 = 496 TMEM columns.  Shared memory per group shrinks to 76 KB by reusing one 16 KB
 // region for S1|P1 -> dS1|dP1 (written in place over the activations they mask) -> dH.
+// MEASURED (profiles/r1_ncu_summary.md, r1f): 123 us against 104 us for the single-tile kernel -- the groups take turns
+// on the tensor pipe, whose pace for these shapes is set by the shared-memory operand read (59-68 cycles per
+// tcgen05.mma whatever N), so overlapping the (already short) epilogues buys nothing and the extra hand-overs cost.
+// Kept behind n2m_s0_set_mlp_bwd_pipelined(1) with its phase profiler (n2m_s0_set_prof); the default is k_mlp_bwd.
 constexpr uint32_t P_A = 0, P_H2 = 16384, P_H1 = 32768, P_Z = 49152, P_AS2 = 65536, P_DY = 69632, P_GRP = 77824;
 constexpr uint32_t P_BYTES = W_BYTES + 2 * P_GRP + 4096;          // + tail so the last group's G3 operand stays in bounds
 constexpr uint32_t Q_C1 = 256, Q_C2 = 320, Q_S1 = 384, Q_P1 = 416, Q_C3 = 448, Q_S2 = 464, Q_P2 = 480;

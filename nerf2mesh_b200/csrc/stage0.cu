@@ -325,10 +325,10 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 
 // ------------------------------------------------------------------------------------------------
 // encode forward: one block = one 128-sample tile image.
-// Also adds the total-variation gradient of the density features (gridencoder.cu:506-609, called from
-// utils.py:801-823) into gtable: the centre and the three +1 neighbours ARE trilinear corners 0,1,2,4 that
-// were just gathered, so TV costs three extra loads here instead of seven in the backward scatter; it is
-// evaluated once per run of consecutive same-cell lanes (it is identical for every sample of a cell).
+// Template TV (tv mode 1, NOT the default -- it was measured to slow this kernel from 76 to 194 us): also adds the
+// total-variation gradient of the density features (gridencoder.cu:506-609, called from utils.py:801-823) into gtable;
+// the centre and the three +1 neighbours ARE trilinear corners 0,1,2,4 that were just gathered, so TV costs three extra
+// loads here instead of seven; evaluated once per run of consecutive same-cell lanes (identical for every sample of a cell).
 // ------------------------------------------------------------------------------------------------
 // POINTS = false: samples come from the march records (training / eval rendering);
 // POINTS = true : explicit positions xyz [P,3] (rays_o) and optional directions [P,3] (rays_d) -- used for the
@@ -470,7 +470,8 @@ k_s0_encode_fwd(n2m_s0_params p, const float4* __restrict__ recs, const int32_t*
 }
 
 // ------------------------------------------------------------------------------------------------
-// encode backward: scatter the (loss-scaled, fp16) feature gradients (the TV gradient is added by the forward kernel).
+// encode backward: scatter the (loss-scaled, fp16) feature gradients (template SCATTER) and / or add the TV gradient of the
+// density features (template TV; by default TV is its own launch of this kernel, n2m_s0_tv, see g_tv_mode).
 // L2 atomic throughput bounds this kernel (profiles/r1_ncu_summary.md), so at the coarse levels -- where the
 // consecutive samples of a ray (= consecutive lanes) sit in the same lattice cell -- the 8 corner
 // contributions are first summed across each run of same-cell lanes with a segmented warp scan and only the
