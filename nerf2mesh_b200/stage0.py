@@ -248,12 +248,27 @@ class Stage0Trainer:
     def export_reference_state(self):
         ed = torch.empty(self.rows, 1, device=self.device); ec = torch.empty(self.rows, 2, device=self.device)
         call("n2m_s0_unpack_tables", ptr(self.table), ptr(self.color_master), self.rows, ptr(ed), ptr(ec), stream())
+        # the complete stage-0 `NeRFNetwork.state_dict()` key set (renderer.py:92-117, grid.py:135-140, network.py:66-75): loads
+        # into the reference model with strict=True (no individual codes / SDF variance in the default recipes)
         state = {"encoder.embeddings": ed, "encoder_color.embeddings": ec,
+                 "encoder.offsets": self.offsets.clone(), "encoder_color.offsets": self.offsets.clone(),
+                 "aabb_train": self.aabb.clone(), "aabb_infer": self.aabb.clone(),
                  "density_grid": self.density_grid.clone(), "density_bitfield": self.density_bitfield.clone()}
         o = 0
         for name, shp in MLP_LAYOUT:
             n = shp[0] * shp[1]
             state[name] = self.mlp[o:o + n].view(shp).clone(); o += n
+        return state
+
+    def save_reference_checkpoint(self, path, epoch=0, stats=None):
+        """A model-only checkpoint in the schema `Trainer.load_checkpoint` reads (nerf/utils.py:1345-1381, 1423-1470):
+        epoch / global_step / stats / stage / mean_density / model."""
+        mean = getattr(self, "mean_density", None)
+        state = {"epoch": int(epoch), "global_step": int(self.global_step), "stage": 0,
+                 "stats": stats or {"loss": [], "valid_loss": [], "results": [], "checkpoints": [], "best_result": None},
+                 "mean_density": float(mean.item()) if mean is not None else 0.0,
+                 "model": {k: v.cpu() for k, v in self.export_reference_state().items()}}
+        torch.save(state, path)
         return state
 
     def export_reference_grads(self):

@@ -430,3 +430,28 @@ def test_entropy_and_cascades_through_the_fused_step(name, lambda_entropy):
     tr.forward_backward()
     g0 = tr.export_reference_grads()["sigma_net.net.0.weight"].cpu()
     assert (g0 - gq["sigma_net.net.0.weight"].cpu()).abs().max().item() > 1e-3 * g0.abs().max().item()
+
+
+def test_reference_state_dict_and_checkpoint_schema(tmp_path):
+    """export_reference_state() carries exactly the stage-0 NeRFNetwork.state_dict() keys (renderer.py:92-117, grid.py:135-140,
+    network.py:66-75) and the checkpoint has the fields Trainer.load_checkpoint reads (utils.py:1423-1470); round trip."""
+    tr, b = make()
+    st = tr.export_reference_state()
+    expect = {"aabb_train", "aabb_infer", "density_grid", "density_bitfield", "encoder.offsets", "encoder.embeddings",
+              "encoder_color.offsets", "encoder_color.embeddings"} | {n for n, _ in MLP_LAYOUT}
+    assert set(st) == expect
+    assert st["encoder.embeddings"].shape == (tr.rows, 1) and st["encoder_color.embeddings"].shape == (tr.rows, 2)
+    assert st["encoder.offsets"].dtype == torch.int32 and st["encoder.offsets"].numel() == 17 and int(st["encoder.offsets"][-1]) == tr.rows
+    assert st["aabb_train"].tolist() == [-1, -1, -1, 1, 1, 1]
+    assert st["density_grid"].shape == (1, 128 ** 3) and st["density_bitfield"].dtype == torch.uint8
+    stage(tr, b)
+    tr.step(use_graph=False)
+    path = tmp_path / "ngp_stage0_ep0001.pth"
+    tr.save_reference_checkpoint(str(path), epoch=1)
+    ck = torch.load(str(path), weights_only=False)
+    assert {"epoch", "global_step", "stats", "stage", "mean_density", "model"} <= set(ck) and ck["global_step"] == 1 and ck["stage"] == 0
+    t2 = Stage0Trainer(tr.cfg, seed=123)
+    t2.load_reference_state(ck["model"])
+    s2 = t2.export_reference_state()
+    for k, v in tr.export_reference_state().items():
+        assert torch.equal(v, s2[k]), k
