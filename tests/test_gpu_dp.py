@@ -40,7 +40,7 @@ def _worker(rank, world, port, q):
         st = tr.export_reference_state()
         if mode == "peer":
             st["encoder_color.embeddings"] = sync.gather_color_master()
-        out[mode] = {k: v.cpu() for k, v in st.items() if "density" not in k}
+        out[mode] = {k: v.cpu() for k, v in st.items() if "density" not in k and v.is_floating_point() and "aabb" not in k}
         out[mode + "_loss"] = tr.read_loss()
         dist.barrier()
     q.put((rank, out))
