@@ -189,6 +189,15 @@ int n2m_s0_encode_bwd_part(const n2m_s0_params* p, const void* recs, const int32
                            const int32_t* offsets, void* gtable, const float* loss_scale, uint32_t part, uint32_t nparts,
                            n2m_stream_t stream);
 
+/* EXPERIMENTAL (compiled, not yet measured on a GPU): the scatter restricted to hash levels [level_lo, level_hi).  A spread RED
+ * costs 1.40 SM-cycles per lane into a 32 MB table and 2.19 into the 98 MB gradient table whatever its payload
+ * (profiles/redbench.py), so two passes over the samples (levels 0-9, then 10-15: ~48 MB of target rows each) may beat one.  Disjoint
+ * ranges covering 0..16 are equivalent to n2m_s0_encode_bwd_part. */
+int n2m_s0_encode_bwd_levels(const n2m_s0_params* p, const void* recs, const int32_t* counters, uint32_t Mcap,
+                             const float* rays_o, const float* rays_d, const void* denc_tiles, const void* table,
+                             const int32_t* offsets, void* gtable, const float* loss_scale, uint32_t part, uint32_t nparts,
+                             uint32_t level_lo, uint32_t level_hi, n2m_stream_t stream);
+
 /* optimizer state block (device, float[8]): [0] loss_scale, [1] growth_tracker, [2] adam step t,
  * [3] found_inf, [4] lr (host-written each step), [5] 1-beta1^t, [6] sqrt(1-beta2^t), [7] 1/loss_scale.
  * Every `loss_scale` pointer argument above is the base of this block: the kernels read [0] and set [3]

@@ -17,7 +17,7 @@ OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libn2m_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-SOURCES = ["raymarching.cu", "gridencoder.cu", "shencoder.cu", "tc_probe.cu", "stage0.cu", "mlp_tc.cu", "optim.cu", "dp.cu"]
+SOURCES = ["raymarching.cu", "gridencoder.cu", "shencoder.cu", "tc_probe.cu", "red_probe.cu", "stage0.cu", "mlp_tc.cu", "optim.cu", "dp.cu"]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [

@@ -477,13 +477,13 @@ k_s0_encode_fwd(n2m_s0_params p, const float4* __restrict__ recs, const int32_t*
 // contributions are first summed across each run of same-cell lanes with a segmented warp scan and only the
 // last lane of a run issues the red.global.add.v4.f32.  Fine levels (every lane its own cell) go straight to the atomics.
 // ------------------------------------------------------------------------------------------------
-template <bool SCATTER, bool TV>
+template <bool SCATTER, bool TV, bool RANGE = false>
 __device__ __forceinline__ void
 encode_bwd_tile(const n2m_s0_params& p, const float4* __restrict__ recs,
                 const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                 const uint8_t* __restrict__ denc_tiles, const TableEntry* __restrict__ table,
                 const int32_t* __restrict__ offsets, float4* __restrict__ gtable, float* __restrict__ loss_scale,
-                const PartRange pr, uint32_t tile) {
+                const PartRange pr, uint32_t tile, uint32_t level_lo = 0, uint32_t level_hi = kLevels) {
     const uint32_t r = threadIdx.x;
     const uint32_t lane = r & 31;
     const uint32_t j = tile * kTile + r;
@@ -525,7 +525,7 @@ encode_bwd_tile(const n2m_s0_params& p, const float4* __restrict__ recs,
         tvw_lane = active ? lam / 6 * loss_scale[0] : 0.f;
     }
 #pragma unroll 1
-    for (uint32_t l = 0; l < kLevels; ++l) {
+    for (uint32_t l = RANGE ? level_lo : 0u; l < (RANGE ? level_hi : kLevels); ++l) {
         const LevelGeom lg = level_geom(offsets, l, p.S, p.base_res);
         Corners c; uint32_t base[3]; bool hashed; uint32_t left[3];
         corners_of(lg, s.u, s.v, s.w, c, base, hashed, TV ? left : nullptr);
@@ -609,6 +609,27 @@ k_s0_encode_bwd(n2m_s0_params p, const float4* __restrict__ recs, const int32_t*
 #pragma unroll 1
     for (uint32_t tile = pr.lo / kTile + blockIdx.x; tile < t1; tile += gridDim.x)
         encode_bwd_tile<SCATTER, TV>(p, recs, rays_o, rays_d, denc_tiles, table, offsets, gtable, loss_scale, pr, tile);
+}
+
+// Level-range variant of the scatter: only levels [level_lo, level_hi).  profiles/redbench.py: a spread RED costs 1.40 SM-cycles
+// per lane into a 32 MB table, 2.19 into a 98 MB one (the whole gradient table) and 11.5 into a 512 MB one, whatever its
+// payload (4-16 B) -- the L2-resident fraction of the TARGET rows sets the pace.  Two passes over the samples (levels 0-9: 48 MB
+// of rows, levels 10-15: 50 MB) keep each pass's targets closer to L2-resident at the price of reading the 144 B/sample
+// of records + feature gradients twice.  Same arithmetic, same atomics.  Not the default until measured (tuning hook).
+template <bool SCATTER, bool TV>
+__global__ void __launch_bounds__(kTile)
+k_s0_encode_bwd_levels(n2m_s0_params p, const float4* __restrict__ recs, const int32_t* __restrict__ counters,
+                       const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                       const uint8_t* __restrict__ denc_tiles, const TableEntry* __restrict__ table,
+                       const int32_t* __restrict__ offsets, float4* __restrict__ gtable, float* __restrict__ loss_scale,
+                       uint32_t part, uint32_t nparts, uint32_t level_lo, uint32_t level_hi) {
+    const PartRange pr = part_range(counters, part, nparts);
+    if (pr.hi <= pr.lo) return;
+    const uint32_t t1 = (pr.hi + kTile - 1) / kTile;
+#pragma unroll 1
+    for (uint32_t tile = pr.lo / kTile + blockIdx.x; tile < t1; tile += gridDim.x)
+        encode_bwd_tile<SCATTER, TV, true>(p, recs, rays_o, rays_d, denc_tiles, table, offsets, gtable, loss_scale, pr, tile,
+                                           level_lo, level_hi);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1054,6 +1075,27 @@ int n2m_s0_encode_bwd(const n2m_s0_params* p, const void* recs, const int32_t* c
                       const float* rays_o, const float* rays_d, const void* denc_tiles, const void* table,
                       const int32_t* offsets, void* gtable, const float* loss_scale, n2m_stream_t stream) {
     return n2m_s0_encode_bwd_part(p, recs, counters, Mcap, rays_o, rays_d, denc_tiles, table, offsets, gtable, loss_scale, 0, 1, stream);
+}
+
+/* scatter restricted to the hash levels [level_lo, level_hi) (see k_s0_encode_bwd_levels); the union of disjoint ranges that
+ * cover 0..16 equals n2m_s0_encode_bwd_part */
+int n2m_s0_encode_bwd_levels(const n2m_s0_params* p, const void* recs, const int32_t* counters, uint32_t Mcap,
+                             const float* rays_o, const float* rays_d, const void* denc_tiles, const void* table,
+                             const int32_t* offsets, void* gtable, const float* loss_scale, uint32_t part, uint32_t nparts,
+                             uint32_t level_lo, uint32_t level_hi, n2m_stream_t stream) {
+    N2M_REQUIRE(p && recs && counters && rays_o && rays_d && denc_tiles && table && offsets && gtable && loss_scale,
+                "s0_encode_bwd_levels", "null pointer");
+    N2M_REQUIRE(p->num_levels == kLevels, "s0_encode_bwd_levels", "fused path supports num_levels == 16");
+    N2M_REQUIRE(Mcap % kTile == 0 && Mcap > 0, "s0_encode_bwd_levels", "Mcap must be a positive multiple of 128");
+    N2M_REQUIRE(valid_parts(part, nparts), "s0_encode_bwd_levels", "nparts must be 1, 2, 4 or 8 and part < nparts");
+    N2M_REQUIRE(level_lo < level_hi && level_hi <= kLevels, "s0_encode_bwd_levels", "empty or out-of-range level interval");
+    const bool tv_here = p->lambda_tv > 0 && g_tv_mode == 0;
+    const uint32_t grid = nparts == 1 ? Mcap / kTile : part_grid(Mcap, nparts);
+    if (tv_here)
+        k_s0_encode_bwd_levels<true, true><<<grid, kTile, 0, as_stream(stream)>>>(N2M_BWD_ARGS, level_lo, level_hi);
+    else
+        k_s0_encode_bwd_levels<true, false><<<grid, kTile, 0, as_stream(stream)>>>(N2M_BWD_ARGS, level_lo, level_hi);
+    return check_launch("s0_encode_bwd_levels");
 }
 
 /* stand-alone TV-gradient launch (same arithmetic as inside the scatter kernel); only meaningful with tv mode 2 */

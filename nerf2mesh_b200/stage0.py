@@ -59,6 +59,7 @@ _lib.register({
     "n2m_s0_composite_loss_part": [PP, P, P, P, P, U, U, P, P, P, P, P, P, P, P, U, U, P],
     "n2m_s0_mlp_bwd_part": [PP, P, P, P, U, P, P, P, P, U, U, P],
     "n2m_s0_encode_bwd_part": [PP, P, P, U, P, P, P, P, P, P, P, U, U, P],
+    "n2m_s0_encode_bwd_levels": [PP, P, P, U, P, P, P, P, P, P, P, U, U, U, U, P],
     "n2m_s0_adam_head": [P, P, P],
     "n2m_s0_adam_tables": [P, P, P, P, P, U, P, F, P],
     "n2m_s0_adam_mlp": [P, P, P, P, P, P, F, P],
@@ -186,6 +187,7 @@ class Stage0Trainer:
         self.part_mode = "chains"           # "pipeline": gathers/scatters on one stream, MLPs on a high-priority one; "chains": a stream per part
         self._mlp_stream = None
         self._adam_stream = None
+        self.scatter_level_cuts = ()        # experimental: e.g. (10,) = two scatter passes, levels 0-9 then 10-15 (include/n2m_b200_fused.h)
         call("n2m_s0_set_tv_mode", 2 if self.tv_overlap else 0)
         self.gtables = [self.gtable]        # PeerAdam adds a second parity (parallel.py)
         self.g_mlps = [self.g_mlp]
@@ -317,9 +319,17 @@ class Stage0Trainer:
              ptr(self.denc_tiles), ptr(self.g_mlps[self.parity]), ptr(self.opt_state), part, nparts, stream())
 
     def encode_bwd(self, part=0, nparts=1):
-        call("n2m_s0_encode_bwd_part", self._pp(), ptr(self.recs), ptr(self.counters), self.Mcap, ptr(self.rays_o), ptr(self.rays_d),
-             ptr(self.denc_tiles), ptr(self.table), ptr(self.offsets), ptr(self.gtables[self.parity]), ptr(self.opt_state),
-             part, nparts, stream())
+        if not self.scatter_level_cuts:
+            call("n2m_s0_encode_bwd_part", self._pp(), ptr(self.recs), ptr(self.counters), self.Mcap, ptr(self.rays_o), ptr(self.rays_d),
+                 ptr(self.denc_tiles), ptr(self.table), ptr(self.offsets), ptr(self.gtables[self.parity]), ptr(self.opt_state),
+                 part, nparts, stream())
+            return
+        # experimental: one scatter launch per level range, so that each launch's target rows are closer to L2-resident
+        bounds = [0, *self.scatter_level_cuts, self.cfg.num_levels]
+        for lo, hi in zip(bounds[:-1], bounds[1:]):
+            call("n2m_s0_encode_bwd_levels", self._pp(), ptr(self.recs), ptr(self.counters), self.Mcap, ptr(self.rays_o), ptr(self.rays_d),
+                 ptr(self.denc_tiles), ptr(self.table), ptr(self.offsets), ptr(self.gtables[self.parity]), ptr(self.opt_state),
+                 part, nparts, lo, hi, stream())
 
     def tv(self):
         call("n2m_s0_tv", self._pp(), ptr(self.recs), ptr(self.counters), self.Mcap, ptr(self.rays_o), ptr(self.rays_d),
@@ -438,7 +448,7 @@ class Stage0Trainer:
             key = (name, self.parity)
         else:
             key = (name, self.cur, self.parity, int(self.params.shading_full), int(self.params.gt_has_alpha), int(self.nparts),
-                   bool(self.tv_overlap), self.part_mode)
+                   bool(self.tv_overlap), self.part_mode, tuple(self.scatter_level_cuts))
         g = self._graphs.get(key)
         if g is None:
             g = torch.cuda.CUDAGraph()

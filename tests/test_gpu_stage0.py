@@ -455,3 +455,22 @@ def test_reference_state_dict_and_checkpoint_schema(tmp_path):
     s2 = t2.export_reference_state()
     for k, v in tr.export_reference_state().items():
         assert torch.equal(v, s2[k]), k
+
+
+@pytest.mark.skipif(__import__("os").environ.get("N2M_EXPERIMENTAL") != "1",
+                    reason="experimental scatter variant, compiled but not yet validated on a GPU (set N2M_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("cuts", [(10,), (5, 10, 13)])
+def test_scatter_level_passes_equal_single_pass(cuts):
+    """n2m_s0_encode_bwd_levels over disjoint level ranges covering 0..16 == the single scatter launch (same atomics, only their
+    order differs)."""
+    tr, b = make()
+    stage(tr, b)
+    tr.forward_backward()
+    g_ref = tr.export_reference_grads()
+    tr.gtable.zero_(); tr.g_mlp.zero_()
+    tr.scatter_level_cuts = cuts
+    tr.forward_backward()
+    g = tr.export_reference_grads()
+    for name in g_ref:
+        a, r = g[name].double(), g_ref[name].double()
+        assert (a - r).abs().max().item() <= 1e-4 * r.abs().max().item() + 1e-12, name
