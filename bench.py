@@ -35,6 +35,10 @@ ALG_BYTES = {"encode_fwd": 1053, "encode_bwd": 1024, "step": 2077}      # SURVEY
 NCU_TRAFFIC = {"encode_bwd": 129.0e6 + 153.6e6, "encode_fwd": 48.78e6 + 12.57e6}
 
 
+RED_LANES_PER_SAMPLE = 1.885e7 / 298645          # profiles/r1_ncu_summary.md r1f: RED sectors of k_s0_encode_bwd / samples of that launch
+RED_PEAK_GLANES = 132.7                           # profiles/redbench.py: v4.f32 REDs into a 98 MB table, G lanes/s
+
+
 def load_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -335,6 +339,13 @@ def run_ours(args):
                 "frac": achieved / peak, "traffic": NCU_TRAFFIC.get(dom), "alg_bytes_per_sample": ALG_BYTES[dom], "samples_per_launch": M_last,
                 "kernel_ms": acc[dom], "stage_ms_cold_l2": {k: round(v, 4) for k, v in acc.items()},
                 "step_frac_of_hbm": ALG_BYTES["step"] * value / 1e9 / peak}
+    if dom == "encode_bwd":
+        # supplementary ruler: the scatter is bound by the rate of spread REDs into a table of its footprint, not by HBM bytes
+        # (profiles/redbench.py: 133 G lane-REDs/s into 98 MB, payload-independent; 63.1 lane-REDs per sample after run merging,
+        # from the l1tex RED sector count of the committed ncu capture)
+        lanes = RED_LANES_PER_SAMPLE * M_last
+        roofline["red_rate"] = {"achieved": lanes / (acc[dom] * 1e-3) / 1e9, "peak": RED_PEAK_GLANES, "unit": "G lane-REDs/s",
+                                "frac": lanes / (acc[dom] * 1e-3) / 1e9 / RED_PEAK_GLANES, "lanes_per_sample": RED_LANES_PER_SAMPLE}
 
     if rank == 0:
         cpu = None
