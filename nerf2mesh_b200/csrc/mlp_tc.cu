@@ -151,7 +151,12 @@ __device__ __forceinline__ tc::Operand opMN(const uint8_t* tile, uint32_t rows) 
 // ================================================================================================
 constexpr uint32_t F_W = 0, F_A = F_W + W_BYTES, F_H = F_A + kTileBytes, F_S1 = F_H + kTileBytes,
                    F_P1 = F_S1 + 8192, F_AS2 = F_P1 + 8192, F_BYTES = F_AS2 + 4096;
+// COMPACT layout (experimental, n2m_s0_set_mlp_fwd_compact): the specular hidden tile P1 aliases the sigma hidden tile S1, which is
+// dead once sigma_net.1 has completed in round 2 (P1 is written in round 4, S1 again in round 1 of the next tile, after the
+// wait on specular_net.1) -- 79 KB -> 71 KB of shared memory per CTA, i.e. three CTAs per SM instead of two (TMEM 3 x 128 columns).
+constexpr uint32_t FC_AS2 = F_S1 + 8192, FC_BYTES = FC_AS2 + 4096;
 
+template <bool COMPACT>
 __global__ void __launch_bounds__(128)
 k_mlp_fwd(n2m_s0_params p, const uint8_t* __restrict__ enc_tiles, const int32_t* __restrict__ counters,
           const uint8_t* __restrict__ wpack, float4* __restrict__ out, float* __restrict__ spec_sq_sum,
@@ -172,7 +177,7 @@ k_mlp_fwd(n2m_s0_params p, const uint8_t* __restrict__ enc_tiles, const int32_t*
     for (uint32_t i = tid; i < W_BYTES / 16; i += 128)
         reinterpret_cast<uint4*>(smem + F_W)[i] = __ldg(reinterpret_cast<const uint4*>(wpack) + i);
     {   // second K chunk of the specular input tile is always zero
-        *reinterpret_cast<uint4*>(smem + F_AS2 + kChunk + tid * 16) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(smem + (COMPACT ? FC_AS2 : F_AS2) + kChunk + tid * 16) = make_uint4(0, 0, 0, 0);
     }
     sync_before_mma();
     const uint32_t tmem = tmem_s, D0 = tmem, D1 = tmem + 64;
@@ -180,7 +185,7 @@ k_mlp_fwd(n2m_s0_params p, const uint8_t* __restrict__ enc_tiles, const int32_t*
     uint32_t ph_mma = 0, ph_tma = 0;
     float spec_sq = 0.f;
     uint8_t* sW = smem + F_W; uint8_t* sA = smem + F_A; uint8_t* sH = smem + F_H;
-    uint8_t* sS1 = smem + F_S1; uint8_t* sP1 = smem + F_P1; uint8_t* sAs2 = smem + F_AS2;
+    uint8_t* sS1 = smem + F_S1; uint8_t* sP1 = smem + (COMPACT ? F_S1 : F_P1); uint8_t* sAs2 = smem + (COMPACT ? FC_AS2 : F_AS2);
     // operand descriptors, built once (only the issuing thread uses them)
     const tc::OpDesc dA = tc::make_opdesc(opK(sA, 128)), dH = tc::make_opdesc(opK(sH, 128)), dS1 = tc::make_opdesc(opK(sS1, 128)),
                      dP1 = tc::make_opdesc(opK(sP1, 128)), dAs2 = tc::make_opdesc(opK(sAs2, 128));
@@ -1004,6 +1009,10 @@ static int num_sms() {
     return n;
 }
 
+static bool g_fwd_compact = false;
+/* experimental tuning hook (compiled, not yet measured): 1 = MLP forward with the compact shared-memory layout, three CTAs per SM */
+int n2m_s0_set_mlp_fwd_compact(int on) { g_fwd_compact = on != 0; return 0; }
+
 static bool g_bwd_pipelined = false;
 /* 0 = single-tile backward kernel (default: measured faster, and it leaves room on the SM for a co-resident gather /
  * scatter kernel), 1 = two-tile pipelined kernel with issuer warp */
@@ -1011,7 +1020,8 @@ int n2m_s0_set_mlp_bwd_pipelined(int on) { g_bwd_pipelined = on != 0; return 0; 
 
 /* one-time function attributes (dynamic shared memory opt-in); safe to call repeatedly */
 int n2m_s0_init(void) {
-    cudaError_t e = cudaFuncSetAttribute(k_mlp_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(k_mlp_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FC_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_bwd2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_BYTES);
     if (e != cudaSuccess) return fail("s0_init", cudaGetErrorString(e));
@@ -1024,10 +1034,17 @@ int n2m_s0_mlp_fwd_part(const n2m_s0_params* p, const void* enc_tiles, const int
     N2M_REQUIRE(p && enc_tiles && counters && wpack && out, "s0_mlp_fwd", "null pointer");
     N2M_REQUIRE(Mcap % kTile == 0 && Mcap > 0, "s0_mlp_fwd", "Mcap must be a positive multiple of 128");
     N2M_REQUIRE(valid_parts(part, nparts), "s0_mlp_fwd", "nparts must be 1, 2, 4 or 8 and part < nparts");
+    if (g_fwd_compact) {
+        const uint32_t grid3 = min(Mcap / kTile, (uint32_t)(3 * num_sms()));
+        k_mlp_fwd<true><<<grid3, 128, FC_BYTES, as_stream(stream)>>>(*p, static_cast<const uint8_t*>(enc_tiles), counters,
+                                                                     static_cast<const uint8_t*>(wpack), static_cast<float4*>(out),
+                                                                     spec_sq_sum, part, nparts);
+        return check_launch("s0_mlp_fwd(compact)");
+    }
     const uint32_t grid = min(Mcap / kTile, (uint32_t)(2 * num_sms()));
-    k_mlp_fwd<<<grid, 128, F_BYTES, as_stream(stream)>>>(*p, static_cast<const uint8_t*>(enc_tiles), counters,
-                                                         static_cast<const uint8_t*>(wpack), static_cast<float4*>(out), spec_sq_sum,
-                                                         part, nparts);
+    k_mlp_fwd<false><<<grid, 128, F_BYTES, as_stream(stream)>>>(*p, static_cast<const uint8_t*>(enc_tiles), counters,
+                                                                static_cast<const uint8_t*>(wpack), static_cast<float4*>(out), spec_sq_sum,
+                                                                part, nparts);
     return check_launch("s0_mlp_fwd");
 }
 

@@ -474,3 +474,27 @@ def test_scatter_level_passes_equal_single_pass(cuts):
     for name in g_ref:
         a, r = g[name].double(), g_ref[name].double()
         assert (a - r).abs().max().item() <= 1e-4 * r.abs().max().item() + 1e-12, name
+
+
+@pytest.mark.skipif(__import__("os").environ.get("N2M_EXPERIMENTAL") != "1",
+                    reason="experimental MLP-forward layout, compiled but not yet validated on a GPU (set N2M_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("shading", ["full", "diffuse"])
+def test_compact_mlp_forward_equals_default(shading):
+    """n2m_s0_set_mlp_fwd_compact(1): the P1 tile aliases the dead S1 tile (3 CTAs/SM); same arithmetic => identical outputs."""
+    from nerf2mesh_b200._lib import call
+    tr, b = make(shading)
+    stage(tr, b)
+    tr._fill_params(shading == "full", True)
+    tr.march(); tr.encode_fwd(); tr.loss_acc.zero_(); tr.mlp_fwd()
+    torch.cuda.synchronize()
+    M = int(tr.counters[1].item())
+    ref = tr.out[:M].clone(); spec = tr.loss_acc[1].item()
+    try:
+        call("n2m_s0_set_mlp_fwd_compact", 1)
+        tr.out.zero_(); tr.loss_acc.zero_()
+        tr.mlp_fwd()
+        torch.cuda.synchronize()
+        assert torch.equal(tr.out[:M], ref)
+        assert abs(tr.loss_acc[1].item() - spec) <= 1e-5 * max(abs(spec), 1e-12)
+    finally:
+        call("n2m_s0_set_mlp_fwd_compact", 0)
