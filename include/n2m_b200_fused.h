@@ -218,6 +218,10 @@ int n2m_s0_adam(void* table, void* color_master, void* gtable, float* m_table, f
 int n2m_s0_adam_head(const float* g_mlp, float* opt_state, n2m_stream_t stream);
 int n2m_s0_adam_tables(void* table, void* color_master, void* gtable, float* m_table, float* v_table, uint32_t rows,
                        const float* opt_state, float eps, n2m_stream_t stream);
+/* EXPERIMENTAL (compiled, not yet measured): `tables` restricted to rows [row_lo, row_hi) -- e.g. the rows of the hash levels
+ * whose gradients are already complete, while n2m_s0_encode_bwd_levels of the other levels is still running */
+int n2m_s0_adam_tables_range(void* table, void* color_master, void* gtable, float* m_table, float* v_table, uint32_t rows,
+                             uint32_t row_lo, uint32_t row_hi, const float* opt_state, float eps, n2m_stream_t stream);
 int n2m_s0_adam_mlp(float* mlp_params, float* g_mlp, float* m_mlp, float* v_mlp, void* wpack, const float* opt_state, float eps,
                     n2m_stream_t stream);
 int n2m_s0_adam_post(float* opt_state, n2m_stream_t stream);

@@ -64,6 +64,7 @@ _lib.register({
     "n2m_s0_adam_tables": [P, P, P, P, P, U, P, F, P],
     "n2m_s0_adam_mlp": [P, P, P, P, P, P, F, P],
     "n2m_s0_adam_post": [P, P],
+    "n2m_s0_adam_tables_range": [P, P, P, P, P, U, U, U, P, F, P],
     "n2m_s0_set_prof": [P],
     "n2m_s0_set_mlp_fwd_compact": [I],
     "n2m_s0_set_gather_carveout": [I],
@@ -142,6 +143,7 @@ class Stage0Trainer:
         c = cfg
         offs = level_offsets(3, c.num_levels, c.per_level_scale, c.base_resolution, c.log2_hashmap_size, False)
         self.offsets = torch.from_numpy(offs).to(dev)
+        self._offsets_host = [int(v) for v in offs]
         self.rows = int(offs[-1])
         R = self.rows
         self.n_mlp = int(_lib.lib.n2m_s0_mlp_param_count())
@@ -188,6 +190,8 @@ class Stage0Trainer:
         self.part_mode = "chains"           # "pipeline": gathers/scatters on one stream, MLPs on a high-priority one; "chains": a stream per part
         self._mlp_stream = None
         self._adam_stream = None
+        self.level_pipe = False             # experimental: optimizer of the first level range under the scatter of the second
+        self._ev_first_pass = []
         self.scatter_level_cuts = ()        # experimental: e.g. (10,) = two scatter passes, levels 0-9 then 10-15 (include/n2m_b200_fused.h)
         call("n2m_s0_set_tv_mode", 2 if self.tv_overlap else 0)
         self.gtables = [self.gtable]        # PeerAdam adds a second parity (parallel.py)
@@ -372,6 +376,7 @@ class Stage0Trainer:
         main = torch.cuda.current_stream()
         P_ = int(self.nparts)
         fork_tv = self.tv_overlap and self.cfg.lambda_tv > 0
+        self._ev_first_pass = []
 
         def launch_tv():
             if fork_tv:
@@ -389,7 +394,7 @@ class Stage0Trainer:
             self.mlp_bwd()
             if fork_tv:
                 main.wait_stream(self._tv_stream)
-            self.encode_bwd()
+            self._scatter(0, 1)
             return
         if self.part_mode == "pipeline":
             # two-stream software pipeline: gathers then scatters of all parts in order on this (normal-priority) stream,
@@ -414,7 +419,7 @@ class Stage0Trainer:
             launch_tv()                      # behind the gathers: fills the wait for the first MLP chain
             for k in range(P_):
                 main.wait_event(done[k])
-                self.encode_bwd(k, P_)
+                self._scatter(k, P_)
         else:
             # independent chains, one stream per part
             launch_tv()
@@ -429,15 +434,65 @@ class Stage0Trainer:
                     self.mlp_fwd(k, P_)
                     self.composite_loss(k, P_)
                     self.mlp_bwd(k, P_)
-                    self.encode_bwd(k, P_)
+                    self._scatter(k, P_)
             for st in streams[1:]:
                 main.wait_stream(st)
         if fork_tv:
             main.wait_stream(self._tv_stream)
 
+    def _level_pipe_on(self):
+        return bool(self.level_pipe) and len(self.scatter_level_cuts) == 1
+
+    def _scatter(self, k, P_):
+        """Scatter of part k on the current stream.  With `level_pipe` (experimental) the first level range is followed by an event:
+        the optimizer of those levels' rows starts as soon as every part has passed it (`_compute_then_adam`)."""
+        if not self._level_pipe_on():
+            self.encode_bwd(k, P_)
+            return
+        cut = int(self.scatter_level_cuts[0])
+        args = (self._pp(), ptr(self.recs), ptr(self.counters), self.Mcap, ptr(self.rays_o), ptr(self.rays_d), ptr(self.denc_tiles),
+                ptr(self.table), ptr(self.offsets), ptr(self.gtables[self.parity]), ptr(self.opt_state), k, P_)
+        call("n2m_s0_encode_bwd_levels", *args, 0, cut, stream())
+        ev = torch.cuda.Event(); ev.record(torch.cuda.current_stream())
+        self._ev_first_pass.append(ev)
+        call("n2m_s0_encode_bwd_levels", *args, cut, self.cfg.num_levels, stream())
+
+    def _compute_then_adam(self):
+        """forward + backward + optimizer of one step.  Default: `_compute()` then `adam()`.
+
+        `level_pipe` (experimental, single-GPU path): the scatter runs as two level ranges; the optimizer of the rows of the
+        first range (head -> k_adam_tables_range) runs on the optimizer stream while the second range is still scattering --
+        an HBM-streaming kernel under a RED-bound one.  Safe because (a) the two ranges touch disjoint rows, (b) every sample's
+        feature gradients were inf-checked by the first pass, so found_inf is final when it ends, (c) the TV launch (all levels)
+        is joined first."""
+        if not self._level_pipe_on():
+            self._compute()
+            self.adam()
+            return
+        main = torch.cuda.current_stream()
+        self._compute()                                   # chains incl. both scatter passes; everything joined into `main`
+        if self._adam_stream is None:
+            self._adam_stream = torch.cuda.Stream(device=self.device)
+        side = self._adam_stream
+        row_cut = int(self._offsets_host[int(self.scatter_level_cuts[0])])
+        for ev in self._ev_first_pass:
+            side.wait_event(ev)
+        if self._tv_stream is not None:
+            side.wait_stream(self._tv_stream)
+        with torch.cuda.stream(side):
+            call("n2m_s0_adam_head", ptr(self.g_mlp), ptr(self.opt_state), stream())
+            call("n2m_s0_adam_tables_range", ptr(self.table), ptr(self.color_master), ptr(self.gtable), ptr(self.m_table),
+                 ptr(self.v_table), self.rows, 0, row_cut, ptr(self.opt_state), self.cfg.eps, stream())
+            call("n2m_s0_adam_mlp", ptr(self.mlp), ptr(self.g_mlp), ptr(self.m_mlp), ptr(self.v_mlp), ptr(self.wpack),
+                 ptr(self.opt_state), self.cfg.eps, stream())
+        main.wait_stream(side)
+        call("n2m_s0_adam_tables_range", ptr(self.table), ptr(self.color_master), ptr(self.gtable), ptr(self.m_table),
+             ptr(self.v_table), self.rows, row_cut, self.rows, ptr(self.opt_state), self.cfg.eps, stream())
+        call("n2m_s0_adam_post", ptr(self.opt_state), stream())
+
     def _step_body(self):
-        self.forward_backward()
-        self.adam()
+        self.march()
+        self._compute_then_adam()
 
     # -------------------------------------------------------------------------------------------
     def _graph(self, name, fn):
@@ -449,7 +504,7 @@ class Stage0Trainer:
             key = (name, self.parity)
         else:
             key = (name, self.cur, self.parity, int(self.params.shading_full), int(self.params.gt_has_alpha), int(self.nparts),
-                   bool(self.tv_overlap), self.part_mode, tuple(self.scatter_level_cuts))
+                   bool(self.tv_overlap), self.part_mode, tuple(self.scatter_level_cuts), bool(self.level_pipe))
         g = self._graphs.get(key)
         if g is None:
             g = torch.cuda.CUDAGraph()
@@ -501,7 +556,7 @@ class Stage0Trainer:
         if not marched:
             self._run("march", self.march, use_graph)
         if grad_sync is None:
-            self._run("compute+adam", lambda: (self._compute(), self.adam()), use_graph)
+            self._run("compute+adam", self._compute_then_adam, use_graph)
         elif getattr(grad_sync, "fused", False):
             # data parallel, sharded optimizer fused with its collective over NVLink peer memory (parallel.PeerAdam)
             self._run("compute", self._compute, use_graph)

@@ -498,3 +498,33 @@ def test_compact_mlp_forward_equals_default(shading):
         assert abs(tr.loss_acc[1].item() - spec) <= 1e-5 * max(abs(spec), 1e-12)
     finally:
         call("n2m_s0_set_mlp_fwd_compact", 0)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("N2M_EXPERIMENTAL") != "1",
+                    reason="experimental level-pipelined optimizer, compiled but not yet validated on a GPU (set N2M_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("nparts,use_graph", [(1, False), (2, True)])
+def test_level_pipelined_optimizer_equals_default_step(nparts, use_graph):
+    """level_pipe: scatter in two level ranges, Adam of the first range's rows under the scatter of the second
+    (n2m_s0_adam_tables_range).  Same arithmetic per row => same parameters after a few steps, up to the fp32 order of the atomics."""
+    res = []
+    for pipe in (False, True):
+        tr, b = make(seed=4)
+        tr.nparts = nparts
+        if pipe:
+            tr.scatter_level_cuts = (10,)
+            tr.level_pipe = True
+        losses = []
+        for it in range(3):
+            tr.step(b["ro"], b["rd"], b["gt"], b["bg"], b["noises"], use_graph=use_graph)
+            losses.append(tr.read_loss())
+        torch.cuda.synchronize()
+        st = tr.export_reference_state()
+        res.append((losses, {k: v.clone() for k, v in st.items() if v.is_floating_point()}, tr.opt_state.clone(),
+                    tr.gtable.abs().max().item(), tr.g_mlp.abs().max().item()))
+    (l0, s0, o0, gz0, gm0), (l1, s1, o1, gz1, gm1) = res
+    assert gz1 == 0 and gm1 == 0                                   # both ranges zeroed their gradient rows
+    assert torch.equal(o0, o1)                                     # step count, loss scale, growth tracker
+    assert np.allclose(l0, l1, rtol=1e-4), (l0, l1)
+    for k in s0:
+        moved = (s0[k] - s0[k].mean()).abs().max().item()
+        assert (s0[k] - s1[k]).abs().max().item() <= 2e-3 * max(moved, 1e-6) + 1e-7, k
