@@ -1,0 +1,32 @@
+"""CPU: the `bench.py --impl reference` arm prints ONE JSON line with the contract's keys, finishes quickly for small K/W, and
+ranks other than 0 print nothing (tier framing (4): the reference arm times the CPU restatement on rank 0 only)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(env_extra):
+    env = dict(os.environ, **env_extra)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return [l for l in r.stdout.splitlines() if l.startswith("{")]
+
+
+def test_reference_arm_json_line():
+    lines = _run({"RANK": "0", "WORLD_SIZE": "1"})
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "ray-samples/sec (train step)" and d["unit"] == "samples/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1 and d["warmup"] == 0
+    assert d["config"]["workload"] == "lego_stage0_converged"
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "rays" in cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_other_ranks_are_silent():
+    assert _run({"RANK": "1", "WORLD_SIZE": "2"}) == []
