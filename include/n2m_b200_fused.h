@@ -84,6 +84,9 @@ int n2m_s0_tv(const n2m_s0_params* p, const void* recs, const int32_t* counters,
 
 /* tuning hook: MLP backward variant, 0 = one tile per CTA (default), 1 = two tiles in flight + issuer warp */
 int n2m_s0_set_mlp_bwd_pipelined(int on);
+/* EXPERIMENTAL tuning hook (compiled, not yet measured on a GPU): issuing warps of the two-tile MLP backward (only with
+ * n2m_s0_set_mlp_bwd_pipelined(1)): 1 = one issuer for both tile groups (default), 2 = one issuer per group */
+int n2m_s0_set_mlp_bwd_issuers(int n);
 /* EXPERIMENTAL tuning hook (compiled, not yet measured on a GPU): 1 = MLP forward with the specular hidden tile aliased onto the
  * dead sigma hidden tile (71 KB of shared memory per CTA => three CTAs per SM), 0 = default layout (two CTAs per SM) */
 int n2m_s0_set_mlp_fwd_compact(int on);

@@ -628,7 +628,12 @@ __device__ unsigned long long* g_prof = nullptr;
 constexpr uint32_t kProfIter = 3;                 // which of block 0's tile iterations is stamped (steady state, not the cold first one)
 #define PROF_STAMP() do { if (pf) { pf[ps++] = (unsigned long long)clock64(); } } while (0)
 
-__global__ void __launch_bounds__(288)
+// ISSUERS = 1: warp 8 issues every tcgen05.mma (the measured variant).  ISSUERS = 2 (experimental, compiled only): warps 8 and 9
+// issue for tile group 0 and 1 respectively -- two issuing threads reach 39-48 cycles per MMA aggregate against 59-68 for one
+// (profiles/tcbench.py).  Both accumulate into the SAME weight-gradient columns, which are therefore zeroed up front with
+// tcgen05.st and always accumulated into (no 'first MMA overwrites' flag that two threads would have to agree on).
+template <int ISSUERS>
+__global__ void __launch_bounds__(ISSUERS == 2 ? 320 : 288)
 k_mlp_bwd2(n2m_s0_params p, const uint8_t* __restrict__ enc_tiles, const float4* __restrict__ dout,
            const int32_t* __restrict__ counters, const uint8_t* __restrict__ wpack, uint8_t* __restrict__ denc_tiles,
            float* __restrict__ g_mlp, const float* __restrict__ loss_scale, uint32_t part, uint32_t nparts) {
@@ -647,7 +652,7 @@ k_mlp_bwd2(n2m_s0_params p, const uint8_t* __restrict__ enc_tiles, const float4*
         tc::mbar_init_fence();
     }
     if (warp == 8) tc::tmem_alloc(&tmem_s, 512);
-    for (uint32_t i = tid; i < W_BYTES / 16; i += 288)
+    for (uint32_t i = tid; i < W_BYTES / 16; i += (ISSUERS == 2 ? 320u : 288u))
         reinterpret_cast<uint4*>(smem)[i] = __ldg(reinterpret_cast<const uint4*>(wpack) + i);
     if (tid < 256) {    // constant-zero chunks of the narrow tiles, finite contents for the never-written ones
         uint8_t* grp = smem + W_BYTES + (tid >> 7) * P_GRP;
@@ -663,8 +668,18 @@ k_mlp_bwd2(n2m_s0_params p, const uint8_t* __restrict__ enc_tiles, const float4*
     sync_before_mma();
     const uint32_t tmem = tmem_s;
     uint8_t* sW = smem;
+    if (ISSUERS == 2) {
+        if (warp < 4) {
+#pragma unroll
+            for (uint32_t c = Q_C1; c < Q_P2 + 16; c += 16) tc::tmem_st16_zero(tmem + ((warp * 32u) << 16) + c);
+            tc::tmem_st_wait();
+        }
+        tc::fence_before_sync();
+        __syncthreads();
+        tc::fence_after_sync();
+    }
 
-    if (warp == 8) {
+    if (ISSUERS == 2 ? warp >= 8 : warp == 8) {
         // ------------------------------ MMA issuer ------------------------------
         if (lane == 0) {
             uint32_t ph_ready[2] = {0, 0};
@@ -673,7 +688,8 @@ k_mlp_bwd2(n2m_s0_params p, const uint8_t* __restrict__ enc_tiles, const float4*
                 const uint32_t first_tile = t0 + blockIdx.x * 2 + g;
                 n_g[g] = first_tile < ntiles ? (ntiles - first_tile + 2 * gridDim.x - 1) / (2 * gridDim.x) : 0;
             }
-            bool f_c1 = false, f_c2 = false, f_s1 = false, f_p1 = false, f_c3 = false, f_s2 = false, f_p2 = false;   // accumulator initialised?
+            bool f_c1 = ISSUERS == 2, f_c2 = ISSUERS == 2, f_s1 = ISSUERS == 2, f_p1 = ISSUERS == 2, f_c3 = ISSUERS == 2,
+                 f_s2 = ISSUERS == 2, f_p2 = ISSUERS == 2;   // accumulator initialised? (two issuers: zeroed above)
             // all operand descriptors, built once per CTA (weights: K-major for forward, MN-major for dgrad)
             const tc::OpDesc wC1k = tc::make_opdesc(opK(sW + W_C1, 64)), wC2k = tc::make_opdesc(opK(sW + W_C2, 64)),
                              wC3k = tc::make_opdesc(opK(sW + W_C3, 16)), wS1k = tc::make_opdesc(opK(sW + W_S1, 32)),
@@ -706,11 +722,11 @@ k_mlp_bwd2(n2m_s0_params p, const uint8_t* __restrict__ enc_tiles, const float4*
             // The issuer serves whichever group has handed over its operands: the two tiles drift apart by about half a
             // round, so one group's GEMMs execute under the other group's epilogue (a fixed g0,g1,g0,... order would keep
             // both groups in lockstep: both in their epilogues, then both waiting on the tensor pipe).
-            unsigned long long* pf0 = blockIdx.x == 0 ? g_prof : nullptr;
+            unsigned long long* pf0 = (blockIdx.x == 0 && warp == 8) ? g_prof : nullptr;
             if (pf0) pf0 += 32;
             uint32_t ps = 0;
             uint32_t rd[2] = {0, 0}, itg[2] = {0, 0};
-            bool act[2] = {n_g[0] > 0, n_g[1] > 0};
+            bool act[2] = {n_g[0] > 0 && (ISSUERS == 1 || warp == 8), n_g[1] > 0 && (ISSUERS == 1 || warp == 9)};
             uint32_t spins = 0;
             while (act[0] || act[1]) {
 #pragma unroll
@@ -1013,6 +1029,9 @@ static bool g_fwd_compact = false;
 /* experimental tuning hook (compiled, not yet measured): 1 = MLP forward with the compact shared-memory layout, three CTAs per SM */
 int n2m_s0_set_mlp_fwd_compact(int on) { g_fwd_compact = on != 0; return 0; }
 
+static int g_bwd_issuers = 1;
+/* experimental tuning hook (compiled, not yet measured): issuing warps of the two-tile MLP backward, 1 (default) or 2 */
+int n2m_s0_set_mlp_bwd_issuers(int n) { g_bwd_issuers = n == 2 ? 2 : 1; return 0; }
 static bool g_bwd_pipelined = false;
 /* 0 = single-tile backward kernel (default: measured faster, and it leaves room on the SM for a co-resident gather /
  * scatter kernel), 1 = two-tile pipelined kernel with issuer warp */
@@ -1023,7 +1042,8 @@ int n2m_s0_init(void) {
     cudaError_t e = cudaFuncSetAttribute(k_mlp_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FC_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_bwd2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_bwd2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_bwd2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_BYTES);
     if (e != cudaSuccess) return fail("s0_init", cudaGetErrorString(e));
     num_sms();
     return 0;
@@ -1061,7 +1081,12 @@ int n2m_s0_mlp_bwd_part(const n2m_s0_params* p, const void* enc_tiles, const voi
     N2M_REQUIRE(valid_parts(part, nparts), "s0_mlp_bwd", "nparts must be 1, 2, 4 or 8 and part < nparts");
     if (g_bwd_pipelined) {
         const uint32_t grid2 = min((Mcap / kTile + 1) / 2, (uint32_t)num_sms());
-        k_mlp_bwd2<<<grid2, 288, P_BYTES, as_stream(stream)>>>(*p, static_cast<const uint8_t*>(enc_tiles), static_cast<const float4*>(dout),
+        if (g_bwd_issuers == 2)
+            k_mlp_bwd2<2><<<grid2, 320, P_BYTES, as_stream(stream)>>>(*p, static_cast<const uint8_t*>(enc_tiles), static_cast<const float4*>(dout),
+                                                                      counters, static_cast<const uint8_t*>(wpack), static_cast<uint8_t*>(denc_tiles),
+                                                                      g_mlp, loss_scale, part, nparts);
+        else
+        k_mlp_bwd2<1><<<grid2, 288, P_BYTES, as_stream(stream)>>>(*p, static_cast<const uint8_t*>(enc_tiles), static_cast<const float4*>(dout),
                                                                counters, static_cast<const uint8_t*>(wpack), static_cast<uint8_t*>(denc_tiles),
                                                                g_mlp, loss_scale, part, nparts);
         return check_launch("s0_mlp_bwd(pipelined)");

@@ -108,6 +108,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// ---- registers -> TMEM: zero 16 consecutive 32-bit columns of the calling thread's lane (same lane rule as the loads below) ----
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
+    const uint32_t z = 0u;
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};"
+                 :: "r"(taddr), "r"(z) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // ---- TMEM -> registers: each thread reads N consecutive fp32 columns of ITS lane (row) ------------
 // warp w may only touch lanes [32*(w%4), 32*(w%4)+32): taddr = ((lane_base) << 16) | column
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {

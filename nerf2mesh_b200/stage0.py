@@ -67,6 +67,7 @@ _lib.register({
     "n2m_s0_adam_tables_range": [P, P, P, P, P, U, U, U, P, F, P],
     "n2m_s0_set_prof": [P],
     "n2m_s0_set_mlp_fwd_compact": [I],
+    "n2m_s0_set_mlp_bwd_issuers": [I],
     "n2m_s0_set_gather_carveout": [I],
 })
 _lib.lib.n2m_s0_wpack_bytes.restype = c_uint32

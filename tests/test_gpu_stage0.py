@@ -231,7 +231,7 @@ def test_pipelined_mlp_backward_equals_single_tile_kernel():
             tr.mlp_bwd()
             torch.cuda.synchronize()
             res.append((tr.denc_tiles.clone(), tr.g_mlp.clone()))
-        call("n2m_s0_set_mlp_bwd_pipelined", 1)
+        call("n2m_s0_set_mlp_bwd_pipelined", 0)            # back to the default (single-tile kernel)
         M = int(tr.counters[1].item())
         d0, d1 = untile(res[0][0], M), untile(res[1][0], M)
         assert torch.equal(d0, d1), (d0 - d1).abs().max()
@@ -528,3 +528,31 @@ def test_level_pipelined_optimizer_equals_default_step(nparts, use_graph):
     for k in s0:
         moved = (s0[k] - s0[k].mean()).abs().max().item()
         assert (s0[k] - s1[k]).abs().max().item() <= 2e-3 * max(moved, 1e-6) + 1e-7, k
+
+
+@pytest.mark.skipif(__import__("os").environ.get("N2M_EXPERIMENTAL") != "1",
+                    reason="experimental two-issuer MLP backward, compiled but not yet validated on a GPU (set N2M_EXPERIMENTAL=1)")
+def test_two_issuer_mlp_backward_equals_single_tile_kernel():
+    """k_mlp_bwd2<2> (one issuing warp per tile group, weight-gradient accumulators zeroed with tcgen05.st and shared by both
+    issuers) vs k_mlp_bwd: same feature gradients bit for bit, weight gradients up to fp32 accumulation order."""
+    from nerf2mesh_b200._lib import call
+    try:
+        for shading in ("full", "diffuse"):
+            tr, b = make(shading, N=192)
+            stage(tr, b)
+            tr._fill_params(shading == "full", True)
+            tr.loss_acc.zero_(); tr.march(); tr.encode_fwd(); tr.mlp_fwd(); tr.composite_loss()
+            res = []
+            for pipelined, issuers in ((0, 1), (1, 2)):
+                call("n2m_s0_set_mlp_bwd_pipelined", pipelined); call("n2m_s0_set_mlp_bwd_issuers", issuers)
+                tr.g_mlp.zero_(); tr.denc_tiles.zero_()
+                tr.mlp_bwd()
+                torch.cuda.synchronize()
+                res.append((tr.denc_tiles.clone(), tr.g_mlp.clone()))
+            M = int(tr.counters[1].item())
+            d0, d1 = untile(res[0][0], M), untile(res[1][0], M)
+            assert torch.equal(d0, d1), (d0 - d1).abs().max()
+            g0, g1 = res[0][1], res[1][1]
+            assert (g0 - g1).abs().max().item() <= 1e-4 * g0.abs().max().item()
+    finally:
+        call("n2m_s0_set_mlp_bwd_pipelined", 0); call("n2m_s0_set_mlp_bwd_issuers", 1)
