@@ -599,7 +599,10 @@ class Stage0Trainer:
         """NeRFRenderer.update_extra_state (renderer.py:1074-1149): evaluate the density field at one jittered
         point per grid cell and cascade (hash gather + sigma_net on tensor cores), grid = max(grid * decay, sigma),
         threshold = min(mean(clamp(grid, 0)), density_thresh), repack the bitfield.  Everything stays on the
-        device (the reference syncs for `mean_density.item()`)."""
+        device (the reference syncs for `mean_density.item()`).
+        With `step(next_batch=...)` a batch whose march is already staged on the side stream keeps the samples of the previous
+        bitfield (the update then takes effect one step later than in the reference); call `drop_prefetch()` first for the
+        reference's exact order."""
         c = self.cfg
         H, cells = c.grid_size, c.grid_size ** 3
         dev = self.device
