@@ -122,3 +122,80 @@ def test_peer_adam_slices_cover_rows_and_stay_aligned():
             lo = [min(R, r * per) for r in range(W)]
             hi = [min(R, (r + 1) * per) for r in range(W)]
             assert lo[0] == 0 and hi[-1] == R and all(hi[r] == lo[r + 1] for r in range(W - 1))
+
+
+def test_step_orchestration_call_sequence(monkeypatch):
+    """Stage0Trainer's per-step orchestration (ray-range parts, TV fork, split optimizer, experimental level pipeline) with the CUDA
+    layer mocked out: the sequence of C-ABI calls on every path, no GPU needed.  Guards the host logic that the GPU tests only
+    exercise on a B200."""
+    import types
+    import nerf2mesh_b200.stage0 as S0
+
+    calls = []
+    monkeypatch.setattr(S0, "call", lambda name, *a: calls.append((name, a)))
+    monkeypatch.setattr(S0, "ptr", lambda t: 0)
+    monkeypatch.setattr(S0, "stream", lambda: 0)
+
+    class FakeStream:
+        def wait_stream(self, o): pass
+        def wait_event(self, e): pass
+        def synchronize(self): pass
+
+    class FakeEvent:
+        def record(self, s=None): pass
+
+    class Ctx:
+        def __init__(self, s): pass
+        def __enter__(self): return self
+        def __exit__(self, *a): return False
+
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: FakeStream())
+    monkeypatch.setattr(torch.cuda, "Stream", lambda *a, **k: FakeStream())
+    monkeypatch.setattr(torch.cuda, "Event", lambda *a, **k: FakeEvent())
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: Ctx(s))
+
+    class T:
+        def zero_(self): return self
+        def __getitem__(self, k): return self
+        def data_ptr(self): return 0
+
+    tr = object.__new__(S0.Stage0Trainer)
+    tr.cfg = types.SimpleNamespace(lambda_tv=1e-8, eps=1e-15, num_levels=16)
+    slot = types.SimpleNamespace(**{k: T() for k in ("rays_o", "rays_d", "gt", "bg", "noises", "rays", "counters", "tbuf", "recs")}, has_alpha=True)
+    tr.slots, tr.cur = [slot, slot], 0
+    for k in ("table", "offsets", "enc_tiles", "opt_state", "wpack", "out", "dout", "image", "weights_sum", "depth", "denc_tiles",
+              "color_master", "gtable", "m_table", "v_table", "mlp", "g_mlp", "m_mlp", "v_mlp", "loss_acc"):
+        setattr(tr, k, T())
+    tr.gtables, tr.g_mlps = [tr.gtable], [tr.g_mlp]
+    tr.params = S0.S0Params(); tr.Mcap, tr.N, tr.rows, tr.parity, tr.device = 128, 4, 160, 0, "cpu"
+    tr.tv_overlap, tr._tv_stream, tr._part_streams, tr.part_mode = True, None, [], "chains"
+    tr._mlp_stream = tr._adam_stream = None
+    tr.level_pipe, tr._ev_first_pass, tr.scatter_level_cuts = False, [], ()
+    tr._offsets_host = list(range(0, 170, 10))
+
+    chain = ["n2m_s0_encode_fwd_part", "n2m_s0_mlp_fwd_part", "n2m_s0_composite_loss_part", "n2m_s0_mlp_bwd_part", "n2m_s0_encode_bwd_part"]
+    adam = ["n2m_s0_adam_head", "n2m_s0_adam_mlp", "n2m_s0_adam_tables", "n2m_s0_adam_post"]
+
+    def names():
+        return [n for n, _ in calls]
+
+    tr.nparts = 1
+    tr._compute_then_adam()
+    assert names() == [chain[0], "n2m_s0_tv"] + chain[1:] + adam
+    for P_ in (2, 4):
+        calls.clear(); tr.nparts = P_
+        tr._compute_then_adam()
+        assert names() == ["n2m_s0_tv"] + chain * P_ + adam
+        parts = [a[-3:-1] for n, a in calls if n == "n2m_s0_mlp_bwd_part"]
+        assert parts == [(k, P_) for k in range(P_)]
+    calls.clear(); tr.nparts, tr.part_mode = 2, "pipeline"
+    tr._compute_then_adam()
+    assert names() == [chain[0], *chain[1:4], chain[0], *chain[1:4], "n2m_s0_tv", chain[4], chain[4]] + adam
+    # experimental level pipeline: two scatter passes per part, optimizer of the first range before the second range's rows
+    calls.clear(); tr.part_mode, tr.level_pipe, tr.scatter_level_cuts = "chains", True, (10,)
+    tr._compute_then_adam()
+    lv = [(a[-5], a[-4], a[-3], a[-2]) for n, a in calls if n == "n2m_s0_encode_bwd_levels"]
+    assert lv == [(0, 2, 0, 10), (0, 2, 10, 16), (1, 2, 0, 10), (1, 2, 10, 16)]
+    rng = [(a[6], a[7]) for n, a in calls if n == "n2m_s0_adam_tables_range"]
+    assert rng == [(0, 100), (100, 160)]
+    assert names()[-5:] == ["n2m_s0_adam_head", "n2m_s0_adam_tables_range", "n2m_s0_adam_mlp", "n2m_s0_adam_tables_range", "n2m_s0_adam_post"]
