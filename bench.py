@@ -222,6 +222,7 @@ def run_ours(args):
     tr.part_mode = args.part_mode
     tr.scatter_level_cuts = tuple(int(x) for x in args.scatter_cuts.split(",") if x)
     tr.level_pipe = bool(args.level_pipe)
+    tr.l2_persist_mb = int(args.l2_persist_mb)
     _lib.call("n2m_s0_set_mlp_bwd_pipelined", 0 if args.mlp_bwd == "single" else 1)
     _lib.call("n2m_s0_set_mlp_bwd_issuers", 2 if args.mlp_bwd == "two-tile-2issuers" else 1)
     if args.mlp_fwd_compact:
@@ -363,7 +364,7 @@ def run_ours(args):
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16",
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "rays_per_batch": NUM_RAYS, "global_rays": NUM_RAYS * world,
-                           "samples_per_step": samples_total / K, "parallelism": f"dp{world}" + ("" if world == 1 else f"-{dp_used}"), "cuda_graph": not args.no_graph, "ray_range_parts": args.parts, "part_mode": args.part_mode, "scatter_level_cuts": list(tr.scatter_level_cuts), "mlp_fwd_compact": bool(args.mlp_fwd_compact), "level_pipe": bool(args.level_pipe), "mlp_bwd": args.mlp_bwd, "march_prefetch": not args.no_prefetch,
+                           "samples_per_step": samples_total / K, "parallelism": f"dp{world}" + ("" if world == 1 else f"-{dp_used}"), "cuda_graph": not args.no_graph, "ray_range_parts": args.parts, "part_mode": args.part_mode, "scatter_level_cuts": list(tr.scatter_level_cuts), "mlp_fwd_compact": bool(args.mlp_fwd_compact), "level_pipe": bool(args.level_pipe), "mlp_bwd": args.mlp_bwd, "l2_persist_mb": int(args.l2_persist_mb), "march_prefetch": not args.no_prefetch,
                            "l2": "inputs cycle over 8 batches; tables+grads+Adam state (0.6 GB touched per step) exceed the 126 MB L2"},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -388,6 +389,8 @@ def main():
     ap.add_argument("--mlp-fwd-compact", action="store_true", help="experimental: MLP forward with the compact smem layout (3 CTAs/SM)")
     ap.add_argument("--mlp-bwd", default="single", choices=["single", "two-tile", "two-tile-2issuers"],
                     help="MLP backward kernel: one tile per CTA (default), two tiles + one issuer warp, or (experimental) two issuer warps")
+    ap.add_argument("--l2-persist-mb", type=int, default=0,
+                    help="experimental (with --scatter-cuts and --level-pipe): persisting-L2 carve-out for the gradient rows of the active scatter pass")
     ap.add_argument("--level-pipe", action="store_true",
                     help="experimental (with one --scatter-cuts level): optimizer of the first level range under the scatter of the second")
     ap.add_argument("--scatter-cuts", default="", help="experimental: comma-separated hash levels at which the scatter is cut into "

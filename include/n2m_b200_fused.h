@@ -169,6 +169,12 @@ int n2m_s0_encode_bwd(const n2m_s0_params* p, const void* recs, const int32_t* c
                       const float* rays_o, const float* rays_d, const void* denc_tiles, const void* table,
                       const int32_t* offsets, void* gtable, const float* loss_scale, n2m_stream_t stream);
 
+/* EXPERIMENTAL (compiled, not yet measured): L2 residency controls.  n2m_l2_persist_limit sets the device's persisting-L2 carve-out
+ * (clamped to the device maximum, *granted receives the value); n2m_l2_window marks [base, base + bytes) as persisting with the given
+ * hit ratio for kernels launched or captured on `stream` afterwards (base NULL or bytes 0 switches the window off). */
+int n2m_l2_persist_limit(uint64_t bytes, uint64_t* granted);
+int n2m_l2_window(n2m_stream_t stream, const void* base, uint64_t bytes, float hit_ratio);
+
 /* Ray-range parts.  The stages between march and optimizer can be run on `nparts` (1, 2, 4 or 8) contiguous ray ranges
  * of the batch -- part k covers rays [N*k/nparts, N*(k+1)/nparts) and their (contiguous, ray-ordered) samples -- so that
  * independent chains  gather -> MLP -> composite -> MLP backward -> scatter  of different parts can be in flight on

@@ -7,6 +7,7 @@
 // opt_state (device float[8]): [0] loss_scale  [1] growth_tracker  [2] adam step t  [3] found_inf
 //                              [4] lr (host-written)  [5] 1 - beta1^t  [6] sqrt(1 - beta2^t)  [7] 1 / loss_scale
 #include "n2m_common.cuh"
+#include <cstring>
 #include "../../include/n2m_b200_fused.h"
 
 namespace n2m {
@@ -223,4 +224,37 @@ extern "C" int n2m_s0_adam(void* table, void* color_master, void* gtable, float*
     if (int e = n2m_s0_adam_tables(table, color_master, gtable, m_table, v_table, rows, opt_state, eps, stream)) return e;
     if (int e = n2m_s0_adam_mlp(mlp_params, g_mlp, m_mlp, v_mlp, wpack, opt_state, eps, stream)) return e;
     return n2m_s0_adam_post(opt_state, stream);
+}
+
+
+/* ---- L2 residency controls (experimental, compiled only): an access-policy window marks [base, base + bytes) as 'persisting'
+ * for kernels subsequently launched (or captured) on `stream`; the spread REDs of the hash-gradient scatter cost 1.40 SM-cycles
+ * per lane when their target rows are in L2 and 2.19 at the whole table's 98 MB footprint (profiles/redbench.py). ---- */
+extern "C" int n2m_l2_persist_limit(uint64_t bytes, uint64_t* granted) {
+    int dev = 0, max_persist = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+    if (e != cudaSuccess) return fail("l2_persist_limit", cudaGetErrorString(e));
+    const size_t want = (size_t)(bytes < (uint64_t)max_persist ? bytes : (uint64_t)max_persist);
+    e = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+    if (e != cudaSuccess) return fail("l2_persist_limit", cudaGetErrorString(e));
+    if (granted) *granted = (uint64_t)want;
+    return 0;
+}
+
+extern "C" int n2m_l2_window(n2m_stream_t stream, const void* base, uint64_t bytes, float hit_ratio) {
+    int dev = 0, max_win = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+    if (e != cudaSuccess) return fail("l2_window", cudaGetErrorString(e));
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof(attr));
+    attr.accessPolicyWindow.base_ptr = const_cast<void*>(base);
+    attr.accessPolicyWindow.num_bytes = base ? (size_t)(bytes < (uint64_t)max_win ? bytes : (uint64_t)max_win) : 0;    /* 0 bytes = window off */
+    attr.accessPolicyWindow.hitRatio = hit_ratio;
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    e = cudaStreamSetAttribute(as_stream(stream), cudaStreamAttributeAccessPolicyWindow, &attr);
+    if (e != cudaSuccess) return fail("l2_window", cudaGetErrorString(e));
+    return 0;
 }

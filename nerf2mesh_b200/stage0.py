@@ -68,6 +68,8 @@ _lib.register({
     "n2m_s0_set_prof": [P],
     "n2m_s0_set_mlp_fwd_compact": [I],
     "n2m_s0_set_mlp_bwd_issuers": [I],
+    "n2m_l2_persist_limit": [ctypes.c_uint64, P],
+    "n2m_l2_window": [P, P, ctypes.c_uint64, F],
     "n2m_s0_set_gather_carveout": [I],
 })
 _lib.lib.n2m_s0_wpack_bytes.restype = c_uint32
@@ -191,6 +193,8 @@ class Stage0Trainer:
         self.part_mode = "chains"           # "pipeline": gathers/scatters on one stream, MLPs on a high-priority one; "chains": a stream per part
         self._mlp_stream = None
         self._adam_stream = None
+        self.l2_persist_mb = 0              # experimental: persisting-L2 carve-out (MB) used for the gradient rows of the active scatter pass
+        self._l2_granted = None
         self.level_pipe = False             # experimental: optimizer of the first level range under the scatter of the second
         self._ev_first_pass = []
         self.scatter_level_cuts = ()        # experimental: e.g. (10,) = two scatter passes, levels 0-9 then 10-15 (include/n2m_b200_fused.h)
@@ -453,10 +457,29 @@ class Stage0Trainer:
         cut = int(self.scatter_level_cuts[0])
         args = (self._pp(), ptr(self.recs), ptr(self.counters), self.Mcap, ptr(self.rays_o), ptr(self.rays_d), ptr(self.denc_tiles),
                 ptr(self.table), ptr(self.offsets), ptr(self.gtables[self.parity]), ptr(self.opt_state), k, P_)
+        self._l2_window_rows(0, self._offsets_host[cut])
         call("n2m_s0_encode_bwd_levels", *args, 0, cut, stream())
         ev = torch.cuda.Event(); ev.record(torch.cuda.current_stream())
         self._ev_first_pass.append(ev)
+        self._l2_window_rows(self._offsets_host[cut], self.rows)
         call("n2m_s0_encode_bwd_levels", *args, cut, self.cfg.num_levels, stream())
+        self._l2_window_rows(0, 0)
+
+    def _l2_window_rows(self, row_lo, row_hi):
+        """experimental (`l2_persist_mb` > 0): mark the gradient rows [row_lo, row_hi) as L2-persisting for the launches that follow
+        on the current stream; (0, 0) switches the window off."""
+        if not self.l2_persist_mb:
+            return
+        if self._l2_granted is None:
+            g = ctypes.c_uint64(0)
+            call("n2m_l2_persist_limit", int(self.l2_persist_mb) << 20, ctypes.byref(g))
+            self._l2_granted = int(g.value)
+        nbytes = (row_hi - row_lo) * 16
+        if nbytes <= 0 or self._l2_granted == 0:
+            call("n2m_l2_window", stream(), None, 0, 0.0)
+            return
+        base = self.gtables[self.parity].data_ptr() + row_lo * 16
+        call("n2m_l2_window", stream(), ctypes.c_void_p(base), nbytes, min(1.0, self._l2_granted / nbytes))
 
     def _compute_then_adam(self):
         """forward + backward + optimizer of one step.  Default: `_compute()` then `adam()`.
@@ -505,7 +528,7 @@ class Stage0Trainer:
             key = (name, self.parity)
         else:
             key = (name, self.cur, self.parity, int(self.params.shading_full), int(self.params.gt_has_alpha), int(self.nparts),
-                   bool(self.tv_overlap), self.part_mode, tuple(self.scatter_level_cuts), bool(self.level_pipe))
+                   bool(self.tv_overlap), self.part_mode, tuple(self.scatter_level_cuts), bool(self.level_pipe), int(self.l2_persist_mb))
         g = self._graphs.get(key)
         if g is None:
             g = torch.cuda.CUDAGraph()

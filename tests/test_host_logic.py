@@ -171,6 +171,7 @@ def test_step_orchestration_call_sequence(monkeypatch):
     tr.tv_overlap, tr._tv_stream, tr._part_streams, tr.part_mode = True, None, [], "chains"
     tr._mlp_stream = tr._adam_stream = None
     tr.level_pipe, tr._ev_first_pass, tr.scatter_level_cuts = False, [], ()
+    tr.l2_persist_mb, tr._l2_granted = 0, None
     tr._offsets_host = list(range(0, 170, 10))
 
     chain = ["n2m_s0_encode_fwd_part", "n2m_s0_mlp_fwd_part", "n2m_s0_composite_loss_part", "n2m_s0_mlp_bwd_part", "n2m_s0_encode_bwd_part"]
@@ -199,3 +200,27 @@ def test_step_orchestration_call_sequence(monkeypatch):
     rng = [(a[6], a[7]) for n, a in calls if n == "n2m_s0_adam_tables_range"]
     assert rng == [(0, 100), (100, 160)]
     assert names()[-5:] == ["n2m_s0_adam_head", "n2m_s0_adam_tables_range", "n2m_s0_adam_mlp", "n2m_s0_adam_tables_range", "n2m_s0_adam_post"]
+
+
+def test_l2_window_bookkeeping(monkeypatch):
+    """experimental L2 residency hook: window = gradient rows of the active level range, hit ratio = granted carve-out / window,
+    switched off after the last pass (mocked CUDA layer)."""
+    import types
+    import nerf2mesh_b200.stage0 as S0
+    calls = []
+    monkeypatch.setattr(S0, "call", lambda name, *a: calls.append((name, a)))
+    monkeypatch.setattr(S0, "stream", lambda: 7)
+    tr = object.__new__(S0.Stage0Trainer)
+    tr.l2_persist_mb, tr._l2_granted, tr.parity, tr.rows = 64, 1000, 0, 160
+    tr.gtables = [types.SimpleNamespace(data_ptr=lambda: 4096)]
+    tr._l2_window_rows(0, 100)
+    tr._l2_window_rows(100, 160)
+    tr._l2_window_rows(0, 0)
+    (n0, a0), (n1, a1), (n2, a2) = calls
+    assert n0 == n1 == n2 == "n2m_l2_window" and a0[0] == 7
+    assert (a0[1].value, a0[2], round(a0[3], 6)) == (4096, 1600, 0.625)
+    assert (a1[1].value, a1[2], a1[3]) == (4096 + 1600, 960, 1.0)
+    assert a2[1] is None and a2[2] == 0
+    tr.l2_persist_mb = 0; calls.clear()
+    tr._l2_window_rows(0, 100)
+    assert calls == []
