@@ -32,6 +32,9 @@
  *   counters   int32 [16]: [0] M (total samples marched), [1] min(M, Mcap), [2] overflow flag, [3] unused,
  *              [4..12] sample offset of the first ray of every eighth of the batch (ray N*e/8, e = 0..8; [4] = 0,
  *              [12] = [1]): the boundaries of the ray-range parts of the *_part entry points below.
+ *              [13] += 1 for every march whose M exceeded Mcap, [14] = largest M seen (persistent capacity accounting: the rays
+ *              that do not fit -- always the last rays of the batch -- are rendered as background and get no gradient, which
+ *              the reference never does (it allocates exactly M, raymarching.py:232-238); hosts must watch [13] and grow Mcap).
  *              Entry points without parts (and nparts == 1) read only [1], so hand-filled 4-entry arrays keep working.
  *   wpack      packed fp16 MLP weights in tensor-core tile layout (n2m_s0_pack_weights).
  */
@@ -128,7 +131,8 @@ int n2m_s0_encode_points(const n2m_s0_params* p, const float* xyz, const float* 
                          const void* table, const int32_t* offsets, void* enc_tiles, n2m_stream_t stream);
 
 /* density-grid update pieces (NeRFRenderer.update_extra_state, renderer.py:1074-1149):
- *   grid_points : jittered centres of cells [first_cell, first_cell+count) of one cascade, Morton order; noise [count,3] in [0,1)
+ *   grid_points : jittered centres of cells [first_cell, first_cell+count) of one cascade, Morton order; noise [H^3,3] in [0,1) is the
+ *                 cascade's whole draw in the reference's meshgrid order (row x*H*H + y*H + z), i.e. torch.rand_like(cas_xyzs)
  *   grid_update : cells[i] = max(cells[i] * decay, sigma_i) where both >= 0 (sigma_i = out[i].x)
  *   packbits_dev: bit = grid > min(*mean_density, density_thresh), threshold read on the device */
 int n2m_s0_grid_points(uint32_t H, uint32_t first_cell, uint32_t count, float cas_bound, const float* noise, float* xyz,
@@ -234,6 +238,16 @@ int n2m_s0_adam_tables_range(void* table, void* color_master, void* gtable, floa
 int n2m_s0_adam_mlp(float* mlp_params, float* g_mlp, float* m_mlp, float* v_mlp, void* wpack, const float* opt_state, float eps,
                     n2m_stream_t stream);
 int n2m_s0_adam_post(float* opt_state, n2m_stream_t stream);
+
+/* EMA of the parameters = torch_ema.ExponentialMovingAverage as the reference's Trainer holds it (nerf/utils.py:544-545, decay 0.95
+ * from main.py:241): `update` once per EPOCH (utils.py:1213-1214), parameters swapped with the shadow for evaluation
+ * (utils.py:1250-1252,1340-1341) and for the 'best' checkpoint (utils.py:1389-1401).  shadow_density [rows] f32, shadow_color [rows] float2,
+ * shadow_mlp [7648] f32.  ema_update: shadow -= one_minus_decay * (shadow - param).  ema_swap: params <-> shadow in place, fp16 working
+ * copies (table colour half2, wpack) refreshed. */
+int n2m_s0_ema_update(const void* table, const void* color_master, const float* mlp_params, float* shadow_density, void* shadow_color,
+                      float* shadow_mlp, uint32_t rows, float one_minus_decay, n2m_stream_t stream);
+int n2m_s0_ema_swap(void* table, void* color_master, float* mlp_params, float* shadow_density, void* shadow_color, float* shadow_mlp,
+                    uint32_t rows, void* wpack, n2m_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Data-parallel optimizer fused with its collective over NVLink peer memory (csrc/dp.cu).

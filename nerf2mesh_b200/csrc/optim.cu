@@ -163,6 +163,45 @@ k_adam_head(const float* __restrict__ g, uint32_t n, float* __restrict__ st) {
     st[7] = 1.f / st[0];
 }
 
+// ---- EMA of the parameters (torch_ema.ExponentialMovingAverage as the reference's Trainer uses it: created at
+// nerf/utils.py:544-545 with decay 0.95, `update()` ONCE PER EPOCH at utils.py:1213-1214, swapped in for evaluation at
+// utils.py:1250-1252 / 1340-1341 and for the 'best' checkpoint at :1389-1401).  shadow -= (1 - decay) * (shadow - param), in the
+// library's operation order (tmp = shadow - param; tmp *= one_minus_decay; shadow -= tmp).
+__global__ void __launch_bounds__(256)
+k_ema_update(const TableEntry* __restrict__ table, const float2* __restrict__ cmaster, const float* __restrict__ mlp,
+             float* __restrict__ sh_d, float2* __restrict__ sh_c, float* __restrict__ sh_mlp, uint32_t rows, uint32_t n_mlp,
+             float one_minus_decay) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < rows) {
+        const float pd = table[i].d; const float2 pc = cmaster[i];
+        float sd = sh_d[i]; float2 sc = sh_c[i];
+        sd = __fsub_rn(sd, __fmul_rn(__fsub_rn(sd, pd), one_minus_decay));
+        sc.x = __fsub_rn(sc.x, __fmul_rn(__fsub_rn(sc.x, pc.x), one_minus_decay));
+        sc.y = __fsub_rn(sc.y, __fmul_rn(__fsub_rn(sc.y, pc.y), one_minus_decay));
+        sh_d[i] = sd; sh_c[i] = sc;
+    }
+    if (i < n_mlp) {
+        const float s = sh_mlp[i];
+        sh_mlp[i] = __fsub_rn(s, __fmul_rn(__fsub_rn(s, mlp[i]), one_minus_decay));
+    }
+}
+
+// parameters <-> shadow, in place (ema.store(); ema.copy_to()  ==  swap;   ema.restore()  ==  swap back); the fp16 working copy of
+// the colour features is refreshed from the swapped-in fp32 values
+__global__ void __launch_bounds__(256)
+k_ema_swap(TableEntry* __restrict__ table, float2* __restrict__ cmaster, float* __restrict__ mlp,
+           float* __restrict__ sh_d, float2* __restrict__ sh_c, float* __restrict__ sh_mlp, uint32_t rows, uint32_t n_mlp) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < rows) {
+        TableEntry e = table[i]; const float2 pc = cmaster[i];
+        const float sd = sh_d[i]; const float2 sc = sh_c[i];
+        sh_d[i] = e.d; sh_c[i] = pc;
+        e.d = sd; e.c = __floats2half2_rn(sc.x, sc.y);
+        table[i] = e; cmaster[i] = sc;
+    }
+    if (i < n_mlp) { const float s = sh_mlp[i]; sh_mlp[i] = mlp[i]; mlp[i] = s; }
+}
+
 }  // namespace
 }  // namespace n2m
 
@@ -226,6 +265,32 @@ extern "C" int n2m_s0_adam(void* table, void* color_master, void* gtable, float*
     return n2m_s0_adam_post(opt_state, stream);
 }
 
+
+/* EMA shadow update over the hash tables (fp32 density feature in the table, fp32 colour masters) and the MLP parameters */
+extern "C" int n2m_s0_ema_update(const void* table, const void* color_master, const float* mlp_params, float* shadow_density,
+                                 void* shadow_color, float* shadow_mlp, uint32_t rows, float one_minus_decay, n2m_stream_t stream) {
+    N2M_REQUIRE(table && color_master && mlp_params && shadow_density && shadow_color && shadow_mlp, "s0_ema_update", "null pointer");
+    const uint32_t n = n2m_s0_mlp_param_count();
+    const uint32_t work = rows > n ? rows : n;
+    if (work == 0) return 0;
+    k_ema_update<<<div_up(work, 256u), 256, 0, as_stream(stream)>>>(static_cast<const TableEntry*>(table), static_cast<const float2*>(color_master),
+                                                                     mlp_params, shadow_density, static_cast<float2*>(shadow_color), shadow_mlp,
+                                                                     rows, n, one_minus_decay);
+    return check_launch("s0_ema_update");
+}
+
+/* swap parameters and EMA shadow in place (+ weight repack) */
+extern "C" int n2m_s0_ema_swap(void* table, void* color_master, float* mlp_params, float* shadow_density, void* shadow_color,
+                               float* shadow_mlp, uint32_t rows, void* wpack, n2m_stream_t stream) {
+    N2M_REQUIRE(table && color_master && mlp_params && shadow_density && shadow_color && shadow_mlp && wpack, "s0_ema_swap", "null pointer");
+    const uint32_t n = n2m_s0_mlp_param_count();
+    const uint32_t work = rows > n ? rows : n;
+    if (work == 0) return 0;
+    k_ema_swap<<<div_up(work, 256u), 256, 0, as_stream(stream)>>>(static_cast<TableEntry*>(table), static_cast<float2*>(color_master), mlp_params,
+                                                                   shadow_density, static_cast<float2*>(shadow_color), shadow_mlp, rows, n);
+    if (int e = check_launch("s0_ema_swap")) return e;
+    return n2m_s0_pack_weights(mlp_params, wpack, stream);
+}
 
 /* ---- L2 residency controls (experimental, compiled only): an access-policy window marks [base, base + bytes) as 'persisting'
  * for kernels subsequently launched (or captured) on `stream`; the spread REDs of the hash-gradient scatter cost 1.40 SM-cycles

@@ -187,6 +187,9 @@ k_s0_scan(int32_t* __restrict__ rays, uint32_t N, uint32_t Mcap, int32_t* __rest
         counters[1] = (int32_t)min(M, Mcap);
         counters[2] = M > Mcap ? 1 : 0;
         counters[3] = 0;
+        // persistent capacity accounting (never reset by the march): steps that overflowed the sample slab, largest M seen
+        if (M > Mcap) counters[13] += 1;
+        counters[14] = max(counters[14], (int32_t)M);
     }
     // part boundaries (n2m_common.cuh part_range): sample offset of the first ray of every eighth of the batch
     if (threadIdx.x <= kPartSlots) {
@@ -792,7 +795,9 @@ k_s0_composite_loss(n2m_s0_params p, const float4* __restrict__ out, const float
 // density-grid update (NeRFRenderer.update_extra_state, renderer.py:1074-1149)
 // ------------------------------------------------------------------------------------------------
 // jittered cell centres of one cascade, cells enumerated in MORTON order (cell m <-> coords morton3D_invert(m)),
-// so sigma lands directly at density_grid[cas, m] (renderer.py:1100-1118)
+// so sigma lands directly at density_grid[cas, m] (renderer.py:1100-1118).  `noise` is the cascade's whole [H^3, 3] draw in the
+// reference's MESHGRID order (row x*H*H + y*H + z, renderer.py:1098-1099,1110: torch.rand_like(cas_xyzs)), so that the same torch
+// generator state gives every cell the same jitter as in the reference.
 __global__ void __launch_bounds__(256)
 k_s0_grid_points(uint32_t H, uint32_t first_cell, uint32_t count, float cas_bound, const float* __restrict__ noise,
                  float* __restrict__ xyz) {
@@ -802,10 +807,11 @@ k_s0_grid_points(uint32_t H, uint32_t first_cell, uint32_t count, float cas_boun
     const float hgs = cas_bound / (float)H;                  // half_grid_size = bound / grid_size (:1105)
     const float span = cas_bound - hgs;
     const uint32_t c[3] = {compact3(m), compact3(m >> 1), compact3(m >> 2)};
+    const uint32_t lin = (c[0] * H + c[1]) * H + c[2];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         const float base = __fadd_rn(__fdiv_rn(__fmul_rn(2.0f, (float)c[a]), (float)(H - 1)), -1.0f);   // 2*coord/(H-1) - 1
-        const float jit = __fmul_rn(__fadd_rn(__fmul_rn(noise[3 * i + a], 2.0f), -1.0f), hgs);           // (rand*2-1)*hgs
+        const float jit = __fmul_rn(__fadd_rn(__fmul_rn(noise[3 * (size_t)lin + a], 2.0f), -1.0f), hgs);   // (rand*2-1)*hgs
         xyz[3 * i + a] = __fadd_rn(__fmul_rn(base, span), jit);
     }
 }

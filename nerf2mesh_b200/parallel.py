@@ -132,6 +132,8 @@ class PeerAdam:
         self.ctx = torch.frombuffer(bytearray(host.raw), dtype=torch.uint8).to(dev)
         torch.cuda.synchronize()
         dist.barrier(group=group)
+        # from here on trainer.color_master is stale (the masters live in the per-rank slices): exports must gather them
+        t._color_master_provider = self.gather_color_master
 
     def run(self, parity):
         """Enqueue barrier -> reduce-scatter + Adam + all-gather -> barrier for gradient parity `parity`."""

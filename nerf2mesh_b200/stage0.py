@@ -71,6 +71,8 @@ _lib.register({
     "n2m_l2_persist_limit": [ctypes.c_uint64, P],
     "n2m_l2_window": [P, P, ctypes.c_uint64, F],
     "n2m_s0_set_gather_carveout": [I],
+    "n2m_s0_ema_update": [P, P, P, P, P, P, U, F, P],
+    "n2m_s0_ema_swap": [P, P, P, P, P, P, U, P, P],
 })
 _lib.lib.n2m_s0_wpack_bytes.restype = c_uint32
 _lib.lib.n2m_s0_mlp_param_count.restype = c_uint32
@@ -103,8 +105,10 @@ class Stage0Config:
         self.lambda_entropy = float(lambda_entropy)          # main.py --lambda_entropy (garden recipe: 1e-3)
         self.lr, self.eps = float(lr), float(eps)
         self.num_rays = int(num_rays)
-        # sample capacity of the per-step buffers; rays whose samples do not fit are dropped for the
-        # step (like the reference's `offset + num_steps > M` guard, raymarching.cu:521)
+        # sample capacity of the per-step buffers.  The reference allocates exactly M samples per step (raymarching.py:232-238)
+        # and never drops a ray; here a step whose M exceeds the capacity renders the rays that do not fit (the LAST rays of the
+        # batch) as background without gradient -- counted on the device (counters[13], [14]); Stage0Trainer.check_capacity()
+        # reports / grows the slab, training loops call it at every density-grid update.
         self.max_samples = int(max_samples) if max_samples else self.num_rays * 128
         self.max_samples = (self.max_samples + 127) // 128 * 128
         self.loss_scale = float(loss_scale)
@@ -121,9 +125,10 @@ class _Slot:
         self.counters = torch.zeros(16, dtype=torch.int32, device=dev)    # include/n2m_b200_fused.h: [4..12] part boundaries
         self.tbuf = torch.empty(N * max_steps * 2, device=dev)
         self.recs = torch.zeros(Mc, 4, device=dev)
+        self.cam_nf = torch.zeros(N, 2, device=dev)                      # per-ray (near, far) clamp, renderer.py:689-691
         self.has_alpha = True
 
-    def load(self, rays_o, rays_d, gt, bg, noises=None):
+    def load(self, rays_o, rays_d, gt, bg, noises=None, cam_near_far=None):
         N = self.rays_o.shape[0]
         if gt.shape[-1] == 3:
             self.gt.view(-1)[: N * 3].view(N, 3).copy_(gt, non_blocking=True)       # packed [N,3] at the front
@@ -135,6 +140,8 @@ class _Slot:
         self.bg.copy_(bg, non_blocking=True)
         if noises is not None:
             self.noises.copy_(noises, non_blocking=True)
+        if cam_near_far is not None:
+            self.cam_nf.copy_(cam_near_far, non_blocking=True)
 
 
 class Stage0Trainer:
@@ -186,7 +193,8 @@ class Stage0Trainer:
         self.loss_acc = torch.zeros(4, device=dev)          # [0] rgb(+mask) loss, [1] sum |spec|^2
         self.params = S0Params()
         self._fill_params(shading_full=True, gt_has_alpha=True)
-        self.tv_overlap = True              # TV gradient as its own launch overlapped with the MLP kernels (tv mode 2)
+        self.use_cam_near_far = False       # clamp (near, far) with the per-ray values in the slot's cam_nf (--enable_cam_near_far)
+        self._tv_overlap = True             # TV gradient as its own launch overlapped with the MLP kernels (tv mode 2)
         self._tv_stream = None
         self.nparts = 1                     # ray-range parts run as concurrent chains on forked streams (1, 2, 4 or 8)
         self._part_streams = []
@@ -198,13 +206,34 @@ class Stage0Trainer:
         self.level_pipe = False             # experimental: optimizer of the first level range under the scatter of the second
         self._ev_first_pass = []
         self.scatter_level_cuts = ()        # experimental: e.g. (10,) = two scatter passes, levels 0-9 then 10-15 (include/n2m_b200_fused.h)
-        call("n2m_s0_set_tv_mode", 2 if self.tv_overlap else 0)
+        call("n2m_s0_set_tv_mode", 2 if self._tv_overlap else 0)
+        # EMA of the parameters (Trainer(ema_decay=0.95), main.py:241): shadow buffers are allocated by enable_ema()
+        self.ema_decay = None
+        self.ema_num_updates = 0
+        self._ema = None
+        self._ema_swapped = False
+        self._color_master_provider = None  # PeerAdam: the fp32 colour masters live in per-rank slices (parallel.py)
         self.gtables = [self.gtable]        # PeerAdam adds a second parity (parallel.py)
         self.g_mlps = [self.g_mlp]
         self.parity = 0
         self.global_step = 0
         self._graphs = {}
         self.reset_parameters(seed)
+
+    @property
+    def tv_overlap(self):
+        return self._tv_overlap
+
+    @tv_overlap.setter
+    def tv_overlap(self, on):
+        """True: the TV gradient is its own launch (n2m_s0_tv) on a forked stream; False: it is evaluated inside the scatter kernel.
+        The kernel-side mode is a process-wide switch, so it is set here together with the host-side flag (and captured graphs of
+        the other mode are dropped)."""
+        on = bool(on)
+        if on != self._tv_overlap:
+            self._tv_overlap = on
+            call("n2m_s0_set_tv_mode", 2 if on else 0)
+            self._graphs = {k: g for k, g in self._graphs.items() if k[0] in ("march", "adam", "peer_adam")}
 
     # current slot's buffers under their historical names
     rays_o = property(lambda self: self.slots[self.cur].rays_o)
@@ -259,7 +288,9 @@ class Stage0Trainer:
 
     def export_reference_state(self):
         ed = torch.empty(self.rows, 1, device=self.device); ec = torch.empty(self.rows, 2, device=self.device)
-        call("n2m_s0_unpack_tables", ptr(self.table), ptr(self.color_master), self.rows, ptr(ed), ptr(ec), stream())
+        # under PeerAdam the fp32 colour masters are sharded over the ranks: gather them (a collective -- every rank must call)
+        cm = self.color_master if self._color_master_provider is None else self._color_master_provider().contiguous()
+        call("n2m_s0_unpack_tables", ptr(self.table), ptr(cm), self.rows, ptr(ed), ptr(ec), stream())
         # the complete stage-0 `NeRFNetwork.state_dict()` key set (renderer.py:92-117, grid.py:135-140, network.py:66-75): loads
         # into the reference model with strict=True (no individual codes / SDF variance in the default recipes)
         state = {"encoder.embeddings": ed, "encoder_color.embeddings": ec,
@@ -272,16 +303,78 @@ class Stage0Trainer:
             state[name] = self.mlp[o:o + n].view(shp).clone(); o += n
         return state
 
-    def save_reference_checkpoint(self, path, epoch=0, stats=None):
-        """A model-only checkpoint in the schema `Trainer.load_checkpoint` reads (nerf/utils.py:1345-1381, 1423-1470):
-        epoch / global_step / stats / stage / mean_density / model."""
+    def save_reference_checkpoint(self, path, epoch=0, stats=None, best=False, full=False):
+        """A checkpoint in the schema `Trainer.save_checkpoint` writes and `Trainer.load_checkpoint` reads (nerf/utils.py:1345-1381,
+        1407-1473): epoch / global_step / stats / stage / mean_density / model (+ 'ema' when `full`).  `best=True` stores the EMA
+        parameters as the model, as the reference does for its best checkpoint (utils.py:1389-1401)."""
         mean = getattr(self, "mean_density", None)
         state = {"epoch": int(epoch), "global_step": int(self.global_step), "stage": 0,
                  "stats": stats or {"loss": [], "valid_loss": [], "results": [], "checkpoints": [], "best_result": None},
-                 "mean_density": float(mean.item()) if mean is not None else 0.0,
-                 "model": {k: v.cpu() for k, v in self.export_reference_state().items()}}
+                 "mean_density": float(mean.item()) if mean is not None else 0.0}
+        if full and self._ema is not None:
+            state["ema"] = {k: ([t.cpu() for t in v] if isinstance(v, list) else v) for k, v in self.ema_state_dict().items()}
+        if best:
+            self.ema_apply()
+        state["model"] = {k: v.cpu() for k, v in self.export_reference_state().items()}
+        if best:
+            self.ema_restore()
         torch.save(state, path)
         return state
+
+    # -------------------------------------------------------------------------------------------
+    # EMA (torch_ema.ExponentialMovingAverage as the reference's Trainer uses it)
+    # -------------------------------------------------------------------------------------------
+    def enable_ema(self, decay=0.95):
+        """Trainer(ema_decay=0.95) (main.py:241; utils.py:544-545): shadow parameters start as a copy of the parameters."""
+        if self._color_master_provider is not None:
+            raise NotImplementedError("EMA with the sharded PeerAdam optimizer: use GradSync, or keep the EMA on one rank")
+        self.ema_decay, self.ema_num_updates, self._ema_swapped = float(decay), 0, False
+        st = self.export_reference_state()
+        self._ema = {"d": st["encoder.embeddings"].reshape(-1).contiguous(), "c": st["encoder_color.embeddings"].contiguous(),
+                     "mlp": self.mlp.clone()}
+
+    def ema_update(self):
+        """`self.ema.update()` -- the reference calls it once per EPOCH (utils.py:1213-1214), not per step.  torch_ema's warm-up:
+        decay = min(decay, (1 + num_updates) / (10 + num_updates)) with num_updates incremented first."""
+        assert self._ema is not None and not self._ema_swapped
+        self.ema_num_updates += 1
+        decay = min(self.ema_decay, (1 + self.ema_num_updates) / (10 + self.ema_num_updates))
+        e = self._ema
+        call("n2m_s0_ema_update", ptr(self.table), ptr(self.color_master), ptr(self.mlp), ptr(e["d"]), ptr(e["c"]), ptr(e["mlp"]),
+             self.rows, 1.0 - decay, stream())
+
+    def _ema_swap(self):
+        e = self._ema
+        call("n2m_s0_ema_swap", ptr(self.table), ptr(self.color_master), ptr(self.mlp), ptr(e["d"]), ptr(e["c"]), ptr(e["mlp"]),
+             self.rows, ptr(self.wpack), stream())
+        self._ema_swapped = not self._ema_swapped
+
+    def ema_apply(self):
+        """`ema.store(); ema.copy_to()` (utils.py:1250-1252): evaluate / export with the averaged parameters.  In place: the live
+        parameters are parked in the shadow buffers until ema_restore()."""
+        if self._ema is not None and not self._ema_swapped:
+            self._ema_swap()
+
+    def ema_restore(self):
+        """`ema.restore()` (utils.py:1340-1341)."""
+        if self._ema is not None and self._ema_swapped:
+            self._ema_swap()
+
+    def ema_state_dict(self):
+        """torch_ema's state_dict() for a 'full' checkpoint (utils.py:1364-1365): shadow parameters in model.parameters() order
+        (encoder, sigma_net, encoder_color, color_net, specular_net: nerf/network.py:66-75)."""
+        assert self._ema is not None and not self._ema_swapped
+        e = self._ema
+        mlps, o = {}, 0
+        for name, shp in MLP_LAYOUT:
+            n = shp[0] * shp[1]
+            mlps[name] = e["mlp"][o:o + n].view(shp).clone(); o += n
+        order = ["encoder.embeddings", "sigma_net.net.0.weight", "sigma_net.net.1.weight", "encoder_color.embeddings",
+                 "color_net.net.0.weight", "color_net.net.1.weight", "color_net.net.2.weight",
+                 "specular_net.net.0.weight", "specular_net.net.1.weight"]
+        tensors = {"encoder.embeddings": e["d"].view(-1, 1).clone(), "encoder_color.embeddings": e["c"].clone(), **mlps}
+        return {"decay": self.ema_decay, "num_updates": self.ema_num_updates, "shadow_params": [tensors[k] for k in order],
+                "collected_params": None}
 
     def export_reference_grads(self):
         """Current (un-scaled) gradients in reference layout -- for parity tests; call before the optimizer."""
@@ -307,7 +400,8 @@ class Stage0Trainer:
         return ctypes.byref(self.params)
 
     def march(self):
-        call("n2m_s0_march", self._pp(), ptr(self.rays_o), ptr(self.rays_d), ptr(self.aabb), None, ptr(self.density_bitfield),
+        call("n2m_s0_march", self._pp(), ptr(self.rays_o), ptr(self.rays_d), ptr(self.aabb),
+             ptr(self.slots[self.cur].cam_nf) if self.use_cam_near_far else None, ptr(self.density_bitfield),
              ptr(self.noises), self.N, ptr(self.rays), ptr(self.counters), ptr(self.tbuf), ptr(self.recs), self.Mcap, stream())
 
     def encode_fwd(self, part=0, nparts=1):
@@ -523,7 +617,7 @@ class Stage0Trainer:
         """Capture-once CUDA graph of `fn` for the current (slot, shading, alpha) configuration."""
         # only what the captured launches actually depend on goes into the key (fewer captures)
         if name == "march":
-            key = (name, self.cur)
+            key = (name, self.cur, bool(self.use_cam_near_far))
         elif name in ("adam", "peer_adam"):
             key = (name, self.parity)
         else:
@@ -544,12 +638,13 @@ class Stage0Trainer:
             fn()
 
     def step(self, rays_o=None, rays_d=None, gt=None, bg_color=None, noises=None, shading="full", lr=None, use_graph=True,
-             grad_sync=None, next_batch=None):
+             grad_sync=None, next_batch=None, cam_near_far=None):
         """One optimizer step on the batch (rays_o, rays_d, gt, bg_color[, noises]).
 
         * tensors given: copied into the step buffers first (pinned host -> async H2D);
           with rays_o=None the buffers of the current slot are used as they are.
-        * `next_batch=(rays_o, rays_d, gt, bg[, noises])`: the NEXT step's batch; its H2D copy and its march
+        * `cam_near_far` [N,2]: per-ray (near, far) clamp (used when `use_cam_near_far` is set; renderer.py:689-691).
+        * `next_batch=(rays_o, rays_d, gt, bg[, noises[, cam_near_far]])`: the NEXT step's batch; its H2D copy and its march
           (which do not depend on the parameters) are enqueued on a side stream and overlap this step's
           compute.  The following step() call must then pass that same batch (its copy and march are skipped).
         * `grad_sync`: callable run between backward and optimizer (data-parallel gradient all-reduce).
@@ -562,7 +657,7 @@ class Stage0Trainer:
             marched = True
         else:
             if rays_o is not None:
-                self.slots[self.cur].load(rays_o, rays_d, gt, bg_color, noises)
+                self.slots[self.cur].load(rays_o, rays_d, gt, bg_color, noises, cam_near_far)
             marched = False
         if lr is not None:
             self.opt_state[4:5].fill_(float(lr))
@@ -639,9 +734,9 @@ class Stage0Trainer:
         for cas in range(c.cascade):
             bound = float(min(2 ** cas, c.bound))
             row = self.density_grid[cas]
+            noise = torch.rand(cells, 3, device=dev)          # == torch.rand_like(cas_xyzs) of the reference (renderer.py:1110)
             for first in range(0, cells, self.Mcap):
                 cnt = min(self.Mcap, cells - first)
-                noise = torch.rand(cnt, 3, device=dev)
                 call("n2m_s0_grid_points", H, first, cnt, bound, ptr(noise), ptr(self._pts), stream())
                 self._pcount.fill_(cnt)
                 call("n2m_s0_encode_points", pp, ptr(self._pts), None, ptr(self._pcount), self.Mcap, ptr(self.table),
@@ -650,6 +745,9 @@ class Stage0Trainer:
                      None, stream())
                 call("n2m_s0_grid_update", ptr(self.out), cnt, float(decay), row.data_ptr() + 4 * first, stream())
         self.mean_density = self.density_grid.clamp(min=0).mean().reshape(1)
+        if self._side is not None:
+            # a prefetched march on the side stream may still be reading the bitfield
+            torch.cuda.current_stream().wait_stream(self._side)
         call("n2m_s0_packbits_dev", ptr(self.density_grid), self.density_bitfield.numel(), ptr(self.mean_density),
              float(density_thresh), ptr(self.density_bitfield), stream())
 
@@ -672,11 +770,41 @@ class Stage0Trainer:
             ro[:n] = rays_o[a:b]; rd[:n] = rays_d[a:b]
             if n < self.N:
                 ro[n:] = 1e6            # padding rays miss the volume
-            slot.load(ro, rd, zeros3, bg if bg is not None else bg_color[a:b], torch.zeros(self.N, device=self.device))
+            if bg is None:
+                bgc = torch.ones(self.N, 3, device=self.device); bgc[:n] = bg_color[a:b]
+            slot.load(ro, rd, zeros3, bg if bg is not None else bgc, torch.zeros(self.N, device=self.device))
             self.loss_acc.zero_()
             self.march(); self.encode_fwd(); self.mlp_fwd(); self.composite_loss()
             img[a:b] = self.image[:n]; ws[a:b] = self.weights_sum[:n]; dep[a:b] = self.depth[:n]
         return img, ws, dep
+
+    def check_capacity(self, grow=True, headroom=1.25):
+        """(host sync) -> (overflowed steps since the last call, largest M seen).  With `grow` the per-step sample buffers are
+        re-allocated for headroom * max M (and the captured graphs dropped) when a step overflowed."""
+        self.drop_prefetch()
+        torch.cuda.synchronize()
+        over = sum(int(s.counters[13].item()) for s in self.slots)
+        max_m = max(int(s.counters[14].item()) for s in self.slots)
+        for s_ in self.slots:
+            s_.counters[13:15] = 0
+        if over and grow:
+            new_cap = (int(max_m * headroom) + 127) // 128 * 128
+            if new_cap > self.Mcap:
+                self._resize_samples(new_cap)
+        return over, max_m
+
+    def _resize_samples(self, Mc):
+        dev = self.device
+        self.Mcap = self.cfg.max_samples = int(Mc)
+        for s_ in self.slots:
+            s_.recs = torch.zeros(Mc, 4, device=dev)
+        self.enc_tiles = torch.zeros(Mc * 64, dtype=torch.float16, device=dev)
+        self.denc_tiles = torch.zeros(Mc * 64, dtype=torch.float16, device=dev)
+        self.out = torch.zeros(Mc, 4, device=dev)
+        self.dout = torch.zeros(Mc, 4, device=dev)
+        if hasattr(self, "_pts"):
+            del self._pts
+        self._graphs = {}
 
     def drop_prefetch(self):
         """Forget a batch staged by `next_batch=` (e.g. when the caller changes its batch sequence)."""

@@ -37,9 +37,7 @@ def _worker(rank, world, port, q):
         for it in range(4):
             tr.step(ro, rd, gt, bg, noises, grad_sync=sync, use_graph=(it > 0))
         torch.cuda.synchronize()
-        st = tr.export_reference_state()
-        if mode == "peer":
-            st["encoder_color.embeddings"] = sync.gather_color_master()
+        st = tr.export_reference_state()         # under PeerAdam this gathers the sharded fp32 colour masters itself
         out[mode] = {k: v.cpu() for k, v in st.items() if "density" not in k and v.is_floating_point() and "aabb" not in k}
         out[mode + "_loss"] = tr.read_loss()
         dist.barrier()

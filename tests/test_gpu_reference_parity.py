@@ -1,0 +1,438 @@
+"""Parity of the BENCHMARKED path -- one fused 4096-ray train step (Stage0Trainer) -- against the reference's OWN CUDA path:
+the unmodified nerf/network.py + nerf/renderer.py + nerf/utils.py (Trainer.train_step / post_train_step) over the unmodified
+raymarching / gridencoder wrappers and the reference's kernels compiled for sm_100a (oracle/ref_stage.py, oracle/_ref).
+
+Both sides start from the same parameters (a few fused warm-up steps away from the initialisation, so that densities, colours
+and gradients are non-trivial), the same rays, ground truth, background colours and march noises (same torch CUDA generator
+state: Trainer.train_step draws bg_color, utils.py:660, then march_rays_train draws the noises, raymarching.py:223).
+
+Configurations: BASELINE config 2 (lego recipe, bound 1, dt_gamma 0, RGBA + mask loss) and config 4 (garden recipe, bound 16 =>
+5 cascades, dt_gamma 1/256, per-ray camera near/far, entropy regulariser, TV with 10x outer weight, RGB images), 4096 rays.
+
+What is asserted
+  * sample counts M, per-ray counts, (t, dt) of every sample: bit-exact;
+  * sigma / rgb per sample, image, weights_sum, depth, loss: north_star's 1e-3 (relative to the tensor scale);
+  * every gradient: the error against the reference's fp16 run must stay within a small multiple of the reference's OWN
+    fp16 quantisation error (|reference fp16 run - reference fp32 run|, measured here) and of its run-to-run spread
+    (two identical reference runs differ through atomic order); the measured numbers go to gpurun_out/parity_<case>.json
+    and are committed under profiles/.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from nerf2mesh_b200 import synthetic as S
+from nerf2mesh_b200.stage0 import MLP_LAYOUT, Stage0Config, Stage0Trainer
+
+pytestmark = pytest.mark.gpu
+
+N = 4096
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+CASES = {
+    "lego": dict(bound=1.0, dt_gamma=0.0, lambda_entropy=0.0, radius=S.LEGO_RADIUS, alpha=True, cam_nf=False, cap=160),
+    "garden": dict(bound=16.0, dt_gamma=1.0 / 256, lambda_entropy=1e-3, radius=1.2, alpha=False, cam_nf=True, cap=256),
+}
+
+
+def _ref_stack():
+    from oracle import ref_stage
+    if not ref_stage.staged():
+        pytest.skip("reference Python files not staged under oracle/_ref/py (build() stages them where /root/reference exists)")
+    return ref_stage, ref_stage.load("ref")
+
+
+def _batch(c, seed):
+    g = torch.Generator().manual_seed(seed)
+    poses = S.orbit_cameras(100, radius=c["radius"], seed=seed)
+    ro, rd, _, _ = S.sample_rays(poses, S.lego_intrinsics(), 800, 800, N, g)
+    return ro, rd
+
+
+def _scene(c):
+    cas = 1 + int(np.ceil(np.log2(c["bound"])))
+    grid, bits, bricks = S.occupancy_regime("converged", cascades=cas, bound=c["bound"])
+    return grid, bits, bricks
+
+
+def _gt(c, ro, rd, bricks):
+    rgba = S.render_bricks(ro, rd, bricks)
+    if c["alpha"]:
+        return rgba
+    return (rgba[:, :3] * rgba[:, 3:] + (1 - rgba[:, 3:])).contiguous()          # RGB images (colmap data): white where nothing is hit
+
+
+def _cam_nf(c, ro):
+    if not c["cam_nf"]:
+        return None
+    d = ro.norm(dim=-1)
+    return torch.stack([(d - 1.1).clamp(min=0.05), d + 1.3], -1).contiguous()   # per-view near/far as colmap_provider derives them
+
+
+def _make_ours(c, bits, grid):
+    cfg = Stage0Config(bound=c["bound"], dt_gamma=c["dt_gamma"], num_rays=N, max_samples=N * c["cap"], lambda_entropy=c["lambda_entropy"])
+    tr = Stage0Trainer(cfg, seed=3)
+    tr.set_occupancy(bits, grid)
+    tr.use_cam_near_far = c["cam_nf"]
+    return tr
+
+
+def _warm_up(tr, c, bricks, steps=40):
+    """a few fused optimizer steps: diffuse first, then full shading (the reference's schedule in miniature)"""
+    for it in range(steps):
+        ro, rd = _batch(c, 100 + it)
+        g = torch.Generator().manual_seed(1000 + it)
+        tr.step(ro, rd, _gt(c, ro, rd, bricks), torch.rand(N, 3, generator=g), torch.rand(N, generator=g),
+                shading="diffuse" if it < steps // 2 else "full", use_graph=False, cam_near_far=_cam_nf(c, ro))
+    torch.cuda.synchronize()
+    assert tr.counters[2].item() == 0, "sample capacity overflow during warm-up"
+
+
+def _ref_trainer(ref_stage, ns, c, state, fp16):
+    opt = ref_stage.default_opt(bound=c["bound"], dt_gamma=c["dt_gamma"], lambda_entropy=c["lambda_entropy"], fp16=fp16,
+                                adaptive_num_rays=False, num_rays=N, enable_cam_near_far=c["cam_nf"])
+    model = ns.make_model(opt)
+    model.load_state_dict({k: v.clone() for k, v in state.items()}, strict=True)       # the complete key set, strict
+    model.cuda().train()
+    tr = ns.utils.Trainer("ngp", opt, model, device=torch.device("cuda"), workspace=None, mute=True,
+                          optimizer=lambda m: torch.optim.Adam(m.get_params(opt.lr), eps=1e-15),        # main.py:221
+                          criterion=torch.nn.MSELoss(reduction="none"), ema_decay=None, fp16=fp16,
+                          use_checkpoint="scratch", use_tensorboardX=False, scheduler_update_every_step=True)
+    tr.global_step = 2000           # past --diffuse_step (utils.py:669-672): 'full' shading
+    tr.ns = ns
+    return tr
+
+
+def _ref_step(rt, data, seed):
+    """the body of Trainer.train_one_epoch for one batch (nerf/utils.py:1163-1177), driven from outside; returns everything"""
+    cap, res, marched = {}, {}, {}
+    h = rt.model.register_forward_hook(lambda m, inp, out: cap.update(sigma=out[0], rgb=out[1], spec=out[2]))
+    ren = rt.model.render
+    rm = rt.ns.raymarching
+    march = rm.march_rays_train
+
+    def render_spy(*a, **k):
+        out = ren(*a, **k)
+        res.update(out)
+        return out
+
+    def march_spy(*a, **k):
+        out = march(*a, **k)
+        marched.update(xyzs=out[0], ts=out[2], rays=out[3])
+        return out
+
+    rt.model.render = render_spy
+    rm.march_rays_train = march_spy
+    try:
+        torch.manual_seed(seed)
+        rt.optimizer.zero_grad()
+        pred, truth, loss = rt.train_step(dict(data))
+        rt.scaler.scale(loss).backward()
+        rt.post_train_step()
+    finally:
+        h.remove()
+        rt.model.render = ren
+        rm.march_rays_train = march
+    grads = {n: p.grad.detach().clone() for n, p in rt.model.named_parameters() if p.grad is not None}
+    torch.cuda.synchronize()
+    rays = marched["rays"]
+    return dict(loss=float(loss), pred=pred.detach(), grads=grads, rays=rays, ts=_by_ray(marched["ts"], rays),
+                sigma=_by_ray(cap["sigma"].detach().float(), rays), rgb=_by_ray(cap["rgb"].detach().float(), rays),
+                ws=res["weights_sum"].detach(), depth=res["depth"].detach(), image=res["image"].detach(), M=int(res["num_points"]))
+
+
+def _by_ray(x, rays):
+    """per-sample rows of the reference (offsets in atomic order) -> ray order (ours: offsets are the exclusive scan)"""
+    off, cnt = rays[:, 0].long(), rays[:, 1].long()
+    start = torch.repeat_interleave(off, cnt)
+    first = torch.cumsum(cnt, 0) - cnt
+    k = torch.arange(int(cnt.sum()), device=x.device) - torch.repeat_interleave(first, cnt)
+    return x[start + k]
+
+
+def _cmp(a, r):
+    a, r = a.double().flatten(), r.double().flatten()
+    scale = r.abs().max().item()
+    return dict(max_err_of_scale=(a - r).abs().max().item() / max(scale, 1e-300), rel_l2=((a - r).norm() / max(r.norm().item(), 1e-300)).item(),
+                cos=(torch.dot(a, r) / (a.norm() * r.norm() + 1e-300)).item(), scale=scale)
+
+
+@pytest.mark.parametrize("name", ["lego", "garden"])
+def test_fused_step_matches_reference_cuda_path(name):
+    c = CASES[name]
+    ref_stage, ns = _ref_stack()
+    grid, bits, bricks = _scene(c)
+    tr = _make_ours(c, bits, grid)
+    _warm_up(tr, c, bricks)
+    state = tr.export_reference_state()
+
+    # ---------------- the batch under test ----------------
+    seed = 4242
+    ro, rd = _batch(c, 7)
+    gt = _gt(c, ro, rd, bricks)
+    cnf = _cam_nf(c, ro)
+    data = dict(rays_o=ro.cuda(), rays_d=rd.cuda(), index=[0], images=gt.cuda())
+    if cnf is not None:
+        data["cam_near_far"] = cnf.cuda()
+    torch.manual_seed(seed)
+    bg = torch.rand(N, 3, device="cuda"); noises = torch.rand(N, device="cuda")       # the draws train_step / march_rays_train will make
+
+    # ---------------- reference: fp16 twice (run-to-run spread), fp32 once (its own quantisation error) ----------------
+    r16a = _ref_step(_ref_trainer(ref_stage, ns, c, state, True), data, seed)
+    r16b = _ref_step(_ref_trainer(ref_stage, ns, c, state, True), data, seed)
+    r32 = _ref_step(_ref_trainer(ref_stage, ns, c, state, False), data, seed)
+    # ---------------- ours ----------------
+    tr.slots[tr.cur].load(data["rays_o"], data["rays_d"], data["images"], bg, noises, data.get("cam_near_far"))
+    tr._fill_params(True, c["alpha"])
+    tr.forward_backward()
+    torch.cuda.synchronize()
+    M = int(tr.counters[1].item())
+    g_ours = tr.export_reference_grads()
+    loss_ours = tr.read_loss()
+
+    rep = {"case": name, "rays": N, "samples": M, "config": {k: v for k, v in c.items()}}
+    # ---- integers: bit-exact ----
+    assert tr.counters[2].item() == 0
+    assert M == r16a["M"] == r16b["M"] == r32["M"], (M, r16a["M"], r32["M"])
+    assert torch.equal(tr.rays[:, 1], r16a["rays"][:, 1]), "per-ray sample counts differ"
+    assert torch.equal(tr.recs[:M, 2], r16a["ts"][:, 0]) and torch.equal(tr.recs[:M, 1], r16a["ts"][:, 1]), "(t, dt) differ"
+    rep["per_ray_counts_equal"] = True
+    fw = {}
+    for tag, run in (("ref16", r16a), ("ref16_again", r16b), ("ref32", r32)):
+        fw[tag] = dict(sigma=run["sigma"], rgb=run["rgb"], image=run["image"], ws=run["ws"], depth=run["depth"], loss=run["loss"])
+    ours = dict(sigma=tr.out[:M, 0], rgb=tr.out[:M, 1:], image=tr.image, ws=tr.weights_sum, depth=tr.depth, loss=loss_ours)
+    rep["forward"] = {}
+    for k in ("sigma", "rgb", "image", "ws", "depth"):
+        rep["forward"][k] = {"ours_vs_ref16": _cmp(ours[k], fw["ref16"][k]), "ref16_vs_ref32": _cmp(fw["ref16"][k], fw["ref32"][k]),
+                             "ours_vs_ref32": _cmp(ours[k], fw["ref32"][k]), "ref16_run_to_run": _cmp(fw["ref16_again"][k], fw["ref16"][k])}
+    rep["loss"] = {"ours": loss_ours, "ref16": r16a["loss"], "ref32": r32["loss"], "rel_err_vs_ref16": abs(loss_ours - r16a["loss"]) / abs(r16a["loss"])}
+
+    # ---- gradients ----
+    names = {"encoder.embeddings": "encoder.embeddings", "encoder_color.embeddings": "encoder_color.embeddings"}
+    for nm, _ in MLP_LAYOUT:
+        names[nm] = nm
+    rep["grads"] = {}
+    for nm in names:
+        ga, gb, g32 = r16a["grads"][nm], r16b["grads"][nm], r32["grads"][nm]
+        rep["grads"][nm] = {"ours_vs_ref16": _cmp(g_ours[nm], ga), "ref16_run_to_run": _cmp(gb, ga), "ref16_vs_ref32": _cmp(ga, g32),
+                            "ours_vs_ref32": _cmp(g_ours[nm], g32)}
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", f"parity_{name}.json"), "w") as f:
+        json.dump(rep, f, indent=1, default=float)
+
+    # ---- assertions: forward at north_star's 1e-3 of the tensor scale; sigma through exp() of an fp16 value carries one fp16
+    # ulp of its exponent (2^-11 * |h| relative), so its bound is the reference's own fp16-vs-fp32 error, measured above ----
+    f = rep["forward"]
+    assert f["image"]["ours_vs_ref16"]["max_err_of_scale"] <= 1e-3, f["image"]
+    assert f["ws"]["ours_vs_ref16"]["max_err_of_scale"] <= 1e-3, f["ws"]
+    assert f["depth"]["ours_vs_ref16"]["max_err_of_scale"] <= 1e-3, f["depth"]
+    assert f["rgb"]["ours_vs_ref16"]["rel_l2"] <= 1e-3, f["rgb"]
+    assert f["sigma"]["ours_vs_ref16"]["rel_l2"] <= 1e-3 or \
+        f["sigma"]["ours_vs_ref16"]["rel_l2"] <= 1.5 * f["sigma"]["ref16_vs_ref32"]["rel_l2"], f["sigma"]
+    assert f["rgb"]["ours_vs_ref32"]["rel_l2"] <= 1.5 * f["rgb"]["ref16_vs_ref32"]["rel_l2"] + 1e-4, f["rgb"]
+    assert rep["loss"]["rel_err_vs_ref16"] <= 1e-3, rep["loss"]
+    for nm, g in rep["grads"].items():
+        floor = max(g["ref16_vs_ref32"]["rel_l2"], g["ref16_run_to_run"]["rel_l2"])
+        # our fp16 path against the exact (fp32) gradient must be no worse than ~ the reference's own fp16 path against it,
+        # and against the reference's fp16 run it must stay within 2x that noise floor (two independent fp16 roundings)
+        assert g["ours_vs_ref32"]["rel_l2"] <= 1.5 * g["ref16_vs_ref32"]["rel_l2"] + 1e-3, (nm, g)
+        assert g["ours_vs_ref16"]["rel_l2"] <= 2.0 * floor + 1e-3, (nm, g)
+        assert g["ours_vs_ref16"]["cos"] > 0.9999 or g["ours_vs_ref16"]["cos"] >= g["ref16_vs_ref32"]["cos"] - 1e-4, (nm, g)
+
+
+def test_unmodified_reference_model_runs_over_the_drop_in_operators():
+    """the unmodified nerf/network.py + nerf/renderer.py import `raymarching`,
+    `gridencoder`, `shencoder` from nerf2mesh_b200.install() and give the same training render, gradients and inference render as
+    over the reference's own wrappers + kernels (bit-exact wherever no atomics are involved)."""
+    from oracle import ref_stage
+    if not ref_stage.staged():
+        pytest.skip("reference Python files not staged")
+    ns_ref, ns_our = ref_stage.load("ref"), ref_stage.load("ours")
+    assert ns_our.raymarching.__name__.startswith("nerf2mesh_b200") and not ns_ref.raymarching.__name__.startswith("nerf2mesh_b200")
+    c = CASES["lego"]
+    grid, bits, bricks = _scene(c)
+    n = 1024
+    ro, rd = cases.rays(n, seed=5)
+    ro, rd = ro.cuda(), rd.cuda()
+    bg = torch.rand(n, 3, device="cuda")
+    outs = []
+    for ns in (ns_ref, ns_our):
+        opt = ref_stage.default_opt(bound=1.0, dt_gamma=0.0, adaptive_num_rays=False)
+        torch.manual_seed(0)
+        model = ns.make_model(opt).cuda()
+        with torch.no_grad():       # same parameters on both sides (seeded init), a visible density
+            model.sigma_net.net[1].weight.mul_(30.0)
+            model.density_bitfield.copy_(bits.cuda()); model.density_grid.copy_(grid.cuda())
+        model.train()
+        torch.manual_seed(1)
+        res = model.render(ro, rd, bg_color=bg, perturb=True, **{k: v for k, v in vars(opt).items() if k not in ("bg_color", "perturb")})
+        loss = ((res["image"] - 0.5) ** 2).mean() + 1e-2 * res["weights_sum"].mean()
+        scaler = torch.amp.GradScaler("cuda")
+        scaler.scale(loss).backward()
+        grads = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+        model.eval()
+        with torch.no_grad():
+            ev = model.render(ro, rd, bg_color=1, perturb=False, **{k: v for k, v in vars(opt).items() if k not in ("bg_color", "perturb")})
+        outs.append(dict(M=res["num_points"], image=res["image"].detach(), ws=res["weights_sum"].detach(), depth=res["depth"].detach(),
+                         grads=grads, ev_image=ev["image"], ev_depth=ev["depth"], enc=type(model.encoder).__module__))
+    a, b = outs
+    assert a["enc"] == "gridencoder.grid" and b["enc"].startswith("nerf2mesh_b200")
+    assert a["M"] == b["M"] and a["M"] > 20000
+    for k in ("ev_image", "ev_depth"):      # inference: deterministic kernels and identical row order on both sides => bit-exact
+        assert torch.equal(a[k], b[k]), k
+    for k in ("image", "ws", "depth"):      # training: the reference's sample offsets follow atomic order, ours the ray order --
+        # same per-ray arithmetic, but a cuBLAS row may round differently at another position in the batch
+        assert torch.equal(a[k], b[k]) or (a[k] - b[k]).abs().max().item() <= 1e-5 * max(1.0, a[k].abs().max().item()), k
+    for k in a["grads"]:                                               # atomics: order-dependent rounding only
+        x, y = a["grads"][k].double(), b["grads"][k].double()
+        assert (x - y).abs().max().item() <= 2e-3 * x.abs().max().item(), k
+
+
+# ------------------------------------------------------------------------------------------------
+# around the step: density-grid update, evaluation render, checkpoint hand-off, EMA -- each against the unmodified reference
+# ------------------------------------------------------------------------------------------------
+def _trained_pair(name, fp16=True, ema=False, steps=40):
+    """(ours, reference Trainer over the reference kernels) holding the same, slightly trained parameters"""
+    c = CASES[name]
+    ref_stage, ns = _ref_stack()
+    grid, bits, bricks = _scene(c)
+    tr = _make_ours(c, bits, grid)
+    _warm_up(tr, c, bricks, steps)
+    rt = _ref_trainer(ref_stage, ns, c, tr.export_reference_state(), fp16)
+    return c, tr, rt, bricks
+
+
+@pytest.mark.parametrize("name", ["lego", "garden"])
+def test_density_grid_update_matches_reference_update_extra_state(name):
+    """Stage0Trainer.update_density_grid vs the unmodified NeRFRenderer.update_extra_state
+    (renderer.py:1074-1149) over the reference kernels: same parameters, same torch generator state => same jitter per cell.
+    The density values agree to the fp16 rounding of the network; the bitfield may then differ only for cells whose density sits
+    within that rounding of the threshold."""
+    c, tr, rt, _ = _trained_pair(name)
+    for rnd in range(2):                               # the second round exercises the decay of a non-trivial grid
+        torch.manual_seed(77 + rnd)
+        rt.model.update_extra_state()
+        torch.manual_seed(77 + rnd)
+        tr.update_density_grid(decay=0.95, density_thresh=10.0)
+        torch.cuda.synchronize()
+        g_ref, g = rt.model.density_grid, tr.density_grid
+        scale = g_ref.abs().max().item()
+        assert scale > 0
+        assert (g - g_ref).abs().max().item() <= 2e-3 * scale, (rnd, (g - g_ref).abs().max().item(), scale)
+        assert abs(tr.mean_density.item() - rt.model.mean_density) <= 1e-4 * abs(rt.model.mean_density)
+        # bit i of byte n <-> cell 8n+i (raymarching.cu:279-288)
+        shifts = torch.arange(8, device="cuda", dtype=torch.uint8)
+        ours_bits = ((tr.density_bitfield[:, None] >> shifts) & 1).reshape(-1).bool()
+        ref_bits = ((rt.model.density_bitfield[:, None] >> shifts) & 1).reshape(-1).bool()
+        thr = min(rt.model.mean_density, 10.0)
+        occ = ref_bits.float().mean().item()
+        assert 0.001 < occ < 0.999, occ
+        # our bitfield is exactly packbits of OUR grid at OUR threshold (the operator is bit-exact, test_gpu_raymarching) ...
+        assert torch.equal(ours_bits, (g.reshape(-1) > min(tr.mean_density.item(), 10.0)))
+        # ... so it can differ from the reference's only where the reference's density is within the network's fp16 rounding
+        # of the threshold
+        mism = ours_bits != ref_bits
+        band = (g_ref.reshape(-1) - thr).abs() <= 4e-3 * thr
+        assert not (mism & ~band).any(), int((mism & ~band).sum().item())
+        frac = mism.float().mean().item()
+        assert frac < 2e-3, (rnd, frac)
+
+
+def test_evaluation_render_matches_reference_inference_loop():
+    """Stage0Trainer.render (march + gather + tcgen05 MLPs + composite in ray chunks, no host loop
+    over slabs) vs the unmodified NeRFRenderer.render in eval mode (march_rays / composite_rays slab loop with alive-ray
+    compaction, renderer.py:749-802) over the reference kernels, same parameters."""
+    c, tr, rt, bricks = _trained_pair("lego")
+    from nerf2mesh_b200.train_synthetic import full_image_rays
+    pose = S.orbit_cameras(3, seed=99)[1]
+    ro, rd = full_image_rays(pose, S.lego_intrinsics() / 8, 100, 100)            # a 100 x 100 view (10 000 rays: 3 ragged chunks)
+    ro, rd = ro.cuda(), rd.cuda()
+    rt.model.eval()
+    opt = rt.opt
+    with torch.no_grad():
+        ev = rt.model.render(ro, rd, bg_color=1, perturb=False, **{k: v for k, v in vars(opt).items() if k not in ("bg_color", "perturb")})
+    img, ws, dep = tr.render(ro, rd, bg_color=1.0)
+    torch.cuda.synchronize()
+    assert ev["image"].shape == img.shape
+    covered = (ws > 0.5).float().mean().item()
+    assert 0.02 < covered < 0.98, covered                                           # the view really shows the object
+    assert (img - ev["image"]).abs().max().item() <= 2e-3, (img - ev["image"]).abs().max().item()
+    assert (img - ev["image"]).abs().mean().item() <= 2e-4
+    assert (dep - ev["depth"]).abs().max().item() <= 2e-3 * ev["depth"].abs().max().item()
+    # per-ray background tensor on a ragged chunk (the last chunk is shorter than num_rays)
+    bgt = torch.rand(ro.shape[0], 3, device="cuda")
+    img2, _, _ = tr.render(ro, rd, bg_color=bgt)
+    with torch.no_grad():
+        ev2 = rt.model.render(ro, rd, bg_color=bgt, perturb=False, **{k: v for k, v in vars(opt).items() if k not in ("bg_color", "perturb")})
+    assert (img2 - ev2["image"]).abs().max().item() <= 2e-3
+
+
+def test_checkpoint_is_accepted_by_the_reference_trainer_and_ema_matches(tmp_path):
+    """SURVEY.md section 8 f1 (EMA) + f4 (hand-off): a checkpoint written by Stage0Trainer.save_reference_checkpoint is read by the
+    UNMODIFIED Trainer.load_checkpoint (nerf/utils.py:1407-1473) without missing / unexpected keys, including the torch_ema state;
+    the reference model then renders the same image; and the fused EMA kernels follow torch_ema step by step."""
+    c, tr, rt, bricks = _trained_pair("lego", steps=24)
+    ref_stage, ns = _ref_stack()
+    # --- EMA: ours vs torch_ema (oracle/torch_ema_port.py unless the real package is installed) on the reference's parameters ---
+    EMA = ns.utils.ExponentialMovingAverage
+    ema_ref = EMA(rt.model.parameters(), decay=0.95)
+    tr.enable_ema(0.95)
+    for epoch in range(3):
+        for it in range(4):       # a few optimizer steps per "epoch" on our side, mirrored into the reference's parameters
+            ro, rd = _batch(c, 500 + 10 * epoch + it)
+            g = torch.Generator().manual_seed(9000 + 10 * epoch + it)
+            tr.step(ro, rd, _gt(c, ro, rd, bricks), torch.rand(N, 3, generator=g), torch.rand(N, generator=g), use_graph=False)
+        rt.model.load_state_dict(tr.export_reference_state(), strict=True)
+        ema_ref.update()          # utils.py:1213-1214: once per epoch
+        tr.ema_update()
+    st = tr.ema_state_dict()
+    assert st["num_updates"] == ema_ref.num_updates == 3 and st["decay"] == ema_ref.decay
+    names = [n for n, _ in rt.model.named_parameters()]
+    assert len(names) == len(st["shadow_params"]) == len(ema_ref.shadow_params)
+    for n, a, b in zip(names, st["shadow_params"], ema_ref.shadow_params):
+        assert a.shape == b.shape, n
+        assert (a - b).abs().max().item() <= 1e-6 * max(b.abs().max().item(), 1e-12) + 1e-9, n
+    # ema_apply / ema_restore == store + copy_to / restore
+    before = tr.export_reference_state()
+    tr.ema_apply()
+    applied = tr.export_reference_state()
+    for n, b in zip(names, ema_ref.shadow_params):
+        assert torch.allclose(applied[n], b, rtol=1e-6, atol=1e-9), n
+    tab_c = tr.table.view(torch.float16).view(-1, 4)[:, 2:4].float()
+    assert torch.equal(tab_c, applied["encoder_color.embeddings"].half().float())          # fp16 working copy refreshed
+    tr.ema_restore()
+    after = tr.export_reference_state()
+    for k in before:
+        assert torch.equal(before[k], after[k]), k
+
+    # --- checkpoint hand-off ---
+    tr.update_density_grid()
+    path = tmp_path / "ngp_stage0_ep0003.pth"
+    tr.save_reference_checkpoint(str(path), epoch=3, full=True)
+    opt = ref_stage.default_opt(bound=1.0, dt_gamma=0.0, adaptive_num_rays=False)
+    fresh = ns.make_model(opt)
+    logs = []
+    rt2 = ns.utils.Trainer("ngp", opt, fresh, device=torch.device("cuda"), workspace=None, mute=True,
+                           optimizer=lambda m: torch.optim.Adam(m.get_params(opt.lr), eps=1e-15),
+                           criterion=torch.nn.MSELoss(reduction="none"), ema_decay=0.95, fp16=True,
+                           use_checkpoint="scratch", use_tensorboardX=False, scheduler_update_every_step=True)
+    rt2.log = lambda *a, **k: logs.append(" ".join(str(x) for x in a))
+    rt2.load_checkpoint(str(path))                                     # the unmodified loader
+    assert not any("[WARN]" in m for m in logs), logs
+    assert any("loaded EMA" in m for m in logs), logs
+    assert rt2.epoch == 3 and rt2.global_step == tr.global_step
+    assert abs(rt2.model.mean_density - tr.mean_density.item()) < 1e-7
+    for n, a, b in zip(names, rt2.ema.shadow_params, st["shadow_params"]):
+        assert torch.equal(a, b.to(a.device)), n
+    assert torch.equal(rt2.model.density_bitfield, tr.density_bitfield)
+    ro, rd = cases.rays(2048, seed=21)
+    with torch.no_grad():
+        rt2.model.eval()
+        ev = rt2.model.render(ro.cuda(), rd.cuda(), bg_color=1, perturb=False,
+                              **{k: v for k, v in vars(opt).items() if k not in ("bg_color", "perturb")})
+    img, ws, _ = tr.render(ro.cuda(), rd.cuda(), bg_color=1.0)
+    assert (img - ev["image"]).abs().max().item() <= 2e-3

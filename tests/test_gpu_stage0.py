@@ -242,7 +242,8 @@ def test_pipelined_mlp_backward_equals_single_tile_kernel():
 
 def test_update_density_grid_matches_reference_composition():
     """Stage0Trainer.update_density_grid vs the reference's update_extra_state arithmetic (renderer.py:1074-1149)
-    composed from torch + the (bit-exact) operator-level encoder, same random jitter."""
+    composed from torch + the (bit-exact) operator-level encoder, same random jitter (one [H^3, 3] draw per cascade in the
+    reference's meshgrid order).  The comparison against the UNMODIFIED reference method is in test_gpu_reference_parity.py."""
     import torch.nn.functional as Fnn
     from nerf2mesh_b200 import raymarching as rm
     tr, b = make()
@@ -253,34 +254,37 @@ def test_update_density_grid_matches_reference_composition():
     torch.manual_seed(123)
     tr.update_density_grid(decay=0.95, density_thresh=10.0)
     torch.cuda.synchronize()
-    # reference composition
+    # reference composition (renderer.py:1095-1118)
     torch.manual_seed(123)
     ax = torch.arange(H, dtype=torch.int32, device="cuda")
-    grid = torch.zeros(1, H ** 3, device="cuda")
-    cells = H ** 3
-    for first in range(0, cells, tr.Mcap):
-        cnt = min(tr.Mcap, cells - first)
-        noise = torch.rand(cnt, 3, device="cuda")
-        idx = torch.arange(first, first + cnt, dtype=torch.int32, device="cuda")
-        coords = rm.morton3D_invert(idx)
-        xyz = 2 * coords.float() / (H - 1) - 1
-        hgs = 1.0 / H
-        xyz = xyz * (1.0 - hgs) + (noise * 2 - 1) * hgs
-        enc = grid_encode((xyz + 1) / 2, st["encoder.embeddings"], tr.offsets, c.per_level_scale, 16)
+    xx, yy, zz = torch.meshgrid(ax, ax, ax, indexing="ij")
+    coords = torch.cat([xx.reshape(-1, 1), yy.reshape(-1, 1), zz.reshape(-1, 1)], dim=-1)
+    indices = rm.morton3D(coords).long()
+    xyz = 2 * coords.float() / (H - 1) - 1
+    hgs = 1.0 / H
+    xyz = xyz * (1.0 - hgs)
+    xyz += (torch.rand_like(xyz) * 2 - 1) * hgs
+    sig = torch.empty(H ** 3, device="cuda")
+    for a0 in range(0, H ** 3, 1 << 19):
+        x = xyz[a0:a0 + (1 << 19)]
+        enc = grid_encode((x + 1) / 2, st["encoder.embeddings"], tr.offsets, c.per_level_scale, 16)
         with torch.autocast("cuda", dtype=torch.float16):
-            h = Fnn.linear(torch.cat([xyz, enc], -1), st["sigma_net.net.0.weight"]).relu()
+            h = Fnn.linear(torch.cat([x, enc], -1), st["sigma_net.net.0.weight"]).relu()
             h = Fnn.linear(h, st["sigma_net.net.1.weight"])
-        sigma = torch.exp(h[:, 0].float())
-        grid[0, first:first + cnt] = torch.maximum(grid[0, first:first + cnt] * 0.95, sigma)
+        sig[a0:a0 + (1 << 19)] = torch.exp(h[:, 0].float())
+    grid = torch.zeros(1, H ** 3, device="cuda")
+    grid[0, indices] = sig                                   # max(0 * decay, sigma)
     assert (tr.density_grid - grid).abs().max().item() <= 2e-3 * grid.abs().max().item()
     mean = tr.density_grid.clamp(min=0).mean().item()
     assert abs(tr.mean_density.item() - mean) < 1e-6
-    assert torch.equal(tr.density_bitfield, rm.packbits(tr.density_grid, min(mean, 10.0)))
+    assert torch.equal(tr.density_bitfield, rm.packbits(tr.density_grid, min(mean, 10.0)))      # on-device threshold == host threshold
     occ = (tr.density_grid > min(mean, 10.0)).float().mean().item()
     assert 0.05 < occ < 0.95
 
 
 def test_render_equals_training_forward():
+    """chunked render() == the training forward on the same rays (host chunking / padding logic; the parity of render() against the
+    reference's inference loop is test_evaluation_render_matches_reference_inference_loop in test_gpu_reference_parity.py)"""
     tr, b = make()
     stage(tr, b)
     tr.noises.zero_()
@@ -293,6 +297,10 @@ def test_render_equals_training_forward():
     img2, ws2, _ = tr.render(ro2, rd2, bg_color=1.0)
     assert img2.shape == (N + 10, 3) and torch.equal(img2[:10], img2[N:])
     assert torch.isfinite(img2).all()
+    # per-ray background tensor with a ragged last chunk
+    bgt = torch.rand(N + 10, 3, device="cuda")
+    img3, _, _ = tr.render(ro2, rd2, bg_color=bgt)
+    assert torch.allclose(img3 - (1 - ws2)[:, None] * bgt, img2 - (1 - ws2)[:, None], atol=1e-6)
 
 
 @pytest.mark.parametrize("nparts", [2, 4, 8])

@@ -168,7 +168,7 @@ def test_step_orchestration_call_sequence(monkeypatch):
         setattr(tr, k, T())
     tr.gtables, tr.g_mlps = [tr.gtable], [tr.g_mlp]
     tr.params = S0.S0Params(); tr.Mcap, tr.N, tr.rows, tr.parity, tr.device = 128, 4, 160, 0, "cpu"
-    tr.tv_overlap, tr._tv_stream, tr._part_streams, tr.part_mode = True, None, [], "chains"
+    tr._tv_overlap, tr._tv_stream, tr._part_streams, tr.part_mode = True, None, [], "chains"
     tr._mlp_stream = tr._adam_stream = None
     tr.level_pipe, tr._ev_first_pass, tr.scatter_level_cuts = False, [], ()
     tr.l2_persist_mb, tr._l2_granted = 0, None
