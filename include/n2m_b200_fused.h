@@ -205,6 +205,16 @@ int n2m_s0_encode_bwd_part(const n2m_s0_params* p, const void* recs, const int32
                            const int32_t* offsets, void* gtable, const float* loss_scale, uint32_t part, uint32_t nparts,
                            n2m_stream_t stream);
 
+/* Fused backward (csrc/fused.cu): MLP backward (tcgen05) + hash-grid scatter of one part in ONE persistent, warp-specialised launch --
+ * warps 0-3 run the MLP backward of a 128-sample tile, warps 4-11 scatter the previous tile's feature gradients, which are handed over
+ * through a double-buffered shared-memory image instead of `denc_tiles` in HBM.  Same arithmetic as n2m_s0_mlp_bwd_part followed by
+ * n2m_s0_encode_bwd_part (gradients equal up to fp32 atomic order); the TV gradient stays with n2m_s0_tv.  n2m_s0_fused_init sets the
+ * kernel attributes once per process. */
+int n2m_s0_fused_init(void);
+int n2m_s0_bwd_fused_part(const n2m_s0_params* p, const void* enc_tiles, const void* dout, const void* recs, const int32_t* counters,
+                          uint32_t Mcap, const float* rays_o, const float* rays_d, const void* wpack, const int32_t* offsets,
+                          void* gtable, float* g_mlp, float* loss_scale, uint32_t part, uint32_t nparts, n2m_stream_t stream);
+
 /* EXPERIMENTAL (compiled, not yet measured on a GPU): the scatter restricted to hash levels [level_lo, level_hi).  A spread RED
  * costs 1.40 SM-cycles per lane into a 32 MB table and 2.19 into the 98 MB gradient table whatever its payload
  * (profiles/redbench.py), so two passes over the samples (levels 0-9, then 10-15: ~48 MB of target rows each) may beat one.  Disjoint

@@ -17,7 +17,10 @@ OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libn2m_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-SOURCES = ["raymarching.cu", "gridencoder.cu", "shencoder.cu", "tc_probe.cu", "red_probe.cu", "stage0.cu", "mlp_tc.cu", "optim.cu", "dp.cu"]
+SOURCES = ["raymarching.cu", "gridencoder.cu", "shencoder.cu", "stage0.cu", "mlp_tc.cu", "fused.cu", "optim.cu", "dp.cu"]
+# micro-benchmarks and the tcgen05 layout probe: test / profiling infrastructure, kept OUT of the product library
+PROBE_SOURCES = ["tc_probe.cu", "red_probe.cu"]
+PROBE_LIB = os.path.join(HERE, "libn2m_probes.so")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
@@ -41,8 +44,15 @@ def _headers():
 
 
 def build(force=False, verbose=False):
+    lib = _build(SOURCES, LIB, [], force, verbose)
+    # the probes resolve the error / launch-count plumbing from the product library (rpath $ORIGIN)
+    _build(PROBE_SOURCES, PROBE_LIB, ["-L", HERE, "-ln2m_b200", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"], force, verbose)
+    return lib
+
+
+def _build(sources, LIB, link_extra, force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
-    srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    srcs = [s for s in sources if os.path.exists(os.path.join(CSRC, s))]
     hdrs = _headers()
     jobs = []
     objs = []
@@ -66,7 +76,7 @@ def build(force=False, verbose=False):
                 if verbose and out.strip():
                     print(out)
     if jobs or force or not os.path.exists(LIB) or any(_newer(o, LIB) for o in objs):
-        run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs)
+        run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + link_extra)
     return LIB
 
 

@@ -1,0 +1,477 @@
+// fused.cu -- warp-specialised fused kernels of the stage-0 train path.
+//
+// k_s0_bwd_fused: the whole per-sample backward (autograd of the three MLPs on tcgen05 + the hash-grid scatter of
+// gridencoder.cu:248-339) in ONE persistent kernel.  The stand-alone kernels (k_mlp_bwd: a latency-bound chain of ten dependent
+// tensor-core rounds per tile, 6 % occupancy; k_s0_encode_bwd: bound by the rate of spread red.global.add.v4.f32, no tensor or
+// shared-memory use) leave each other's resources idle and run back to back (122 + 179 us).  Here one CTA per SM holds
+//     warps 0-3  : the MLP backward of k_mlp_bwd, one 128-sample tile at a time (thread = sample, thread 0 issues the MMAs);
+//                  the feature gradients of a finished tile go to a double-buffered shared-memory image instead of HBM,
+//     warps 4-11 : the scatter of the previous tile: warp = (32-sample group, even / odd levels), lane = sample, so consecutive
+//                  lanes are consecutive samples of a ray and runs of same-cell lanes are merged before the RED as before,
+// handing tiles over through two mbarrier pairs (full / empty).  The tensor chain of tile k+1 runs under the REDs of tile k, the
+// `denc_tiles` round trip through HBM (2 x 128 B per sample) disappears, and the step loses one launch per part.
+#include "n2m_common.cuh"
+#include "tc05.cuh"
+#include "s0_geom.cuh"
+#include "mlp_common.cuh"
+#include "../../include/n2m_b200_fused.h"
+
+namespace n2m {
+namespace {
+
+constexpr uint32_t kMlpThreads = 128, kScatWarps = 8, kFusedThreads = kMlpThreads + 32 * kScatWarps;      // 384
+constexpr uint32_t D_CHUNKS = 7;                          // gradient columns 0..55 (cols 3..50 are used)
+constexpr uint32_t D_BYTES = D_CHUNKS * kChunk;           // 14336
+constexpr uint32_t FB_DENC = B_BYTES;
+constexpr uint32_t FB_BYTES = B_BYTES + 2 * D_BYTES;      // 168960
+
+__device__ __forceinline__ void bar_mlp() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// MLP warps only: make generic smem writes visible to the tensor core, order TMEM accesses, meet at named barrier 1
+__device__ __forceinline__ void sync_mlp() {
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    bar_mlp();
+    tc::fence_after_sync();
+}
+__device__ __forceinline__ void mbar_arrive1(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(tc::smem_u32(bar)) : "memory");
+}
+
+// ---- scatter of one tile by one warp: rows [32 * sg, 32 * sg + 32) of the tile, levels PAR, PAR + 2, ..., PAR + 14 ----
+template <int PAR>
+__device__ __forceinline__ void scatter_levels(const n2m_s0_params& p, const Sample& s, bool active, const uint4 (&q)[D_CHUNKS],
+                                               const int32_t* __restrict__ offsets, float4* __restrict__ gtable, uint32_t lane) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t l = 2 * i + PAR;
+        // this level's gradients: column kColDens + l, columns kColColor + 2l, + 2l + 1 (compile-time positions in q[])
+        constexpr uint32_t dummy = 0; (void)dummy;
+        const uint32_t cd = kColDens + l, cc = kColColor + 2 * l;
+        const uint32_t wd = reinterpret_cast<const uint32_t*>(&q[cd >> 3])[(cd & 7) >> 1];
+        const __half hd = (cd & 1) ? __ushort_as_half((unsigned short)(wd >> 16)) : __ushort_as_half((unsigned short)(wd & 0xffffu));
+        float g0, g1;
+        if ((cc & 1) == 0) {
+            const uint32_t wc = reinterpret_cast<const uint32_t*>(&q[cc >> 3])[(cc & 7) >> 1];
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&wc));
+            g0 = f.x; g1 = f.y;
+        } else {          // the pair straddles two 32-bit words (kColColor is odd)
+            const uint32_t wa = reinterpret_cast<const uint32_t*>(&q[cc >> 3])[(cc & 7) >> 1];
+            const uint32_t wb = reinterpret_cast<const uint32_t*>(&q[(cc + 1) >> 3])[((cc + 1) & 7) >> 1];
+            g0 = __half2float(__ushort_as_half((unsigned short)(wa >> 16)));
+            g1 = __half2float(__ushort_as_half((unsigned short)(wb & 0xffffu)));
+        }
+        const float gd = active ? __half2float(hd) : 0.f;
+        g0 = active ? g0 : 0.f; g1 = active ? g1 : 0.f;
+
+        const LevelGeom lg = level_geom(offsets, l, p.S, p.base_res);
+        Corners c; uint32_t base[3]; bool hashed;
+        corners_of(lg, s.u, s.v, s.w, c, base, hashed, nullptr);
+        float4* gt = gtable + lg.row0;
+        float vd[8], v0[8], v1[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { vd[k] = c.w[k] * gd; v0[k] = c.w[k] * g0; v1[k] = c.w[k] * g1; }
+        // runs of consecutive lanes in the same cell: sum them first, the last lane of a run issues the REDs
+        const uint32_t key = active ? (base[0] | (base[1] << 10) | (base[2] << 20)) : 0xffffffffu;
+        const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+        const uint32_t heads = __ballot_sync(0xffffffffu, lane == 0 || key != prev);
+        const bool merge = lg.res < 1023u && __popc(heads) <= 20;
+        bool issue = active;
+        if (merge) {
+            const uint32_t run_start = 31u - __clz(heads & (0xffffffffu >> (31u - lane)));
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const bool take = lane >= run_start + (uint32_t)o;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float a = __shfl_up_sync(0xffffffffu, vd[k], o), b = __shfl_up_sync(0xffffffffu, v0[k], o),
+                                cq = __shfl_up_sync(0xffffffffu, v1[k], o);
+                    if (take) { vd[k] += a; v0[k] += b; v1[k] += cq; }
+                }
+            }
+            issue = active && (lane == 31 || ((heads >> (lane + 1)) & 1u));
+        }
+        if (issue) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) atomicAdd(gt + c.row[k], make_float4(vd[k], v0[k], v1[k], 0.f));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kFusedThreads, 1)
+k_s0_bwd_fused(n2m_s0_params p, const uint8_t* __restrict__ enc_tiles, const float4* __restrict__ dout,
+               const float4* __restrict__ recs, const int32_t* __restrict__ counters, const float* __restrict__ rays_o,
+               const float* __restrict__ rays_d, const uint8_t* __restrict__ wpack, const int32_t* __restrict__ offsets,
+               float4* __restrict__ gtable, float* __restrict__ g_mlp, float* __restrict__ loss_scale, uint32_t part, uint32_t nparts) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar_mma, bar_tma, bar_full[2], bar_empty[2];
+    __shared__ uint32_t tmem_s;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const PartRange pr = part_range(counters, part, nparts);
+    const uint32_t M = pr.M;
+    const uint32_t t0 = pr.lo / kTile, t1 = (pr.hi + kTile - 1) / kTile;
+    if (pr.hi <= pr.lo || t0 + blockIdx.x >= t1) return;
+
+    if (tid == 0) {
+        tc::mbar_init(&bar_mma, 1); tc::mbar_init(&bar_tma, 1);
+        tc::mbar_init(&bar_full[0], 1); tc::mbar_init(&bar_full[1], 1);
+        tc::mbar_init(&bar_empty[0], kScatWarps); tc::mbar_init(&bar_empty[1], kScatWarps);
+        tc::mbar_init_fence();
+    }
+    if (warp == 0) tc::tmem_alloc(&tmem_s, 512);
+    for (uint32_t i = tid; i < W_BYTES / 16; i += kFusedThreads)
+        reinterpret_cast<uint4*>(smem + B_W)[i] = __ldg(reinterpret_cast<const uint4*>(wpack) + i);
+    uint8_t* sW = smem + B_W; uint8_t* act = smem + B_ACT; uint8_t* grd = smem + B_GRAD;
+    uint8_t* sA = act + A_A; uint8_t* sH2 = act + A_H2; uint8_t* sH1 = act + A_H1; uint8_t* sS1 = act + A_S1;
+    uint8_t* sP1 = act + A_P1; uint8_t* sAs2 = act + A_AS2;
+    uint8_t* sdH = grd + G_DH; uint8_t* sdS1 = grd + G_DS1; uint8_t* sdP1 = grd + G_DP1; uint8_t* sdO = grd + G_DO;
+    uint8_t* sdOs = grd + G_DOS; uint8_t* sdO2 = grd + G_DO2;
+    uint8_t* sD = smem + FB_DENC;
+    if (tid < kMlpThreads) {   // constant-zero parts of the narrow tiles (their second K chunk, and unused columns of the first)
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(sAs2 + kChunk + tid * 16) = z;
+        *reinterpret_cast<uint4*>(sdO + kChunk + tid * 16) = z;
+        *reinterpret_cast<uint4*>(sdOs + kChunk + tid * 16) = z;
+        *reinterpret_cast<uint4*>(sdO2 + kChunk + tid * 16) = z;
+        *reinterpret_cast<uint4*>(sAs2 + tid * 16) = z;
+        *reinterpret_cast<uint4*>(sP1 + tid * 16) = z; *reinterpret_cast<uint4*>(sP1 + kChunk + tid * 16) = z;
+        *reinterpret_cast<uint4*>(sP1 + 2 * kChunk + tid * 16) = z; *reinterpret_cast<uint4*>(sP1 + 3 * kChunk + tid * 16) = z;
+        *reinterpret_cast<uint4*>(sdP1 + tid * 16) = z; *reinterpret_cast<uint4*>(sdP1 + kChunk + tid * 16) = z;
+        *reinterpret_cast<uint4*>(sdP1 + 2 * kChunk + tid * 16) = z; *reinterpret_cast<uint4*>(sdP1 + 3 * kChunk + tid * 16) = z;
+    }
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_s;
+
+    if (warp >= 4) {
+        // =========================================== scatter warps ===========================================
+        const uint32_t sw = warp - 4, sg = sw & 3, par = sw >> 2;
+        uint32_t it = 0;
+        for (uint32_t tile = t0 + blockIdx.x; tile < t1; tile += gridDim.x, ++it) {
+            const uint32_t buf = it & 1, use = it >> 1;
+            const uint32_t r = sg * 32 + lane;
+            const uint32_t j = tile * kTile + r;
+            Sample s;
+            bool active = j >= pr.lo && j < pr.hi;
+            if (active) {
+                s = sample_of(recs[j], rays_o, rays_d, p);
+                active = !((s.u < 0 || s.u > 1) || (s.v < 0 || s.v > 1) || (s.w < 0 || s.w > 1));
+            } else {
+                s.x = s.y = s.z = s.u = s.v = s.w = 0.5f; s.dx = s.dy = s.dz = 0.f;
+            }
+            tc::mbar_wait(&bar_full[buf], use & 1);
+            uint4 q[D_CHUNKS];
+            const uint8_t* src = sD + buf * D_BYTES + r * 16;
+#pragma unroll
+            for (uint32_t ch = 0; ch < D_CHUNKS; ++ch) q[ch] = *reinterpret_cast<const uint4*>(src + ch * kChunk);
+            __syncwarp();
+            if (lane == 0) mbar_arrive1(&bar_empty[buf]);
+            if (par == 0) {   // fp16 overflow of the loss-scaled gradients => GradScaler semantics: flag, the step is skipped
+                bool bad = false;
+                if (active) {
+#pragma unroll
+                    for (uint32_t ch = 0; ch < D_CHUNKS; ++ch) {
+                        const uint32_t ww[4] = {q[ch].x, q[ch].y, q[ch].z, q[ch].w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&ww[i]));
+                            const uint32_t col = 8 * ch + 2 * i;
+                            if (col >= kColDens && col < kColDir) bad |= !isfinite(f.x);
+                            if (col + 1 >= kColDens && col + 1 < kColDir) bad |= !isfinite(f.y);
+                        }
+                    }
+                }
+                if (bad) loss_scale[3] = 1.f;
+                scatter_levels<0>(p, s, active, q, offsets, gtable, lane);
+            } else {
+                scatter_levels<1>(p, s, active, q, offsets, gtable, lane);
+            }
+        }
+    } else {
+        // =========================================== MLP warps (k_mlp_bwd) ===========================================
+        const uint32_t lane_t = (warp * 32u) << 16;
+        const uint32_t K0 = tmem + T_K0, K1 = tmem + T_K1;
+        uint32_t ph_mma = 0, ph_tma = 0;
+        const bool full = p.shading_full != 0;
+        const float ls = loss_scale[0];
+        const float spec_reg = (M > 0) ? 2.0f * p.lambda_specular / (float)M * ls : 0.f;
+        bool first = true;
+        const tc::Operand G1 = opMN(sA, 128), G2 = opMN(sH2, 128), G3 = opMN(sS1, 128);
+        uint32_t it = 0;
+        for (uint32_t tile = t0 + blockIdx.x; tile < t1; tile += gridDim.x, ++it) {
+            const uint32_t buf = it & 1, use = it >> 1;
+            if (tid == 0) bulk_g2s(sA, enc_tiles + (size_t)tile * kTileBytes, kTileBytes, &bar_tma);
+            const uint32_t j = tile * kTile + tid;
+            float4 dv = make_float4(0.f, 0.f, 0.f, 0.f);
+            const bool own = j >= pr.lo && j < pr.hi;
+            if (own) dv = dout[j];
+            tc::mbar_wait(&bar_tma, ph_tma); ph_tma ^= 1;
+
+            // ---------------- forward recompute ----------------
+            if (tid == 0) {
+                tc::gemm_issue(K0, opK(sA, 128), opK(sW + W_C1, 64), 128, 64, 64, false);
+                tc::gemm_issue(K1, opK(sA, 128), opK(sW + W_S1, 32), 128, 32, 64, false);
+                tc::mma_commit(&bar_mma);
+            }
+            tc::mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1; tc::fence_after_sync();
+            epi_store_row<64, true>(K0 + lane_t, sH1, tid, nullptr);
+            epi_store_row<32, true>(K1 + lane_t, sS1, tid, nullptr);
+            sync_mlp();
+            if (tid == 0) {
+                tc::gemm_issue(K0, opK(sH1, 128), opK(sW + W_C2, 64), 128, 64, 64, false);
+                tc::gemm_issue(K1, opK(sS1, 128), opK(sW + W_S2, 16), 128, 16, 32, false);
+                tc::mma_commit(&bar_mma);
+            }
+            tc::mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1; tc::fence_after_sync();
+            float h_sig;
+            { float v[8]; tc::tmem_ld8(K1 + lane_t, v); h_sig = round_h(v[0]); }
+            epi_store_row<64, true>(K0 + lane_t, sH2, tid, nullptr);
+            sync_mlp();
+            if (tid == 0) {
+                tc::gemm_issue(K0, opK(sH2, 128), opK(sW + W_C3, 16), 128, 16, 64, false);
+                tc::mma_commit(&bar_mma);
+            }
+            tc::mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1; tc::fence_after_sync();
+            float feat[6];
+            { float v[8]; tc::tmem_ld8(K0 + lane_t, v);
+#pragma unroll
+              for (int i = 0; i < 6; ++i) feat[i] = sigmoid_h(v[i]); }
+            float sp[3] = {0.f, 0.f, 0.f};
+            if (full) {
+                const uint4 dq = *reinterpret_cast<const uint4*>(sA + 6 * kChunk + tid * 16);
+                const __half2 d01 = *reinterpret_cast<const __half2*>(&dq.y);
+                const __half2 d23 = *reinterpret_cast<const __half2*>(&dq.z);
+                const float in[8] = {__high2float(d01), __low2float(d23), __high2float(d23), feat[3], feat[4], feat[5], 0.f, 0.f};
+                store_chunk(sAs2, 0, tid, in);
+                sync_mlp();
+                if (tid == 0) {
+                    tc::gemm_issue(K1, opK(sAs2, 128), opK(sW + W_P1, 32), 128, 32, 16, false);
+                    tc::mma_commit(&bar_mma);
+                }
+                tc::mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1; tc::fence_after_sync();
+                epi_store_row<32, true>(K1 + lane_t, sP1, tid, nullptr);
+                sync_mlp();
+                if (tid == 0) {
+                    tc::gemm_issue(K0, opK(sP1, 128), opK(sW + W_P2, 16), 128, 16, 32, false);
+                    tc::mma_commit(&bar_mma);
+                }
+                tc::mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1; tc::fence_after_sync();
+                float v[8];
+                tc::tmem_ld8(K0 + lane_t, v);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) sp[i] = sigmoid_h(v[i]);
+            }
+
+            // ---------------- output-side chain rule (thread-per-sample) ----------------
+            float dfeat[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            {
+                const float dcol[3] = {dv.y, dv.z, dv.w};
+                float dO2[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    float g = dcol[c];
+                    if (full) {
+                        const float cs = round_h(sp[c] + feat[c]);
+                        if (!(cs >= 0.f && cs <= 1.f)) g = 0.f;            // clamp(0,1) backward
+                        const float dsp = own ? g + spec_reg * sp[c] : 0.f;
+                        dO2[c] = dsp * sp[c] * (1.0f - sp[c]);            // sigmoid backward
+                    }
+                    dfeat[c] = g;
+                }
+                float dOs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                dOs[0] = dv.x * __expf(fminf(fmaxf(h_sig, -15.f), 15.f));   // trunc_exp backward (activation.py:13-17)
+                store_chunk(sdOs, 0, tid, dOs);
+                if (full) store_chunk(sdO2, 0, tid, dO2);
+            }
+            sync_mlp();
+
+            // ---------------- B1 ----------------
+            if (tid == 0) {
+                tc::gemm_issue(K0, opK(sdOs, 128), opMN(sW + W_S2, 16), 128, 32, 16, false);
+                tc::gemm_issue(tmem + T_S2, G3, opMN(sdOs, 128), 128, 16, 128, !first);
+                if (full) {
+                    tc::gemm_issue(K1, opK(sdO2, 128), opMN(sW + W_P2, 16), 128, 32, 16, false);
+                    tc::gemm_issue(tmem + T_P2, G3, opMN(sdO2, 128), 128, 16, 128, !first);
+                }
+                tc::mma_commit(&bar_mma);
+            }
+            tc::mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1; tc::fence_after_sync();
+            epi_store_row<32, false>(K0 + lane_t, sdS1, tid, sS1);
+            if (full) epi_store_row<32, false>(K1 + lane_t, sdP1, tid, sP1);
+            sync_mlp();
+
+            // ---------------- B2 ----------------
+            if (tid == 0) {
+                tc::gemm_issue(K0, opK(sdS1, 128), opMN(sW + W_S1, 32), 128, 64, 32, false);
+                tc::gemm_issue(tmem + T_S1, G1, opMN(sdS1, 128), 128, 32, 128, !first);
+                if (full) {
+                    tc::gemm_issue(K1, opK(sdP1, 128), opMN(sW + W_P1, 32), 128, 16, 32, false);
+                    tc::gemm_issue(tmem + T_P1, G3, opMN(sdP1, 128), 128, 32, 128, !first);
+                }
+                tc::mma_commit(&bar_mma);
+            }
+            tc::mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1; tc::fence_after_sync();
+            {
+                if (full) {
+                    float v[8];
+                    tc::tmem_ld8(K1 + lane_t, v);
+                    dfeat[3] = v[3]; dfeat[4] = v[4]; dfeat[5] = v[5];
+                }
+                float dO[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int i = 0; i < 6; ++i) dO[i] = dfeat[i] * feat[i] * (1.0f - feat[i]);
+                store_chunk(sdO, 0, tid, dO);
+            }
+            sync_mlp();
+
+            // ---------------- B3 ----------------
+            if (tid == 0) {
+                tc::gemm_issue(K1, opK(sdO, 128), opMN(sW + W_C3, 16), 128, 64, 16, false);
+                tc::gemm_issue(tmem + T_C3, G2, opMN(sdO, 128), 128, 16, 128, !first);
+                tc::mma_commit(&bar_mma);
+            }
+            tc::mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1; tc::fence_after_sync();
+            epi_store_row<64, false>(K1 + lane_t, sdH, tid, sH2);
+            sync_mlp();
+
+            // ---------------- B4 ----------------
+            if (tid == 0) {
+                tc::gemm_issue(K1, opK(sdH, 128), opMN(sW + W_C2, 64), 128, 64, 64, false);
+                tc::gemm_issue(tmem + T_C2, G2, opMN(sdH, 128), 128, 64, 128, !first);
+                tc::mma_commit(&bar_mma);
+            }
+            tc::mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1; tc::fence_after_sync();
+            epi_store_row<64, false>(K1 + lane_t, sdH, tid, sH1);
+            sync_mlp();
+
+            // ---------------- B5 ----------------
+            if (tid == 0) {
+                tc::gemm_issue(K0, opK(sdH, 128), opMN(sW + W_C1, 64), 128, 64, 64, true);
+                tc::gemm_issue(tmem + T_C1, G1, opMN(sdH, 128), 128, 64, 128, !first);
+                tc::mma_commit(&bar_mma);
+            }
+            // the scatter warps must have taken the buffer's previous contents (two tiles ago) before it is overwritten
+            tc::mbar_wait(&bar_empty[buf], (use & 1) ^ 1);
+            tc::mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1; tc::fence_after_sync();
+            {   // this sample's feature gradients -> its row of the shared-memory gradient image (zeros for rows of other parts)
+                uint8_t* dst = sD + buf * D_BYTES + tid * 16;
+#pragma unroll
+                for (int c0 = 0; c0 < 64; c0 += 16) {
+                    float v[16];
+                    tc::tmem_ld16(K0 + lane_t + c0, v);
+#pragma unroll
+                    for (int qq = 0; qq < 2; ++qq) {
+                        if (c0 / 8 + qq >= (int)D_CHUNKS) continue;
+                        uint4 o;
+                        o.x = pack2(v[8 * qq + 0], v[8 * qq + 1]); o.y = pack2(v[8 * qq + 2], v[8 * qq + 3]);
+                        o.z = pack2(v[8 * qq + 4], v[8 * qq + 5]); o.w = pack2(v[8 * qq + 6], v[8 * qq + 7]);
+                        if (!own) o = make_uint4(0, 0, 0, 0);
+                        *reinterpret_cast<uint4*>(dst + (c0 / 8 + qq) * kChunk) = o;
+                    }
+                }
+            }
+            first = false;
+            sync_mlp();          // every row of the image is written, all reads of this tile's smem / TMEM are done
+            if (tid == 0) mbar_arrive1(&bar_full[buf]);
+        }
+
+        // ---------------- flush the weight-gradient accumulators (one row of each per thread) ----------------
+        {
+            const uint32_t i = tid;
+            float v[16];
+            {
+                const int k = i < 64 ? map_c1(i) : -1;
+#pragma unroll
+                for (int c0 = 0; c0 < 64; c0 += 16) {
+                    tc::tmem_ld16(tmem + T_C1 + lane_t + c0, v);
+                    if (k >= 0) {
+#pragma unroll
+                        for (int o = 0; o < 16; ++o) atomicAdd(g_mlp + P_C0 + (c0 + o) * 35 + k, v[o]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int c0 = 0; c0 < 64; c0 += 16) {
+                tc::tmem_ld16(tmem + T_C2 + lane_t + c0, v);
+                if (i >= 64) {
+#pragma unroll
+                    for (int o = 0; o < 16; ++o) atomicAdd(g_mlp + P_C1 + (c0 + o) * 64 + (i - 64), v[o]);
+                }
+            }
+            tc::tmem_ld16(tmem + T_C3 + lane_t, v);
+            if (i < 64) {
+#pragma unroll
+                for (int o = 0; o < 6; ++o) atomicAdd(g_mlp + P_C2 + o * 64 + i, v[o]);
+            }
+#pragma unroll
+            for (int c0 = 0; c0 < 32; c0 += 16) {
+                tc::tmem_ld16(tmem + T_S1 + lane_t + c0, v);
+                const int k = i < 64 ? map_s1(i) : -1;
+                if (k >= 0) {
+#pragma unroll
+                    for (int o = 0; o < 16; ++o) atomicAdd(g_mlp + P_S0 + (c0 + o) * 19 + k, v[o]);
+                }
+            }
+            tc::tmem_ld16(tmem + T_S2 + lane_t, v);
+            if (i < 32) atomicAdd(g_mlp + P_S1 + i, v[0]);
+            if (full) {
+                tc::tmem_ld16(tmem + T_P2 + lane_t, v);
+                if (i >= 32 && i < 64) {
+#pragma unroll
+                    for (int o = 0; o < 3; ++o) atomicAdd(g_mlp + P_P1 + o * 32 + (i - 32), v[o]);
+                }
+#pragma unroll
+                for (int c0 = 0; c0 < 32; c0 += 16) {
+                    tc::tmem_ld16(tmem + T_P1 + lane_t + c0, v);
+                    if (i >= 64 && i < 70) {
+#pragma unroll
+                        for (int o = 0; o < 16; ++o) atomicAdd(g_mlp + P_P0 + (c0 + o) * 6 + (i - 64), v[o]);
+                    }
+                }
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+}  // namespace
+}  // namespace n2m
+
+using namespace n2m;
+
+static int fused_num_sms() {
+    static int n = 0;
+    if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
+    return n;
+}
+
+extern "C" {
+
+int n2m_s0_fused_init(void) {
+    cudaError_t e = cudaFuncSetAttribute(k_s0_bwd_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FB_BYTES);
+    if (e != cudaSuccess) return fail("s0_fused_init", cudaGetErrorString(e));
+    fused_num_sms();
+    return 0;
+}
+
+/* MLP backward + hash-grid scatter of one part of the batch in one persistent launch (replaces n2m_s0_mlp_bwd_part followed by
+ * n2m_s0_encode_bwd_part; the TV gradient stays with n2m_s0_tv) */
+int n2m_s0_bwd_fused_part(const n2m_s0_params* p, const void* enc_tiles, const void* dout, const void* recs, const int32_t* counters,
+                          uint32_t Mcap, const float* rays_o, const float* rays_d, const void* wpack, const int32_t* offsets,
+                          void* gtable, float* g_mlp, float* loss_scale, uint32_t part, uint32_t nparts, n2m_stream_t stream) {
+    N2M_REQUIRE(p && enc_tiles && dout && recs && counters && rays_o && rays_d && wpack && offsets && gtable && g_mlp && loss_scale,
+                "s0_bwd_fused", "null pointer");
+    N2M_REQUIRE(p->num_levels == kLevels, "s0_bwd_fused", "fused path supports num_levels == 16");
+    N2M_REQUIRE(Mcap % kTile == 0 && Mcap > 0, "s0_bwd_fused", "Mcap must be a positive multiple of 128");
+    N2M_REQUIRE(valid_parts(part, nparts), "s0_bwd_fused", "nparts must be 1, 2, 4 or 8 and part < nparts");
+    const uint32_t grid = min(Mcap / kTile, (uint32_t)fused_num_sms());
+    k_s0_bwd_fused<<<grid, kFusedThreads, FB_BYTES, as_stream(stream)>>>(
+        *p, static_cast<const uint8_t*>(enc_tiles), static_cast<const float4*>(dout), static_cast<const float4*>(recs), counters,
+        rays_o, rays_d, static_cast<const uint8_t*>(wpack), offsets, static_cast<float4*>(gtable), g_mlp, loss_scale, part, nparts);
+    return check_launch("s0_bwd_fused");
+}
+
+}  // extern "C"

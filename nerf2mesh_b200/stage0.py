@@ -71,6 +71,8 @@ _lib.register({
     "n2m_l2_persist_limit": [ctypes.c_uint64, P],
     "n2m_l2_window": [P, P, ctypes.c_uint64, F],
     "n2m_s0_set_gather_carveout": [I],
+    "n2m_s0_fused_init": [],
+    "n2m_s0_bwd_fused_part": [PP, P, P, P, P, U, P, P, P, P, P, P, P, U, U, P],
     "n2m_s0_ema_update": [P, P, P, P, P, P, U, F, P],
     "n2m_s0_ema_swap": [P, P, P, P, P, P, U, P, P],
 })
@@ -150,6 +152,7 @@ class Stage0Trainer:
         self.device = torch.device(device)
         dev = self.device
         call("n2m_s0_init")
+        call("n2m_s0_fused_init")
         c = cfg
         offs = level_offsets(3, c.num_levels, c.per_level_scale, c.base_resolution, c.log2_hashmap_size, False)
         self.offsets = torch.from_numpy(offs).to(dev)
@@ -193,6 +196,7 @@ class Stage0Trainer:
         self.loss_acc = torch.zeros(4, device=dev)          # [0] rgb(+mask) loss, [1] sum |spec|^2
         self.params = S0Params()
         self._fill_params(shading_full=True, gt_has_alpha=True)
+        self.fused_bwd = True               # MLP backward + scatter as one warp-specialised launch (csrc/fused.cu); False: two launches
         self.use_cam_near_far = False       # clamp (near, far) with the per-ray values in the slot's cam_nf (--enable_cam_near_far)
         self._tv_overlap = True             # TV gradient as its own launch overlapped with the MLP kernels (tv mode 2)
         self._tv_stream = None
@@ -422,6 +426,19 @@ class Stage0Trainer:
         call("n2m_s0_mlp_bwd_part", self._pp(), ptr(self.enc_tiles), ptr(self.dout), ptr(self.counters), self.Mcap, ptr(self.wpack),
              ptr(self.denc_tiles), ptr(self.g_mlps[self.parity]), ptr(self.opt_state), part, nparts, stream())
 
+    def bwd_fused(self, part=0, nparts=1):
+        call("n2m_s0_bwd_fused_part", self._pp(), ptr(self.enc_tiles), ptr(self.dout), ptr(self.recs), ptr(self.counters), self.Mcap,
+             ptr(self.rays_o), ptr(self.rays_d), ptr(self.wpack), ptr(self.offsets), ptr(self.gtables[self.parity]),
+             ptr(self.g_mlps[self.parity]), ptr(self.opt_state), part, nparts, stream())
+
+    def _backward(self, part=0, nparts=1):
+        """per-sample backward of one part on the current stream"""
+        if self.fused_bwd and not self.scatter_level_cuts:
+            self.bwd_fused(part, nparts)
+        else:
+            self.mlp_bwd(part, nparts)
+            self._scatter(part, nparts)
+
     def encode_bwd(self, part=0, nparts=1):
         if not self.scatter_level_cuts:
             call("n2m_s0_encode_bwd_part", self._pp(), ptr(self.recs), ptr(self.counters), self.Mcap, ptr(self.rays_o), ptr(self.rays_d),
@@ -490,10 +507,9 @@ class Stage0Trainer:
             launch_tv()
             self.mlp_fwd()
             self.composite_loss()
-            self.mlp_bwd()
+            self._backward(0, 1)
             if fork_tv:
                 main.wait_stream(self._tv_stream)
-            self._scatter(0, 1)
             return
         if self.part_mode == "pipeline":
             # two-stream software pipeline: gathers then scatters of all parts in order on this (normal-priority) stream,
@@ -532,8 +548,7 @@ class Stage0Trainer:
                     self.encode_fwd(k, P_)
                     self.mlp_fwd(k, P_)
                     self.composite_loss(k, P_)
-                    self.mlp_bwd(k, P_)
-                    self._scatter(k, P_)
+                    self._backward(k, P_)
             for st in streams[1:]:
                 main.wait_stream(st)
         if fork_tv:
@@ -622,7 +637,8 @@ class Stage0Trainer:
             key = (name, self.parity)
         else:
             key = (name, self.cur, self.parity, int(self.params.shading_full), int(self.params.gt_has_alpha), int(self.nparts),
-                   bool(self.tv_overlap), self.part_mode, tuple(self.scatter_level_cuts), bool(self.level_pipe), int(self.l2_persist_mb))
+                   bool(self.tv_overlap), self.part_mode, tuple(self.scatter_level_cuts), bool(self.level_pipe), int(self.l2_persist_mb),
+                   bool(self.fused_bwd))
         g = self._graphs.get(key)
         if g is None:
             g = torch.cuda.CUDAGraph()

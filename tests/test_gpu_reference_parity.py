@@ -92,7 +92,7 @@ def _warm_up(tr, c, bricks, steps=40):
     assert tr.counters[2].item() == 0, "sample capacity overflow during warm-up"
 
 
-def _ref_trainer(ref_stage, ns, c, state, fp16):
+def _ref_trainer(ref_stage, ns, c, state, fp16, loss_scale=None):
     opt = ref_stage.default_opt(bound=c["bound"], dt_gamma=c["dt_gamma"], lambda_entropy=c["lambda_entropy"], fp16=fp16,
                                 adaptive_num_rays=False, num_rays=N, enable_cam_near_far=c["cam_nf"])
     model = ns.make_model(opt)
@@ -104,6 +104,8 @@ def _ref_trainer(ref_stage, ns, c, state, fp16):
                           use_checkpoint="scratch", use_tensorboardX=False, scheduler_update_every_step=True)
     tr.global_step = 2000           # past --diffuse_step (utils.py:669-672): 'full' shading
     tr.ns = ns
+    if loss_scale is not None and fp16:
+        tr.scaler = torch.amp.GradScaler("cuda", init_scale=float(loss_scale))
     return tr
 
 
@@ -182,9 +184,18 @@ def test_fused_step_matches_reference_cuda_path(name):
     bg = torch.rand(N, 3, device="cuda"); noises = torch.rand(N, device="cuda")       # the draws train_step / march_rays_train will make
 
     # ---------------- reference: fp16 twice (run-to-run spread), fp32 once (its own quantisation error) ----------------
-    r16a = _ref_step(_ref_trainer(ref_stage, ns, c, state, True), data, seed)
-    r16b = _ref_step(_ref_trainer(ref_stage, ns, c, state, True), data, seed)
+    # GradScaler dynamics: the reference produces the gradient of every fp16-cast weight / colour table IN fp16 (autocast), so at the
+    # initial scale 65536 a 3e5-sample batch overflows and GradScaler halves the scale until it does not (utils.py:1176-1177).  Find
+    # that scale the way the reference would (back-off by 0.5) and run BOTH sides at it.
+    scale = 65536.0
+    for _ in range(16):
+        r16a = _ref_step(_ref_trainer(ref_stage, ns, c, state, True, scale), data, seed)
+        if all(torch.isfinite(g).all().item() for g in r16a["grads"].values()):
+            break
+        scale *= 0.5
+    r16b = _ref_step(_ref_trainer(ref_stage, ns, c, state, True, scale), data, seed)
     r32 = _ref_step(_ref_trainer(ref_stage, ns, c, state, False), data, seed)
+    tr.opt_state[0] = scale
     # ---------------- ours ----------------
     tr.slots[tr.cur].load(data["rays_o"], data["rays_d"], data["images"], bg, noises, data.get("cam_near_far"))
     tr._fill_params(True, c["alpha"])
@@ -194,7 +205,9 @@ def test_fused_step_matches_reference_cuda_path(name):
     g_ours = tr.export_reference_grads()
     loss_ours = tr.read_loss()
 
-    rep = {"case": name, "rays": N, "samples": M, "config": {k: v for k, v in c.items()}}
+    rep = {"case": name, "rays": N, "samples": M, "config": {k: v for k, v in c.items()}, "loss_scale": scale,
+           "found_inf_ours": float(tr.opt_state[3].item())}
+    assert tr.opt_state[3].item() == 0
     # ---- integers: bit-exact ----
     assert tr.counters[2].item() == 0
     assert M == r16a["M"] == r16b["M"] == r32["M"], (M, r16a["M"], r32["M"])

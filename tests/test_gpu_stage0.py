@@ -240,6 +240,37 @@ def test_pipelined_mlp_backward_equals_single_tile_kernel():
         assert (g0 - g1).abs().max().item() <= 1e-4 * g0.abs().max().item()
 
 
+@pytest.mark.parametrize("shading,n_rays,nparts", [("full", 192, 1), ("diffuse", 192, 1), ("full", 3072, 1), ("full", 3072, 2)])
+def test_fused_backward_equals_two_kernel_backward(shading, n_rays, nparts):
+    """k_s0_bwd_fused (MLP backward + scatter in one warp-specialised persistent launch, feature gradients handed over in shared
+    memory) vs k_mlp_bwd followed by k_s0_encode_bwd: same table / weight gradients up to the order of the fp32 atomics; 3072 rays give
+    every CTA several tiles (both buffers and both barrier phases are exercised), two parts exercise the boundary-tile row masks."""
+    tr, b = make(shading, N=n_rays)
+    tr.nparts = nparts
+    stage(tr, b)
+    tr._fill_params(shading == "full", True)
+    res = []
+    for fused in (False, True):
+        tr.fused_bwd = fused
+        tr.gtable.zero_(); tr.g_mlp.zero_(); tr.opt_state[3] = 0
+        tr.forward_backward()
+        torch.cuda.synchronize()
+        res.append({k: v.clone() for k, v in tr.export_reference_grads().items()})
+        assert tr.opt_state[3].item() == 0
+    M = int(tr.counters[1].item())
+    assert M > 128 * (148 if n_rays > 1000 else 1)
+    for name in res[0]:
+        a, r = res[1][name].double(), res[0][name].double()
+        assert r.abs().max().item() > 0, name
+        assert (a - r).abs().max().item() <= 1e-4 * r.abs().max().item() + 1e-12, name
+    # the inf flag is raised by the fused kernel too
+    tr.gtable.zero_(); tr.g_mlp.zero_()
+    tr.opt_state[0] = 1e30
+    tr.forward_backward()
+    torch.cuda.synchronize()
+    assert tr.opt_state[3].item() == 1
+
+
 def test_update_density_grid_matches_reference_composition():
     """Stage0Trainer.update_density_grid vs the reference's update_extra_state arithmetic (renderer.py:1074-1149)
     composed from torch + the (bit-exact) operator-level encoder, same random jitter (one [H^3, 3] draw per cascade in the
@@ -309,6 +340,7 @@ def test_ray_range_parts_equal_whole_batch(nparts):
     both neighbours with row masks) give the same forward values exactly and the same loss / gradients up to fp32
     atomic summation order."""
     tr, b = make()
+    tr.fused_bwd = False          # the two-kernel backward leaves the feature gradients in denc_tiles, compared below
     stage(tr, b)
     tr.forward_backward()
     torch.cuda.synchronize()

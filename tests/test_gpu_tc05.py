@@ -9,7 +9,7 @@ from nerf2mesh_b200._lib import P, U, I, call, ptr, stream
 
 pytestmark = pytest.mark.gpu
 
-_lib.register({"n2m_tc_probe": [P, P, P, U, U, I, I, P]})
+from profiles.probes import call as probe_call
 
 
 @pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1), (1, 0)])
@@ -22,7 +22,7 @@ def test_umma_matches_matmul(a_mn, b_mn, N, K):
     Ap = (A.t().contiguous() if a_mn else A).cuda()          # MN-major: stored [K, M]
     Bp = (B.t().contiguous() if b_mn else B).cuda()          # MN-major: stored [K, N]
     D = torch.full((128, N), float("nan"), device="cuda")
-    call("n2m_tc_probe", ptr(Ap), ptr(Bp), ptr(D), N, K, a_mn, b_mn, stream())
+    probe_call("n2m_tc_probe", ptr(Ap), ptr(Bp), ptr(D), N, K, a_mn, b_mn, stream())
     torch.cuda.synchronize()
     err = (D.cpu() - ref).abs().max().item()
     assert err <= 1e-3 * ref.abs().max().item(), f"max err {err}"

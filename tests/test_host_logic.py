@@ -173,6 +173,7 @@ def test_step_orchestration_call_sequence(monkeypatch):
     tr.level_pipe, tr._ev_first_pass, tr.scatter_level_cuts = False, [], ()
     tr.l2_persist_mb, tr._l2_granted = 0, None
     tr._offsets_host = list(range(0, 170, 10))
+    tr.fused_bwd = False
 
     chain = ["n2m_s0_encode_fwd_part", "n2m_s0_mlp_fwd_part", "n2m_s0_composite_loss_part", "n2m_s0_mlp_bwd_part", "n2m_s0_encode_bwd_part"]
     adam = ["n2m_s0_adam_head", "n2m_s0_adam_mlp", "n2m_s0_adam_tables", "n2m_s0_adam_post"]
@@ -183,6 +184,16 @@ def test_step_orchestration_call_sequence(monkeypatch):
     tr.nparts = 1
     tr._compute_then_adam()
     assert names() == [chain[0], "n2m_s0_tv"] + chain[1:] + adam
+    # default: MLP backward + scatter as ONE launch (csrc/fused.cu)
+    calls.clear(); tr.fused_bwd = True
+    tr._compute_then_adam()
+    assert names() == [chain[0], "n2m_s0_tv"] + chain[1:3] + ["n2m_s0_bwd_fused_part"] + adam
+    calls.clear(); tr.nparts = 2
+    tr._compute_then_adam()
+    assert names() == ["n2m_s0_tv"] + (chain[:3] + ["n2m_s0_bwd_fused_part"]) * 2 + adam
+    tr.fused_bwd, tr.nparts = False, 1
+    calls.clear()
+    tr._compute_then_adam()
     for P_ in (2, 4):
         calls.clear(); tr.nparts = P_
         tr._compute_then_adam()
