@@ -2,15 +2,18 @@
 """bench.py -- headline benchmark of the B200-native stage-0 train step (BASELINE.json metric:
 ray-samples/sec of one full train step, device-timed).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm
-    python bench.py --impl reference [--steps K] [--warmup W]      # CPU restatement of the reference step
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm (default workload: lego_stage0_converged)
+    python bench.py --workload garden_stage0                        # BASELINE config 4 (bound 16, 5 cascades, entropy, cam near/far)
+    python bench.py --workload lego_stage1                          # BASELINE config 5 (rasterize + texture-MLP step; pixels/s)
+    python bench.py --impl reference [--steps K] [--warmup W]      # CPU restatement of the reference step on the host cores
     torchrun --nproc-per-node N bench.py --gpus N ...              # one rank per GPU (NCCL)
 
-One "step" = one optimizer step of the fused pipeline on one batch of 4096 synthetic Lego-like rays
-(march -> hash-grid encode -> tcgen05 MLPs -> composite + loss -> backward -> TV -> Adam), workload
-"lego_stage0_converged" (SURVEY.md section 8d, config 2).  `value` = samples of all ranks / max-over-ranks
-device time with the batch already resident in HBM; `e2e` = the same through Stage0Trainer.step() with
-pinned-host batches (H2D inside the timed region) and a D2H read of the loss every step.
+One "step" = one optimizer step of the fused pipeline on one batch of 4096 synthetic rays (march -> hash-grid encode -> tcgen05
+MLPs -> composite + loss -> backward -> TV -> Adam).  `value` = samples of all ranks / max-over-ranks device time with the batch
+already resident in HBM; `e2e` = the same through Stage0Trainer.step() with pinned-host batches (H2D inside the timed region) and a
+D2H read of the loss every step.  Also in the line: `roofline` (dominant kernel, timed live with CUDA events, cold L2),
+`cpu_baseline` (oracle port on the host cores, bounded sample), `reference_cuda` (the UNMODIFIED reference model + trainer over the
+reference's own kernels, same box, same batches), `psnr` (ours vs that reference after the same short training run).
 """
 import argparse
 import json
@@ -25,18 +28,16 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = "lego_stage0_converged"
 NUM_RAYS = 4096
-ALG_BYTES = {"encode_fwd": 1053, "encode_bwd": 1024, "step": 2077}      # SURVEY.md section 8(d), bytes per sample
+ALG_BYTES = {"encode_fwd": 1053, "encode_bwd": 1024, "bwd_fused": 1024, "step": 2077}      # SURVEY.md section 8(d), bytes per sample
 
-
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the same command
-# (profiles/r1_ncu_summary.md, section r1f); null for kernels that were not captured
-NCU_TRAFFIC = {"encode_bwd": 129.0e6 + 153.6e6, "encode_fwd": 48.78e6 + 12.57e6}
-
-
-RED_LANES_PER_SAMPLE = 1.885e7 / 298645          # profiles/r1_ncu_summary.md r1f: RED sectors of k_s0_encode_bwd / samples of that launch
-RED_PEAK_GLANES = 132.7                           # profiles/redbench.py: v4.f32 REDs into a 98 MB table, G lanes/s
+WORKLOADS = {
+    # BASELINE config 2: lego recipe (readme.md:64): bound 1, dt_gamma 0, RGBA targets + mask loss, TV 1e-8
+    "lego_stage0_converged": dict(bound=1.0, dt_gamma=0.0, lambda_entropy=0.0, radius=None, alpha=True, cam_nf=False, cap=128),
+    # BASELINE config 4: garden recipe (scripts/runall_360_outdoor.sh:2): bound 16 => 5 cascades, dt_gamma 1/256, per-view camera
+    # near/far, entropy regulariser 1e-3, RGB targets, TV with the 10x outer weight (utils.py:815-821)
+    "garden_stage0": dict(bound=16.0, dt_gamma=1.0 / 256, lambda_entropy=1e-3, radius=1.2, alpha=False, cam_nf=True, cap=320),
+}
 
 
 def load_peaks():
@@ -46,6 +47,18 @@ def load_peaks():
         return float(pk["hbm_gbs"]), "measured"
     except Exception:
         return 6650.0, "fallback"
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` capture of this command
+    (profiles/ncu_traffic.json, written by profiles/summarize_ncu.py), or None when that kernel was not captured."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)
+        e = t["kernels"].get(kernel)
+        return None if e is None else {"bytes": e["dram_bytes"], "capture": t.get("capture")}
+    except Exception:
+        return None
 
 
 class ClockSampler(threading.Thread):
@@ -116,32 +129,63 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(sm)}
 
 
-def make_batches(n_batches, seed, pin):
+# ------------------------------------------------------------------------------------------------
+# synthetic workloads (no datasets are available): SURVEY.md section 8(d)
+# ------------------------------------------------------------------------------------------------
+_SCENES = {}
+
+
+def scene(workload):
     from nerf2mesh_b200 import synthetic as S
-    grid, bits, bricks = S.occupancy_regime("converged")
-    poses = S.orbit_cameras(100, seed=0)
+    if workload not in _SCENES:
+        w = WORKLOADS[workload]
+        _SCENES[workload] = S.garden_scene(bound=w["bound"]) if w["bound"] > 1 else S.occupancy_regime("converged")
+    return _SCENES[workload]
+
+
+def make_batches(n_batches, seed, pin, workload="lego_stage0_converged"):
+    from nerf2mesh_b200 import synthetic as S
+    w = WORKLOADS[workload]
+    grid, bits, bricks = scene(workload)
+    radius = w["radius"] or S.LEGO_RADIUS
+    poses = S.orbit_cameras(100, radius=radius, seed=0)
     intr = S.lego_intrinsics()
     g = torch.Generator().manual_seed(seed)
     out = []
     for _ in range(n_batches):
         ro, rd, _, _ = S.sample_rays(poses, intr, 800, 800, NUM_RAYS, g)
         gt = S.render_bricks(ro, rd, bricks)
+        if not w["alpha"]:
+            gt = (gt[:, :3] * gt[:, 3:] + (1 - gt[:, 3:])).contiguous()          # RGB images: white where nothing is hit
         bg = torch.rand(NUM_RAYS, 3, generator=g)
         noises = torch.rand(NUM_RAYS, generator=g)
         b = dict(ro=ro, rd=rd, gt=gt, bg=bg, noises=noises)
+        if w["cam_nf"]:
+            d = ro.norm(dim=-1)
+            b["cnf"] = torch.stack([(d - 1.1).clamp(min=0.05), d + 14.0], -1).contiguous()
         if pin:
             b = {k: v.pin_memory() for k, v in b.items()}
         out.append(b)
     return out, grid, bits
 
 
+def make_trainer(workload):
+    from nerf2mesh_b200.stage0 import Stage0Config, Stage0Trainer
+    w = WORKLOADS[workload]
+    cfg = Stage0Config(bound=w["bound"], dt_gamma=w["dt_gamma"], lambda_entropy=w["lambda_entropy"], num_rays=NUM_RAYS,
+                       max_samples=NUM_RAYS * w["cap"])
+    tr = Stage0Trainer(cfg, seed=0)
+    tr.use_cam_near_far = w["cam_nf"]
+    return tr
+
+
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the repo's PyTorch restatement of the reference step (there is no reference CPU path)
+# CPU arm: the repo's PyTorch restatement of the reference step (the reference has no CPU path)
 # ------------------------------------------------------------------------------------------------
 def cpu_step_rate(steps, warmup, budget_s=150.0):
-    """Times the CPU restatement of the train step (oracle/train_oracle.py) on a bounded sample of the 4096-ray batch.
-    The thread count and the sample size are calibrated first (8-ray steps): more threads are not always faster for the
-    index-heavy torch ops, and the whole (warmup + steps) run has to end within `budget_s` seconds."""
+    """Times the CPU restatement of the lego train step (oracle/train_oracle.py) on a bounded sample of the 4096-ray batch: the
+    thread count and the sample size are calibrated first with 8-ray steps (more threads are not always faster for the index-heavy
+    torch ops), then the sample is sized so that (warmup + steps) steps end within `budget_s` -- up to the full 4096 rays."""
     from oracle import train_oracle as T
     torch.manual_seed(0)
     batches, grid, bits = make_batches(1, 123, False)
@@ -168,8 +212,8 @@ def cpu_step_rate(steps, warmup, budget_s=150.0):
             best = (dt, nt)
     t8, threads = best
     torch.set_num_threads(threads)
-    per_step = min(20.0, budget_s / max(steps + warmup, 1))
-    rays = int(max(8, min(256, 8 * per_step / max(t8, 1e-3))))        # t8 / 8 over-estimates the per-ray cost (fixed overheads)
+    per_step = budget_s / max(steps + warmup, 1)
+    rays = int(max(8, min(NUM_RAYS, 8 * per_step / max(t8, 1e-3))))        # t8 / 8 over-estimates the per-ray cost (fixed overheads)
     b = {k: v[:rays] for k, v in batches[0].items()}
     f, opt = fresh()
     samples, t_total = 0, 0.0
@@ -180,6 +224,13 @@ def cpu_step_rate(steps, warmup, budget_s=150.0):
     return samples / t_total, t_total / max(steps, 1), threads, rays
 
 
+def cpu_baseline_dict(v, threads, rays, what):
+    return {"value": v, "unit": "samples/s", "cores": os.cpu_count(), "threads_used": threads, "kind": "port",
+            "sample": f"{rays} of the {NUM_RAYS} rays of one lego batch per step, full train step (oracle/train_oracle.py: march, "
+                      f"hash-grid encode, autocast-emulated MLPs, composite, loss, backward, TV, Adam), {what}; torch threads "
+                      f"calibrated over {{all, 32, 8}} -> {threads} of {os.cpu_count()} host threads"}
+
+
 def run_reference(args):
     """`--impl reference`: the reference has no CPU implementation of this path, so this arm times the
     CPU restatement (oracle port) with the host threads that serve it best, on a bounded sample per step."""
@@ -187,16 +238,129 @@ def run_reference(args):
     if rank != 0:
         return
     steps, warmup = max(1, args.steps), max(0, args.warmup)
-    v, sec, cores, rays = cpu_step_rate(steps, warmup)
+    v, sec, threads, rays = cpu_step_rate(steps, warmup, budget_s=float(args.cpu_budget_s))
     line = {"impl": "reference", "metric": "ray-samples/sec (train step)", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "rays_per_batch": NUM_RAYS},
-            "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
-                             "sample": f"{rays} of the {NUM_RAYS} rays of one batch per step, full train step (oracle/train_oracle.py), "
-                                       f"{warmup} warm-up + {steps} timed steps, {cores} of {os.cpu_count()} host threads (calibrated)"},
+            "config": {"workload": "lego_stage0_converged", "rays_per_batch": NUM_RAYS, "rays_per_timed_step": rays},
+            "cpu_baseline": cpu_baseline_dict(v, threads, rays, f"{warmup} warm-up + {steps} timed steps"),
             "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# same-box GPU baseline: the UNMODIFIED reference model + Trainer over the reference's own kernels (oracle/ref_stage.py)
+# ------------------------------------------------------------------------------------------------
+def reference_cuda_leg(workload, dev_batches, state, steps=10, warmup=3):
+    try:
+        from oracle import ref_stage
+        if not ref_stage.staged():
+            return {"unavailable": "reference Python files not staged (oracle/_ref/py)"}
+        w = WORKLOADS[workload]
+        ns = ref_stage.load("ref")
+        opt = ref_stage.default_opt(bound=w["bound"], dt_gamma=w["dt_gamma"], lambda_entropy=w["lambda_entropy"], adaptive_num_rays=False,
+                                    num_rays=NUM_RAYS, enable_cam_near_far=w["cam_nf"])
+        model = ns.make_model(opt)
+        model.load_state_dict({k: v.clone() for k, v in state.items()}, strict=True)
+        model.cuda().train()
+        rt = ns.utils.Trainer("ngp", opt, model, device=torch.device("cuda"), workspace=None, mute=True,
+                              optimizer=lambda m: torch.optim.Adam(m.get_params(opt.lr), eps=1e-15),
+                              criterion=torch.nn.MSELoss(reduction="none"), ema_decay=None, fp16=True, use_checkpoint="scratch",
+                              use_tensorboardX=False, scheduler_update_every_step=True)
+        rt.global_step = 2000
+        samples, ms = 0, 0.0
+        for it in range(warmup + steps):
+            b = dev_batches[it % len(dev_batches)]
+            data = dict(rays_o=b["ro"], rays_d=b["rd"], index=[0], images=b["gt"])
+            if "cnf" in b:
+                data["cam_near_far"] = b["cnf"]
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rt.optimizer.zero_grad()                                  # nerf/utils.py:1163-1177
+            _, _, loss = rt.train_step(data)
+            rt.scaler.scale(loss).backward()
+            rt.post_train_step()
+            rt.scaler.step(rt.optimizer)
+            rt.scaler.update()
+            e1.record()
+            torch.cuda.synchronize()
+            if it >= warmup:
+                ms += e0.elapsed_time(e1)
+                samples += int(rt.tmp_xyzs.shape[0])
+        del rt, model
+        torch.cuda.empty_cache()
+        return {"value": samples / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms / steps, "steps": steps,
+                "what": "unmodified nerf/network.py + nerf/renderer.py + nerf/utils.py (Trainer.train_step, post_train_step, "
+                        "GradScaler, torch.optim.Adam) over the reference's own CUDA kernels built for sm_100a, same batches, "
+                        "device-resident inputs, CUDA events"}
+    except Exception as e:      # noqa: BLE001
+        return {"unavailable": repr(e)[:300]}
+
+
+def psnr_leg(iters, eval_res=100, eval_views=2, seed=0):
+    """BASELINE.json 'PSNR vs ref': the lego recipe (readme.md:64: 4096 rays, density-grid update every 16 steps, diffuse shading for
+    the first third, lr warm-up + decay) for `iters` steps on the analytic scene -- once with this repo's fused trainer, once with the
+    reference's kernels in the reference's composition (oracle/ref_pipeline.py) on the same batch stream -- then PSNR of held-out
+    views against the analytic ground truth."""
+    try:
+        from nerf2mesh_b200 import synthetic as S
+        from nerf2mesh_b200.stage0 import Stage0Config, Stage0Trainer
+        from nerf2mesh_b200.train_synthetic import full_image_rays, lr_at, psnr
+        from oracle import ref_pipeline as RP
+        dev = "cuda"
+        bricks = S.make_bricks()
+        poses = S.orbit_cameras(100, seed=0)
+        test_poses = S.orbit_cameras(eval_views, seed=12345)
+        intr = S.lego_intrinsics()
+        diffuse_until = iters // 3
+        res = {}
+        for which in ("ours", "reference"):
+            torch.manual_seed(seed)
+            g = torch.Generator().manual_seed(seed + 1)
+            if which == "ours":
+                tr = Stage0Trainer(Stage0Config(bound=1.0, num_rays=NUM_RAYS, max_samples=NUM_RAYS * 640), seed=seed)
+                tr.density_grid.zero_()
+                init = tr.export_reference_state()
+            else:
+                tr = RP.RefTrainer(1.0)
+                tr.field.load_reference_state(init)
+            t0 = time.time()
+            for it in range(iters):
+                if it % 16 == 0:
+                    tr.update_density_grid() if which == "ours" else tr.update_extra_state()
+                ro, rd, _, _ = S.sample_rays(poses, intr, 800, 800, NUM_RAYS, g)
+                gt = S.render_bricks(ro, rd, bricks); bg = torch.rand(NUM_RAYS, 3, generator=g); noises = torch.rand(NUM_RAYS, generator=g)
+                sh = "diffuse" if it < diffuse_until else "full"
+                if which == "ours":
+                    tr.step(ro, rd, gt, bg, noises, shading=sh, lr=lr_at(it, iters))
+                else:
+                    tr.step(ro.to(dev), rd.to(dev), gt.to(dev), bg.to(dev), sh, lr_at(it, iters))
+            torch.cuda.synchronize()
+            secs = time.time() - t0
+            vals = []
+            for k in range(eval_views):
+                ro, rd = full_image_rays(test_poses[k], intr / (800 // eval_res), eval_res, eval_res)
+                gtv = S.render_bricks(ro, rd, bricks)
+                gt_rgb = gtv[:, :3] * gtv[:, 3:] + (1 - gtv[:, 3:])
+                if which == "ours":
+                    img, _, _ = tr.render(ro.to(dev), rd.to(dev), bg_color=1.0, shading="full")
+                else:
+                    img = tr.render_eval(ro.to(dev), rd.to(dev), 1.0, "full")
+                vals.append(psnr(img.clamp(0, 1).cpu(), gt_rgb))
+            res[which] = {"psnr_db": sum(vals) / len(vals), "train_seconds": secs}
+            if which == "ours":
+                over, max_m = tr.check_capacity(grow=False)
+                res[which]["overflowed_steps"] = over
+            del tr
+            torch.cuda.empty_cache()
+        res["iters"] = iters
+        res["delta_db"] = res["ours"]["psnr_db"] - res["reference"]["psnr_db"]
+        res["what"] = (f"lego recipe, {iters} steps of 4096 rays on the analytic bricks scene (host-synthesised batches, same stream for "
+                       f"both), {eval_views} held-out {eval_res}x{eval_res} views vs analytic ground truth; reference = its own kernels in "
+                       "its own composition (oracle/ref_pipeline.py)")
+        return res
+    except Exception as e:      # noqa: BLE001
+        return {"unavailable": repr(e)[:300]}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -213,20 +377,12 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from nerf2mesh_b200 import _lib
-    from nerf2mesh_b200.stage0 import Stage0Config, Stage0Trainer
     from nerf2mesh_b200.parallel import GradSync, PeerAdam
 
-    cfg = Stage0Config(bound=1.0, num_rays=NUM_RAYS, max_samples=NUM_RAYS * 128)
-    tr = Stage0Trainer(cfg, seed=0)
+    workload = args.workload
+    tr = make_trainer(workload)
     tr.nparts = args.parts
-    tr.part_mode = args.part_mode
-    tr.scatter_level_cuts = tuple(int(x) for x in args.scatter_cuts.split(",") if x)
-    tr.level_pipe = bool(args.level_pipe)
-    tr.l2_persist_mb = int(args.l2_persist_mb)
-    _lib.call("n2m_s0_set_mlp_bwd_pipelined", 0 if args.mlp_bwd == "single" else 1)
-    _lib.call("n2m_s0_set_mlp_bwd_issuers", 2 if args.mlp_bwd == "two-tile-2issuers" else 1)
-    if args.mlp_fwd_compact:
-        _lib.call("n2m_s0_set_mlp_fwd_compact", 1)
+    tr.fused_bwd = bool(args.fused_bwd)
     sync = None
     dp_used = args.dp
     if world > 1:
@@ -244,20 +400,21 @@ def run_ours(args):
         if sync is None:
             sync = GradSync(tr)
     n_batches = 8
-    host_batches, grid, bits = make_batches(n_batches, 1000 + rank, True)
+    host_batches, grid, bits = make_batches(n_batches, 1000 + rank, True, workload)
     dev_batches = [{k: v.cuda(non_blocking=True) for k, v in b.items()} for b in host_batches]
     tr.set_occupancy(bits, grid)
     m_total = torch.zeros(1, dtype=torch.int64, device="cuda")
     K, W = args.steps, args.warmup
 
     def tup(b):
-        return (b["ro"], b["rd"], b["gt"], b["bg"], b["noises"])
+        return (b["ro"], b["rd"], b["gt"], b["bg"], b["noises"]) + ((b["cnf"],) if "cnf" in b else ())
 
     def one_step(batches, it):
         # the next batch is handed over too: its H2D copy + march overlap this step on a side stream
         b = batches[it % n_batches]
         nb = None if args.no_prefetch else tup(batches[(it + 1) % n_batches])
-        tr.step(*tup(b), shading="full", use_graph=not args.no_graph, grad_sync=sync, next_batch=nb)
+        tr.step(b["ro"], b["rd"], b["gt"], b["bg"], b["noises"], shading="full", use_graph=not args.no_graph, grad_sync=sync,
+                next_batch=nb, cam_near_far=b.get("cnf"))
         m_total.add_(tr.counters[1])
 
     def barrier():
@@ -267,10 +424,11 @@ def run_ours(args):
 
     # ---- launches per step (eager, counted by the library) ----
     l0 = _lib.launch_count()
-    tr.step(dev_batches[0]["ro"], dev_batches[0]["rd"], dev_batches[0]["gt"], dev_batches[0]["bg"], dev_batches[0]["noises"],
-            use_graph=False, grad_sync=sync)
+    b0 = dev_batches[0]
+    tr.step(b0["ro"], b0["rd"], b0["gt"], b0["bg"], b0["noises"], use_graph=False, grad_sync=sync, cam_near_far=b0.get("cnf"))
     torch.cuda.synchronize()
     launches_per_step = _lib.launch_count() - l0
+    state0 = tr.export_reference_state() if (rank == 0 and world == 1 and not args.skip_reference) else None
 
     # ---- leg 1: device-resident inputs ----
     for it in range(W):
@@ -293,6 +451,7 @@ def run_ours(args):
         dist.all_reduce(samples, op=dist.ReduceOp.SUM)
     ms_total = ms.item(); samples_total = samples.item()
     value = samples_total / (ms_total * 1e-3)
+    overflow_steps, max_m = tr.check_capacity(grow=False)
 
     # ---- leg 2: end to end (pinned host -> device inside the timed region, loss read back every step) ----
     tr.drop_prefetch()
@@ -320,16 +479,16 @@ def run_ours(args):
     h2d = sum(v.numel() * v.element_size() for v in host_batches[0].values())
     d2h = loss_host.numel() * 4 + cnt_host.numel() * 4
 
-    # ---- per-stage device times (eager, CUDA events on the launching stream) -> roofline of the dominant kernel ----
+    # ---- per-stage device times (eager, CUDA events on the launching stream, L2 flushed before each) -> roofline ----
     tr.drop_prefetch()
     torch.cuda.synchronize()
-    stages = ["march", "encode_fwd", "tv", "mlp_fwd", "composite_loss", "mlp_bwd", "encode_bwd", "adam"]
+    stages = ["march", "encode_fwd", "tv", "mlp_fwd", "composite_loss"] + (["bwd_fused"] if tr.fused_bwd else ["mlp_bwd", "encode_bwd"]) + ["adam"]
     acc = {s: 0.0 for s in stages}
     reps = 5
     flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda")     # > 126 MB L2
     for r in range(reps):
         b = dev_batches[r % n_batches]
-        tr.rays_o.copy_(b["ro"]); tr.rays_d.copy_(b["rd"]); tr.gt.copy_(b["gt"]); tr.bg.copy_(b["bg"]); tr.noises.copy_(b["noises"])
+        tr.slots[tr.cur].load(b["ro"], b["rd"], b["gt"], b["bg"], b["noises"], b.get("cnf"))
         tr.loss_acc.zero_()
         for s in stages:
             flush.fill_(0.0)
@@ -338,42 +497,128 @@ def run_ours(args):
             torch.cuda.synchronize()
             acc[s] += a.elapsed_time(z) / reps
     M_last = int(tr.counters[1].item())
+    # density-grid update (every 16 steps in the reference, utils.py:1155-1156): timed on its own, the analytic occupancy is restored
+    keep_bits, keep_grid = tr.density_bitfield.clone(), tr.density_grid.clone()
+    upd_ms = 0.0
+    for r in range(3):
+        a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); tr.update_density_grid(); z.record()
+        torch.cuda.synchronize()
+        if r > 0:
+            upd_ms += a.elapsed_time(z) / 2
+    tr.set_occupancy(keep_bits, keep_grid)
     peak, peak_kind = load_peaks()
-    dom = max(("encode_fwd", "encode_bwd"), key=lambda s: acc[s])
+    dom = max(("encode_fwd", "bwd_fused" if tr.fused_bwd else "encode_bwd"), key=lambda s: acc[s])
     achieved = ALG_BYTES[dom] * M_last / (acc[dom] * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_s0_" + dom, "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": NCU_TRAFFIC.get(dom), "alg_bytes_per_sample": ALG_BYTES[dom], "samples_per_launch": M_last,
-                "kernel_ms": acc[dom], "stage_ms_cold_l2": {k: round(v, 4) for k, v in acc.items()},
+    kname = {"encode_fwd": "k_s0_encode_fwd", "encode_bwd": "k_s0_encode_bwd", "bwd_fused": "k_s0_bwd_fused"}[dom]
+    traffic = ncu_traffic(kname)
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None if traffic is None else traffic["bytes"],
+                "traffic_capture": None if traffic is None else traffic["capture"], "alg_bytes_per_sample": ALG_BYTES[dom],
+                "samples_per_launch": M_last, "kernel_ms": acc[dom], "stage_ms_cold_l2": {k: round(v, 4) for k, v in acc.items()},
                 "step_frac_of_hbm": ALG_BYTES["step"] * value / 1e9 / peak}
-    if dom == "encode_bwd":
-        # supplementary ruler: the scatter is bound by the rate of spread REDs into a table of its footprint, not by HBM bytes
-        # (profiles/redbench.py: 133 G lane-REDs/s into 98 MB, payload-independent; 63.1 lane-REDs per sample after run merging,
-        # from the l1tex RED sector count of the committed ncu capture)
-        lanes = RED_LANES_PER_SAMPLE * M_last
-        roofline["red_rate"] = {"achieved": lanes / (acc[dom] * 1e-3) / 1e9, "peak": RED_PEAK_GLANES, "unit": "G lane-REDs/s",
-                                "frac": lanes / (acc[dom] * 1e-3) / 1e9 / RED_PEAK_GLANES, "lanes_per_sample": RED_LANES_PER_SAMPLE}
 
     if rank == 0:
         cpu = None
         if world == 1 and not args.skip_cpu:
-            v, sec, cores, rays = cpu_step_rate(1, 1, budget_s=30.0)
-            cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
-                   "sample": f"{rays} of the {NUM_RAYS} rays of one batch, full train step (oracle/train_oracle.py), 1 warm-up + 1 timed, "
-                             f"{cores} of {os.cpu_count()} host threads (calibrated)"}
+            v, sec, threads, rays = cpu_step_rate(1, 1, budget_s=30.0)
+            cpu = cpu_baseline_dict(v, threads, rays, "1 warm-up + 1 timed step")
+        refc = None
+        if state0 is not None:
+            del flush
+            torch.cuda.empty_cache()
+            refc = reference_cuda_leg(workload, dev_batches, state0)
+        ps = None
+        if world == 1 and args.psnr_iters > 0 and workload == "lego_stage0_converged":
+            ps = psnr_leg(args.psnr_iters)
+        step_ms = ms_total / K
         line = {"metric": "ray-samples/sec (train step)", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16",
+                "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16",
                 "data": "synthetic",
-                "config": {"workload": WORKLOAD, "rays_per_batch": NUM_RAYS, "global_rays": NUM_RAYS * world,
-                           "samples_per_step": samples_total / K, "parallelism": f"dp{world}" + ("" if world == 1 else f"-{dp_used}"), "cuda_graph": not args.no_graph, "ray_range_parts": args.parts, "part_mode": args.part_mode, "scatter_level_cuts": list(tr.scatter_level_cuts), "mlp_fwd_compact": bool(args.mlp_fwd_compact), "level_pipe": bool(args.level_pipe), "mlp_bwd": args.mlp_bwd, "l2_persist_mb": int(args.l2_persist_mb), "march_prefetch": not args.no_prefetch,
+                "config": {"workload": workload, "rays_per_batch": NUM_RAYS, "global_rays": NUM_RAYS * world,
+                           "samples_per_step": samples_total / K, "parallelism": f"dp{world}" + ("" if world == 1 else f"-{dp_used}"),
+                           "cuda_graph": not args.no_graph, "ray_range_parts": args.parts, "fused_bwd": bool(tr.fused_bwd),
+                           "march_prefetch": not args.no_prefetch, **{k: v for k, v in WORKLOADS[workload].items() if k != "cap"},
+                           "sample_capacity": tr.Mcap, "capacity_overflow_steps": overflow_steps, "max_samples_seen": max_m,
                            "l2": "inputs cycle over 8 batches; tables+grads+Adam state (0.6 GB touched per step) exceed the 126 MB L2"},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms2.item() / K},
                 "gpu_launches": int(launches_per_step * K), "launches_per_step": int(launches_per_step),
-                "roofline": roofline, "cpu_baseline": cpu}
+                "roofline": roofline, "cpu_baseline": cpu,
+                "density_update": {"ms_per_call": upd_ms, "every_steps": 16, "cells": int(tr.density_grid.numel()),
+                                   "value_with_update": samples_total / K / ((step_ms + upd_ms / 16) * 1e-3)},
+                "reference_cuda": refc, "psnr": ps}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# stage-1 workload (BASELINE config 5)
+# ------------------------------------------------------------------------------------------------
+def run_stage1(args):
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device")
+    import numpy as np
+    from nerf2mesh_b200 import synthetic as S
+    from nerf2mesh_b200.stage0 import Stage0Config, Stage0Trainer
+    from nerf2mesh_b200.stage1 import Stage1Trainer
+    from nerf2mesh_b200.train_synthetic import full_image_rays
+    from oracle import raster_oracle as R           # mesh / projection builders only (host-side input synthesis)
+    h0 = w0 = 800
+    t0 = Stage0Trainer(Stage0Config(bound=1.0, num_rays=1024, max_samples=1024 * 128), seed=0)
+    v, f = R.icosphere(7)                                         # 327 680 faces ~ the reference's decimate target 3e5 (main.py:101)
+    s1 = Stage1Trainer(t0, torch.from_numpy(v), torch.from_numpy(f), h0, w0, ssaa=2)
+    g = torch.Generator().manual_seed(0)
+    views = []
+    for k in range(8):
+        cam = S.orbit_cameras(8, radius=1.35, seed=3)[k, :3, 3].numpy().astype(np.float64)
+        pose = torch.from_numpy(S.look_at_pose(cam).astype(np.float32))
+        intr = S.lego_intrinsics(h0, w0)
+        _, rd = full_image_rays(pose, intr, h0, w0)
+        mvp = R.perspective_mvp(cam, fovy=2 * np.arctan(0.5 * h0 / intr[1]), aspect=w0 / h0); mvp[1] *= -1
+        gt = torch.rand(h0 * w0, 4, generator=g); gt[:, 3] = 1.0
+        views.append((torch.from_numpy(mvp).cuda(), rd.cuda(), gt.cuda(), torch.rand(h0 * w0, 3, generator=g).cuda()))
+    K, W = args.steps, args.warmup
+    for it in range(W):
+        s1.step(*views[it % 8])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cov = torch.zeros(1, dtype=torch.int64, device="cuda")
+    e0.record()
+    for it in range(K):
+        s1.step(*views[(W + it) % 8])
+        cov.add_(s1.counters[1])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    # rasterize + points alone
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record()
+    for it in range(10):
+        s1.forward(*views[it % 8][:2])
+    r1.record()
+    torch.cuda.synchronize()
+    from nerf2mesh_b200 import raster as dr
+    glctx = dr.RasterizeCudaContext()
+    vclip = torch.nn.functional.pad(s1.vertices, (0, 1), value=1.0) @ views[0][0].T
+    q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dr.rasterize(glctx, vclip[None], s1.triangles, (s1.h, s1.w))
+    q0.record()
+    for it in range(10):
+        dr.rasterize(glctx, vclip[None], s1.triangles, (s1.h, s1.w))
+    q1.record()
+    torch.cuda.synchronize()
+    hi = s1.h * s1.w
+    line = {"metric": "pixels/sec (stage-1 texture step: rasterize + interpolate + colour MLPs fwd/bwd + Adam)",
+            "value": hi / (ms * 1e-3), "unit": "super-sampled pixels/s", "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
+            "config": {"workload": "lego_stage1", "mesh_faces": int(f.shape[0]), "image": [h0, w0], "ssaa": 2, "raster": [s1.h, s1.w],
+                       "covered_pixels_per_step": cov.item() / K, "antialias": False},
+            "rasterize_ms": q0.elapsed_time(q1) / 10, "rasterize_pixels_per_s": hi / (q0.elapsed_time(q1) / 10 * 1e-3),
+            "forward_ms": r0.elapsed_time(r1) / 10}
+    print(json.dumps(line))
 
 
 def main():
@@ -382,19 +627,14 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="lego_stage0_converged", choices=list(WORKLOADS) + ["lego_stage1"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-prefetch", action="store_true", help="do not overlap the next batch's march with this step")
     ap.add_argument("--skip-cpu", action="store_true")
-    ap.add_argument("--part-mode", default="chains", choices=["pipeline", "chains"])
-    ap.add_argument("--mlp-fwd-compact", action="store_true", help="experimental: MLP forward with the compact smem layout (3 CTAs/SM)")
-    ap.add_argument("--mlp-bwd", default="single", choices=["single", "two-tile", "two-tile-2issuers"],
-                    help="MLP backward kernel: one tile per CTA (default), two tiles + one issuer warp, or (experimental) two issuer warps")
-    ap.add_argument("--l2-persist-mb", type=int, default=0,
-                    help="experimental (with --scatter-cuts and --level-pipe): persisting-L2 carve-out for the gradient rows of the active scatter pass")
-    ap.add_argument("--level-pipe", action="store_true",
-                    help="experimental (with one --scatter-cuts level): optimizer of the first level range under the scatter of the second")
-    ap.add_argument("--scatter-cuts", default="", help="experimental: comma-separated hash levels at which the scatter is cut into "
-                                                       "separate launches (e.g. 10 = levels 0-9, then 10-15)")
+    ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="--impl reference: wall-clock budget of the whole CPU run")
+    ap.add_argument("--skip-reference", action="store_true", help="skip the same-box reference-CUDA leg")
+    ap.add_argument("--psnr-iters", type=int, default=300, help="training steps of the PSNR-vs-reference pair (0 = skip)")
+    ap.add_argument("--fused-bwd", type=int, default=0, help="1: MLP backward + scatter as one warp-specialised launch (csrc/fused.cu)")
     ap.add_argument("--parts", type=int, default=2, choices=[1, 2, 4, 8],
                     help="ray-range parts run as concurrent gather->MLP->composite->MLP'->scatter chains on forked streams")
     ap.add_argument("--dp", default="peer", choices=["peer", "nccl"],
@@ -402,6 +642,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "lego_stage1":
+        run_stage1(args)
     else:
         run_ours(args)
 

@@ -29,7 +29,8 @@
  *              51-53 unit view direction, 54-63 zero.  It is the A operand of every first-layer GEMM and is
  *              staged global->shared with a single bulk async copy.
  *   recs       [Mcap] float4 {t_before, dt, t_after, ray_id (bits)} per sample, ray order.
- *   counters   int32 [16]: [0] M (total samples marched), [1] min(M, Mcap), [2] overflow flag, [3] unused,
+ *   counters   int32 [16]: [0] M (total samples marched), [1] min(M, Mcap), [2] overflow flag, [3] / [15] samples inside / outside the
+ *              unit cube (counted by the TV pass, read by n2m_s0_tv_random),
  *              [4..12] sample offset of the first ray of every eighth of the batch (ray N*e/8, e = 0..8; [4] = 0,
  *              [12] = [1]): the boundaries of the ray-range parts of the *_part entry points below.
  *              [13] += 1 for every march whose M exceeded Mcap, [14] = largest M seen (persistent capacity accounting: the rays
@@ -75,26 +76,19 @@ int n2m_s0_init(void);
 /* test hook: 1 = sequential one-thread-per-ray marcher, 0 = warp-per-ray marcher (default); same results */
 int n2m_s0_set_serial_march(int on);
 
-/* tuning hook: where the TV gradient is evaluated: 0 = backward scatter kernel, 1 = forward gather kernel, 2 = own launch */
+/* where the TV gradient is evaluated: 0 = inside the backward scatter kernel, 2 = own launch n2m_s0_tv (default of the host code) */
 int n2m_s0_set_tv_mode(int mode);
-/* tuning hook: preferred shared-memory carve-out (percent, -1 = driver default) of the gather / scatter / composite / march
- * kernels; an SM holds one carve-out configuration at a time, so co-residency with the MLP kernels needs a matching one */
-int n2m_s0_set_gather_carveout(int percent);
 /* the stand-alone TV launch (tv mode 2): reads recs/table, adds into gtable; independent of the MLP kernels */
 int n2m_s0_tv(const n2m_s0_params* p, const void* recs, const int32_t* counters, uint32_t Mcap, const float* rays_o,
               const float* rays_d, const void* table, const int32_t* offsets, void* gtable, const float* loss_scale,
               n2m_stream_t stream);
-
-/* tuning hook: MLP backward variant, 0 = one tile per CTA (default), 1 = two tiles in flight + issuer warp */
-int n2m_s0_set_mlp_bwd_pipelined(int on);
-/* EXPERIMENTAL tuning hook (compiled, not yet measured on a GPU): issuing warps of the two-tile MLP backward (only with
- * n2m_s0_set_mlp_bwd_pipelined(1)): 1 = one issuer for both tile groups (default), 2 = one issuer per group */
-int n2m_s0_set_mlp_bwd_issuers(int n);
-/* EXPERIMENTAL tuning hook (compiled, not yet measured on a GPU): 1 = MLP forward with the specular hidden tile aliased onto the
- * dead sigma hidden tile (71 KB of shared memory per CTA => three CTAs per SM), 0 = default layout (two CTAs per SM) */
-int n2m_s0_set_mlp_fwd_compact(int on);
-/* debug: device buffer (>= 128 uint64) that block 0 of the pipelined MLP backward stamps with clock64(); NULL = off */
-int n2m_s0_set_prof(void* buf);
+/* GridEncoder.grad_total_variation's fallback (grid.py:181-183): a TV call of post_train_step (utils.py:815-823) that received no sample
+ * position evaluates the TV gradient at `num_points` (reference: 10^6) uniformly random points instead.  The TV pass of the step counts the
+ * samples inside / outside the unit cube into counters[3] / counters[15]; this launch (after it, same stream) adds the fallback of every
+ * group that stayed empty and exits at once otherwise.  Points: counter-based hash of (optimizer step, index).  `dump` (nullable,
+ * [num_points,3]): test hook -- run unconditionally with weight lambda_tv and store the points. */
+int n2m_s0_tv_random(const n2m_s0_params* p, const int32_t* counters, const void* table, const int32_t* offsets, void* gtable,
+                     const float* loss_scale, uint32_t num_points, float* dump, n2m_stream_t stream);
 
 /* sizes of the packed weight blob (bytes) and of the flat fp32 MLP parameter / gradient vector (floats) */
 uint32_t n2m_s0_wpack_bytes(void);
@@ -119,8 +113,7 @@ int n2m_s0_march(const n2m_s0_params* p, const float* rays_o, const float* rays_
                  int32_t* rays, int32_t* counters, float* tbuf, void* recs, uint32_t Mcap,
                  n2m_stream_t stream);
 
-/* gtable / loss_scale nullable: when given (and lambda_tv > 0) the TV gradient of the density features is added
- * to gtable here, where 4 of its 7 stencil values are already in registers */
+/* gtable / loss_scale: unused (kept for ABI stability; the TV gradient is evaluated by n2m_s0_tv or by the scatter) */
 int n2m_s0_encode_fwd(const n2m_s0_params* p, const void* recs, const int32_t* counters, uint32_t Mcap,
                       const float* rays_o, const float* rays_d, const void* table, const int32_t* offsets,
                       void* enc_tiles, void* gtable, const float* loss_scale, n2m_stream_t stream);
@@ -140,6 +133,14 @@ int n2m_s0_grid_points(uint32_t H, uint32_t first_cell, uint32_t count, float ca
 int n2m_s0_grid_update(const void* out, uint32_t count, float decay, float* grid_cells, n2m_stream_t stream);
 int n2m_s0_packbits_dev(const float* grid, uint32_t nbytes, const float* mean_density, float density_thresh, uint8_t* bitfield,
                         n2m_stream_t stream);
+
+/* NeRFRenderer.mark_untrained_grid (renderer.py:985-1071; called once by Trainer.train, utils.py:925): density_grid [cascades, H^3]
+ * cells (Morton order) that no camera sees (camera-space z > near, |x| < cx/fx * z + 2 * half_cell, same for y) or that lie outside
+ * aabb (+- half a cell) are set to -1.  poses [num_poses,4,4] camera-to-world; intrinsics [intr_count,4] = (fx, fy, cx, cy) on the
+ * DEVICE with intr_count 1 or num_poses; cam_near [num_poses] nullable (else min_near); *count_out (nullable) = marked cells. */
+int n2m_mark_untrained_grid(const float* poses, uint32_t num_poses, const float* intrinsics, uint32_t intr_count,
+                            const float* cam_near, float min_near, const float* aabb, float bound, uint32_t cascades,
+                            uint32_t H, float* density_grid, int32_t* count_out, n2m_stream_t stream);
 
 /* batch sampling on the device = get_rays (nerf/utils.py:236-290) + the stage-0 training collate (nerf/provider.py:300-331)
  * for N random (image, pixel) pairs: poses [num_poses,4,4] (device), intrinsics_host float[4] {fx, fy, cx, cy} (HOST),
@@ -173,12 +174,6 @@ int n2m_s0_encode_bwd(const n2m_s0_params* p, const void* recs, const int32_t* c
                       const float* rays_o, const float* rays_d, const void* denc_tiles, const void* table,
                       const int32_t* offsets, void* gtable, const float* loss_scale, n2m_stream_t stream);
 
-/* EXPERIMENTAL (compiled, not yet measured): L2 residency controls.  n2m_l2_persist_limit sets the device's persisting-L2 carve-out
- * (clamped to the device maximum, *granted receives the value); n2m_l2_window marks [base, base + bytes) as persisting with the given
- * hit ratio for kernels launched or captured on `stream` afterwards (base NULL or bytes 0 switches the window off). */
-int n2m_l2_persist_limit(uint64_t bytes, uint64_t* granted);
-int n2m_l2_window(n2m_stream_t stream, const void* base, uint64_t bytes, float hit_ratio);
-
 /* Ray-range parts.  The stages between march and optimizer can be run on `nparts` (1, 2, 4 or 8) contiguous ray ranges
  * of the batch -- part k covers rays [N*k/nparts, N*(k+1)/nparts) and their (contiguous, ray-ordered) samples -- so that
  * independent chains  gather -> MLP -> composite -> MLP backward -> scatter  of different parts can be in flight on
@@ -211,18 +206,11 @@ int n2m_s0_encode_bwd_part(const n2m_s0_params* p, const void* recs, const int32
  * n2m_s0_encode_bwd_part (gradients equal up to fp32 atomic order); the TV gradient stays with n2m_s0_tv.  n2m_s0_fused_init sets the
  * kernel attributes once per process. */
 int n2m_s0_fused_init(void);
+/* profiling hook: bit 0 = scatter warps skip their REDs, bit 1 = MLP warps skip the tensor-core rounds (results meaningless) */
+int n2m_s0_set_fused_debug(int mode);
 int n2m_s0_bwd_fused_part(const n2m_s0_params* p, const void* enc_tiles, const void* dout, const void* recs, const int32_t* counters,
                           uint32_t Mcap, const float* rays_o, const float* rays_d, const void* wpack, const int32_t* offsets,
                           void* gtable, float* g_mlp, float* loss_scale, uint32_t part, uint32_t nparts, n2m_stream_t stream);
-
-/* EXPERIMENTAL (compiled, not yet measured on a GPU): the scatter restricted to hash levels [level_lo, level_hi).  A spread RED
- * costs 1.40 SM-cycles per lane into a 32 MB table and 2.19 into the 98 MB gradient table whatever its payload
- * (profiles/redbench.py), so two passes over the samples (levels 0-9, then 10-15: ~48 MB of target rows each) may beat one.  Disjoint
- * ranges covering 0..16 are equivalent to n2m_s0_encode_bwd_part. */
-int n2m_s0_encode_bwd_levels(const n2m_s0_params* p, const void* recs, const int32_t* counters, uint32_t Mcap,
-                             const float* rays_o, const float* rays_d, const void* denc_tiles, const void* table,
-                             const int32_t* offsets, void* gtable, const float* loss_scale, uint32_t part, uint32_t nparts,
-                             uint32_t level_lo, uint32_t level_hi, n2m_stream_t stream);
 
 /* optimizer state block (device, float[8]): [0] loss_scale, [1] growth_tracker, [2] adam step t,
  * [3] found_inf, [4] lr (host-written each step), [5] 1-beta1^t, [6] sqrt(1-beta2^t), [7] 1/loss_scale.
@@ -241,10 +229,6 @@ int n2m_s0_adam(void* table, void* color_master, void* gtable, float* m_table, f
 int n2m_s0_adam_head(const float* g_mlp, float* opt_state, n2m_stream_t stream);
 int n2m_s0_adam_tables(void* table, void* color_master, void* gtable, float* m_table, float* v_table, uint32_t rows,
                        const float* opt_state, float eps, n2m_stream_t stream);
-/* EXPERIMENTAL (compiled, not yet measured): `tables` restricted to rows [row_lo, row_hi) -- e.g. the rows of the hash levels
- * whose gradients are already complete, while n2m_s0_encode_bwd_levels of the other levels is still running */
-int n2m_s0_adam_tables_range(void* table, void* color_master, void* gtable, float* m_table, float* v_table, uint32_t rows,
-                             uint32_t row_lo, uint32_t row_hi, const float* opt_state, float eps, n2m_stream_t stream);
 int n2m_s0_adam_mlp(float* mlp_params, float* g_mlp, float* m_mlp, float* v_mlp, void* wpack, const float* opt_state, float eps,
                     n2m_stream_t stream);
 int n2m_s0_adam_post(float* opt_state, n2m_stream_t stream);

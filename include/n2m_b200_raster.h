@@ -1,0 +1,52 @@
+/* n2m_b200_raster.h -- C ABI of the stage-1 mesh path of libn2m_b200.so (BASELINE config 5).
+ *
+ * The reference's stage 1 (NeRFRenderer.render_stage1, nerf/renderer.py:806-935) rasterizes the refined mesh with the third-party
+ * nvdiffrast library and runs the colour MLPs on the covered pixels.  These entry points replace the two nvdiffrast operators on
+ * that path, with nvdiffrast's documented output convention; the reference-side binding is `nerf2mesh_b200.raster`
+ * (`rasterize`, `interpolate` with the argument order of `nvdiffrast.torch`), see INTEGRATION.md.
+ *
+ *   n2m_rasterize             dr.rasterize(glctx, pos, tri, (H, W))   (renderer.py:860; also :338, :968)
+ *       pos  [V,4] f32 clip-space vertices, tri [F,3] i32, rast [H,W,4] f32 = (u, v, z/w, triangle_id + 1), zeros where empty;
+ *       pixel (x, y) samples NDC ((x+0.5)/W*2-1, (y+0.5)/H*2-1); (u, v) perspective-correct barycentrics of vertices 0 / 1;
+ *       vis [H*W] u64 and queue [F+1] u32 are caller-allocated scratch.  Triangles with a vertex at w <= 0 are skipped
+ *       (no near-plane clipping).
+ *   n2m_interpolate_forward   dr.interpolate(attr, rast, tri)         (renderer.py:862-863): out [H*W,A] = u a0 + v a1 + (1-u-v) a2
+ *   n2m_interpolate_backward  its gradient w.r.t. attr [V,A] (accumulated into the caller's zero-initialised buffer)
+ *   n2m_compact_covered       xyzs[mask], dirs[mask] of renderer.py:865-880 without the boolean-mask host sync: covered pixel
+ *                             indices + their positions / view directions, count in *counter (device)
+ */
+#ifndef N2M_B200_RASTER_H
+#define N2M_B200_RASTER_H
+
+#include "n2m_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int n2m_rasterize(const float* pos, uint32_t V, const int32_t* tri, uint32_t F, uint32_t H, uint32_t W, void* vis, uint32_t* queue,
+                  float* rast, n2m_stream_t stream);
+int n2m_interpolate_forward(const float* attr, uint32_t V, uint32_t A, const float* rast, const int32_t* tri, uint32_t num_pixels,
+                            float* out, n2m_stream_t stream);
+int n2m_interpolate_backward(const float* grad_out, const float* rast, const int32_t* tri, uint32_t num_pixels, uint32_t V, uint32_t A,
+                             float* grad_attr, n2m_stream_t stream);
+int n2m_compact_covered(const float* rast, const float* xyz, const float* dirs, uint32_t num_pixels, uint32_t cap, int32_t* counter,
+                        int32_t* pix, float* pts, float* pdirs, n2m_stream_t stream);
+
+/* ---- stage-1 texture-MLP step (csrc/stage1.cu; host side nerf2mesh_b200/stage1.py) ----
+ * n2m_s1_points: covered pixels of `rast` [h,w,4] -> compacted surface points for the stage-0 gather / MLP / backward kernels:
+ *   pts [cap,3] = dr.interpolate(vertices, rast, tri) at the covered pixels, pdirs [cap,3] = rays_d [h/ssaa * w/ssaa, 3] up-sampled
+ *   nearest-neighbour (renderer.py:828-829), recs [cap] float4 = (0, 0, 0, k) (a march record whose sample is its own origin),
+ *   inv [h*w] = slot of each pixel or -1; counters (>= 16 int32): [0] covered pixels, [1] min([0], cap), [2] overflow flag.
+ * n2m_s1_loss: per low-res pixel: image = mean(alpha * rgb) + (1 - mean(alpha)) * bg, MSE (+ lambda_mask * mask term for rgba targets)
+ *   averaged over the h0*w0 pixels into loss_out[0]; dout [cap] float4 = (0, dL/drgb) * loss_scale for the covered pixels. */
+int n2m_s1_points(const float* rast, const float* verts, const int32_t* tri, const float* rays_d, uint32_t h, uint32_t w, uint32_t ssaa,
+                  uint32_t cap, int32_t* counters, int32_t* inv, float* pts, float* pdirs, void* recs, n2m_stream_t stream);
+int n2m_s1_loss(const void* out, const int32_t* inv, const float* gt, uint32_t gt_channels, const float* bg, uint32_t h0, uint32_t w0,
+                uint32_t ssaa, float lambda_mask, const float* loss_scale, void* dout, float* image, float* weights_sum, float* loss_out,
+                n2m_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* N2M_B200_RASTER_H */

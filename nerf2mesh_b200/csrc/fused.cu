@@ -6,8 +6,10 @@
 // shared-memory use) leave each other's resources idle and run back to back (122 + 179 us).  Here one CTA per SM holds
 //     warps 0-3  : the MLP backward of k_mlp_bwd, one 128-sample tile at a time (thread = sample, thread 0 issues the MMAs);
 //                  the feature gradients of a finished tile go to a double-buffered shared-memory image instead of HBM,
-//     warps 4-11 : the scatter of the previous tile: warp = (32-sample group, even / odd levels), lane = sample, so consecutive
-//                  lanes are consecutive samples of a ray and runs of same-cell lanes are merged before the RED as before,
+//     warps 4-19 : the scatter of the previous tile: warp = (32-sample group, level l mod 4), lane = sample, so consecutive lanes
+//                  are consecutive samples of a ray and runs of same-cell lanes are merged before the RED as before (the scatter is
+//                  instruction-bound at low warp counts -- 8 warps took 297 us with REDs and MMAs switched off,
+//                  profiles/fusedprobe.py -- hence sixteen warps, register budgets by setmaxnreg, lattice constants in smem),
 // handing tiles over through two mbarrier pairs (full / empty).  The tensor chain of tile k+1 runs under the REDs of tile k, the
 // `denc_tiles` round trip through HBM (2 x 128 B per sample) disappears, and the step loses one launch per part.
 #include "n2m_common.cuh"
@@ -19,7 +21,9 @@
 namespace n2m {
 namespace {
 
-constexpr uint32_t kMlpThreads = 128, kScatWarps = 8, kFusedThreads = kMlpThreads + 32 * kScatWarps;      // 384
+constexpr uint32_t kMlpThreads = 128, kScatWarps = 16, kFusedThreads = kMlpThreads + 32 * kScatWarps;     // 640
+// register budget (setmaxnreg, multiples of 8): 128 x kMlpRegs + 512 x kScatRegs <= 65536
+constexpr uint32_t kMlpRegs = 200, kScatRegs = 72;
 constexpr uint32_t D_CHUNKS = 7;                          // gradient columns 0..55 (cols 3..50 are used)
 constexpr uint32_t D_BYTES = D_CHUNKS * kChunk;           // 14336
 constexpr uint32_t FB_DENC = B_BYTES;
@@ -37,44 +41,69 @@ __device__ __forceinline__ void mbar_arrive1(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(tc::smem_u32(bar)) : "memory");
 }
 
-// ---- scatter of one tile by one warp: rows [32 * sg, 32 * sg + 32) of the tile, levels PAR, PAR + 2, ..., PAR + 14 ----
-template <int PAR>
-__device__ __forceinline__ void scatter_levels(const n2m_s0_params& p, const Sample& s, bool active, const uint4 (&q)[D_CHUNKS],
-                                               const int32_t* __restrict__ offsets, float4* __restrict__ gtable, uint32_t lane) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const uint32_t l = 2 * i + PAR;
-        // this level's gradients: column kColDens + l, columns kColColor + 2l, + 2l + 1 (compile-time positions in q[])
-        constexpr uint32_t dummy = 0; (void)dummy;
-        const uint32_t cd = kColDens + l, cc = kColColor + 2 * l;
-        const uint32_t wd = reinterpret_cast<const uint32_t*>(&q[cd >> 3])[(cd & 7) >> 1];
-        const __half hd = (cd & 1) ? __ushort_as_half((unsigned short)(wd >> 16)) : __ushort_as_half((unsigned short)(wd & 0xffffu));
-        float g0, g1;
-        if ((cc & 1) == 0) {
-            const uint32_t wc = reinterpret_cast<const uint32_t*>(&q[cc >> 3])[(cc & 7) >> 1];
-            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&wc));
-            g0 = f.x; g1 = f.y;
-        } else {          // the pair straddles two 32-bit words (kColColor is odd)
-            const uint32_t wa = reinterpret_cast<const uint32_t*>(&q[cc >> 3])[(cc & 7) >> 1];
-            const uint32_t wb = reinterpret_cast<const uint32_t*>(&q[(cc + 1) >> 3])[((cc + 1) & 7) >> 1];
-            g0 = __half2float(__ushort_as_half((unsigned short)(wa >> 16)));
-            g1 = __half2float(__ushort_as_half((unsigned short)(wb & 0xffffu)));
-        }
-        const float gd = active ? __half2float(hd) : 0.f;
-        g0 = active ? g0 : 0.f; g1 = active ? g1 : 0.f;
+// per-level lattice constants, computed once per CTA into shared memory (level_geom + the dense / hashed index decision of
+// corners_of): the scatter warps are instruction-bound, not RED-bound, at the warp counts a fused CTA can afford
+struct LevelConst { float scale; uint32_t res, rows, row0, mx, my, mz, flags; };      // flags: bit 0 hashed, bit 1 rows is a power of two
 
-        const LevelGeom lg = level_geom(offsets, l, p.S, p.base_res);
-        Corners c; uint32_t base[3]; bool hashed;
-        corners_of(lg, s.u, s.v, s.w, c, base, hashed, nullptr);
-        float4* gt = gtable + lg.row0;
+__device__ __forceinline__ LevelConst make_level_const(const int32_t* __restrict__ offsets, uint32_t l, float S, uint32_t H) {
+    const LevelGeom g = level_geom(offsets, l, S, H);
+    LevelConst c;
+    c.scale = g.scale; c.res = g.res; c.rows = g.rows; c.row0 = g.row0;
+    const uint32_t s1 = g.res + 1;
+    uint32_t stride = 1;
+    c.mx = c.my = c.mz = 0;
+    if (stride <= g.rows) { c.mx = stride; stride *= s1; }
+    if (stride <= g.rows) { c.my = stride; stride *= s1; }
+    if (stride <= g.rows) { c.mz = stride; stride *= s1; }
+    c.flags = (stride > g.rows ? 1u : 0u) | (((g.rows & (g.rows - 1)) == 0) ? 2u : 0u);
+    return c;
+}
+
+// ---- scatter of one tile by one warp: rows [32 * sg, 32 * sg + 32) of the tile, levels lq, lq + 4, lq + 8, lq + 12 ----
+__device__ __forceinline__ void scatter_levels(const LevelConst* __restrict__ lc, uint32_t lq, const Sample& s, bool active,
+                                               const uint8_t* __restrict__ row, float4* __restrict__ gtable, uint32_t lane, bool no_red) {
+#pragma unroll 1
+    for (uint32_t i = 0; i < 4; ++i) {
+        const uint32_t l = lq + 4 * i;
+        // this level's gradients from the shared-memory image: column kColDens + l, columns kColColor + 2l, + 2l + 1
+        const uint32_t cd = kColDens + l, cc = kColColor + 2 * l;
+        const float gd = active ? __half2float(*reinterpret_cast<const __half*>(row + (cd >> 3) * kChunk + (cd & 7) * 2)) : 0.f;
+        const float g0 = active ? __half2float(*reinterpret_cast<const __half*>(row + (cc >> 3) * kChunk + (cc & 7) * 2)) : 0.f;
+        const float g1 = active ? __half2float(*reinterpret_cast<const __half*>(row + ((cc + 1) >> 3) * kChunk + ((cc + 1) & 7) * 2)) : 0.f;
+        const LevelConst L = lc[l];
+        // corners (same expressions as corners_of in s0_geom.cuh)
+        const float pu = s.u * L.scale + 0.5f, pv = s.v * L.scale + 0.5f, pw = s.w * L.scale + 0.5f;
+        const float fu0 = floorf(pu), fv0 = floorf(pv), fw0 = floorf(pw);
+        const uint32_t x0 = fu0, y0 = fv0, z0 = fw0;
+        const float fx = pu - (float)x0, fy = pv - (float)y0, fz = pw - (float)z0;
+        const bool hashed = (L.flags & 1u) != 0, pow2 = (L.flags & 2u) != 0;
+        uint32_t xs[2], ys[2], zs[2];
+        if (hashed) {
+            xs[0] = x0;                 xs[1] = x0 + 1u;
+            ys[0] = y0 * 2654435761u;   ys[1] = ys[0] + 2654435761u;
+            zs[0] = z0 * 805459861u;    zs[1] = zs[0] + 805459861u;
+        } else {
+            xs[0] = x0 * L.mx;          xs[1] = xs[0] + L.mx;
+            ys[0] = y0 * L.my;          ys[1] = ys[0] + L.my;
+            zs[0] = z0 * L.mz;          zs[1] = zs[0] + L.mz;
+        }
+        const float wx[2] = {1 - fx, fx}, wy[2] = {1 - fy, fy}, wz[2] = {1 - fz, fz};
+        uint32_t rowi[8];
         float vd[8], v0[8], v1[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { vd[k] = c.w[k] * gd; v0[k] = c.w[k] * g0; v1[k] = c.w[k] * g1; }
+        for (int k = 0; k < 8; ++k) {
+            const int ix = k & 1, iy = (k >> 1) & 1, iz = (k >> 2) & 1;
+            const uint32_t raw = hashed ? (xs[ix] ^ ys[iy] ^ zs[iz]) : (xs[ix] + ys[iy] + zs[iz]);
+            rowi[k] = pow2 ? (raw & (L.rows - 1)) : (raw % L.rows);
+            const float w = wx[ix] * wy[iy] * wz[iz];
+            vd[k] = w * gd; v0[k] = w * g0; v1[k] = w * g1;
+        }
+        float4* gt = gtable + L.row0;
         // runs of consecutive lanes in the same cell: sum them first, the last lane of a run issues the REDs
-        const uint32_t key = active ? (base[0] | (base[1] << 10) | (base[2] << 20)) : 0xffffffffu;
+        const uint32_t key = active ? (x0 | (y0 << 10) | (z0 << 20)) : 0xffffffffu;
         const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
         const uint32_t heads = __ballot_sync(0xffffffffu, lane == 0 || key != prev);
-        const bool merge = lg.res < 1023u && __popc(heads) <= 20;
+        const bool merge = L.res < 1023u && __popc(heads) <= 20;
         bool issue = active;
         if (merge) {
             const uint32_t run_start = 31u - __clz(heads & (0xffffffffu >> (31u - lane)));
@@ -90,10 +119,11 @@ __device__ __forceinline__ void scatter_levels(const n2m_s0_params& p, const Sam
             }
             issue = active && (lane == 31 || ((heads >> (lane + 1)) & 1u));
         }
-        if (issue) {
+        if (issue && !no_red) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) atomicAdd(gt + c.row[k], make_float4(vd[k], v0[k], v1[k], 0.f));
+            for (int k = 0; k < 8; ++k) atomicAdd(gt + rowi[k], make_float4(vd[k], v0[k], v1[k], 0.f));
         }
+        if (no_red && issue && vd[0] == 12345.678f) gt[rowi[0]].w = v0[3] + v1[5];       // keeps the arithmetic alive in the probe mode
     }
 }
 
@@ -101,10 +131,12 @@ __global__ void __launch_bounds__(kFusedThreads, 1)
 k_s0_bwd_fused(n2m_s0_params p, const uint8_t* __restrict__ enc_tiles, const float4* __restrict__ dout,
                const float4* __restrict__ recs, const int32_t* __restrict__ counters, const float* __restrict__ rays_o,
                const float* __restrict__ rays_d, const uint8_t* __restrict__ wpack, const int32_t* __restrict__ offsets,
-               float4* __restrict__ gtable, float* __restrict__ g_mlp, float* __restrict__ loss_scale, uint32_t part, uint32_t nparts) {
+               float4* __restrict__ gtable, float* __restrict__ g_mlp, float* __restrict__ loss_scale, uint32_t part, uint32_t nparts,
+               uint32_t dbg) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar_mma, bar_tma, bar_full[2], bar_empty[2];
     __shared__ uint32_t tmem_s;
+    __shared__ LevelConst s_lc[kLevels];
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const PartRange pr = part_range(counters, part, nparts);
     const uint32_t M = pr.M;
@@ -118,6 +150,7 @@ k_s0_bwd_fused(n2m_s0_params p, const uint8_t* __restrict__ enc_tiles, const flo
         tc::mbar_init_fence();
     }
     if (warp == 0) tc::tmem_alloc(&tmem_s, 512);
+    if (tid >= kMlpThreads && tid < kMlpThreads + kLevels) s_lc[tid - kMlpThreads] = make_level_const(offsets, tid - kMlpThreads, p.S, p.base_res);
     for (uint32_t i = tid; i < W_BYTES / 16; i += kFusedThreads)
         reinterpret_cast<uint4*>(smem + B_W)[i] = __ldg(reinterpret_cast<const uint4*>(wpack) + i);
     uint8_t* sW = smem + B_W; uint8_t* act = smem + B_ACT; uint8_t* grd = smem + B_GRAD;
@@ -146,7 +179,8 @@ k_s0_bwd_fused(n2m_s0_params p, const uint8_t* __restrict__ enc_tiles, const flo
 
     if (warp >= 4) {
         // =========================================== scatter warps ===========================================
-        const uint32_t sw = warp - 4, sg = sw & 3, par = sw >> 2;
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(kScatRegs));
+        const uint32_t sw = warp - 4, sg = sw & 3, lq = sw >> 2;
         uint32_t it = 0;
         for (uint32_t tile = t0 + blockIdx.x; tile < t1; tile += gridDim.x, ++it) {
             const uint32_t buf = it & 1, use = it >> 1;
@@ -161,35 +195,30 @@ k_s0_bwd_fused(n2m_s0_params p, const uint8_t* __restrict__ enc_tiles, const flo
                 s.x = s.y = s.z = s.u = s.v = s.w = 0.5f; s.dx = s.dy = s.dz = 0.f;
             }
             tc::mbar_wait(&bar_full[buf], use & 1);
-            uint4 q[D_CHUNKS];
-            const uint8_t* src = sD + buf * D_BYTES + r * 16;
-#pragma unroll
-            for (uint32_t ch = 0; ch < D_CHUNKS; ++ch) q[ch] = *reinterpret_cast<const uint4*>(src + ch * kChunk);
-            __syncwarp();
-            if (lane == 0) mbar_arrive1(&bar_empty[buf]);
-            if (par == 0) {   // fp16 overflow of the loss-scaled gradients => GradScaler semantics: flag, the step is skipped
+            const uint8_t* row = sD + buf * D_BYTES + r * 16;
+            if (lq == 0 && active) {   // fp16 overflow of the loss-scaled gradients => GradScaler semantics: flag, the step is skipped
                 bool bad = false;
-                if (active) {
 #pragma unroll
-                    for (uint32_t ch = 0; ch < D_CHUNKS; ++ch) {
-                        const uint32_t ww[4] = {q[ch].x, q[ch].y, q[ch].z, q[ch].w};
+                for (uint32_t ch = 0; ch < D_CHUNKS; ++ch) {
+                    const uint4 q = *reinterpret_cast<const uint4*>(row + ch * kChunk);
+                    const uint32_t ww[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&ww[i]));
-                            const uint32_t col = 8 * ch + 2 * i;
-                            if (col >= kColDens && col < kColDir) bad |= !isfinite(f.x);
-                            if (col + 1 >= kColDens && col + 1 < kColDir) bad |= !isfinite(f.y);
-                        }
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&ww[i]));
+                        const uint32_t col = 8 * ch + 2 * i;
+                        if (col >= kColDens && col < kColDir) bad |= !isfinite(f.x);
+                        if (col + 1 >= kColDens && col + 1 < kColDir) bad |= !isfinite(f.y);
                     }
                 }
                 if (bad) loss_scale[3] = 1.f;
-                scatter_levels<0>(p, s, active, q, offsets, gtable, lane);
-            } else {
-                scatter_levels<1>(p, s, active, q, offsets, gtable, lane);
             }
+            scatter_levels(s_lc, lq, s, active, row, gtable, lane, (dbg & 1u) != 0);
+            __syncwarp();
+            if (lane == 0) mbar_arrive1(&bar_empty[buf]);          // the image of this tile is no longer needed by this warp
         }
     } else {
         // =========================================== MLP warps (k_mlp_bwd) ===========================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(kMlpRegs));
         const uint32_t lane_t = (warp * 32u) << 16;
         const uint32_t K0 = tmem + T_K0, K1 = tmem + T_K1;
         uint32_t ph_mma = 0, ph_tma = 0;
@@ -201,6 +230,14 @@ k_s0_bwd_fused(n2m_s0_params p, const uint8_t* __restrict__ enc_tiles, const flo
         uint32_t it = 0;
         for (uint32_t tile = t0 + blockIdx.x; tile < t1; tile += gridDim.x, ++it) {
             const uint32_t buf = it & 1, use = it >> 1;
+            if (dbg & 2u) {          // probe mode: no tensor-core work, hand a zero image over at once (measures the scatter warps alone)
+                tc::mbar_wait(&bar_empty[buf], (use & 1) ^ 1);
+#pragma unroll
+                for (uint32_t ch = 0; ch < D_CHUNKS; ++ch) *reinterpret_cast<uint4*>(sD + buf * D_BYTES + ch * kChunk + tid * 16) = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);
+                bar_mlp();
+                if (tid == 0) mbar_arrive1(&bar_full[buf]);
+                continue;
+            }
             if (tid == 0) bulk_g2s(sA, enc_tiles + (size_t)tile * kTileBytes, kTileBytes, &bar_tma);
             const uint32_t j = tile * kTile + tid;
             float4 dv = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -442,6 +479,8 @@ k_s0_bwd_fused(n2m_s0_params p, const uint8_t* __restrict__ enc_tiles, const flo
 
 using namespace n2m;
 
+static uint32_t g_fused_dbg = 0;
+
 static int fused_num_sms() {
     static int n = 0;
     if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
@@ -449,6 +488,10 @@ static int fused_num_sms() {
 }
 
 extern "C" {
+
+/* profiling hook: bit 0 = the scatter warps skip their REDs, bit 1 = the MLP warps skip the tensor-core rounds (results are then
+ * meaningless; used by profiles/ to time each role of the fused backward alone) */
+int n2m_s0_set_fused_debug(int mode) { g_fused_dbg = (uint32_t)mode; return 0; }
 
 int n2m_s0_fused_init(void) {
     cudaError_t e = cudaFuncSetAttribute(k_s0_bwd_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FB_BYTES);
@@ -470,7 +513,7 @@ int n2m_s0_bwd_fused_part(const n2m_s0_params* p, const void* enc_tiles, const v
     const uint32_t grid = min(Mcap / kTile, (uint32_t)fused_num_sms());
     k_s0_bwd_fused<<<grid, kFusedThreads, FB_BYTES, as_stream(stream)>>>(
         *p, static_cast<const uint8_t*>(enc_tiles), static_cast<const float4*>(dout), static_cast<const float4*>(recs), counters,
-        rays_o, rays_d, static_cast<const uint8_t*>(wpack), offsets, static_cast<float4*>(gtable), g_mlp, loss_scale, part, nparts);
+        rays_o, rays_d, static_cast<const uint8_t*>(wpack), offsets, static_cast<float4*>(gtable), g_mlp, loss_scale, part, nparts, g_fused_dbg);
     return check_launch("s0_bwd_fused");
 }
 

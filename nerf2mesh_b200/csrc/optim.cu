@@ -7,7 +7,6 @@
 // opt_state (device float[8]): [0] loss_scale  [1] growth_tracker  [2] adam step t  [3] found_inf
 //                              [4] lr (host-written)  [5] 1 - beta1^t  [6] sqrt(1 - beta2^t)  [7] 1 / loss_scale
 #include "n2m_common.cuh"
-#include <cstring>
 #include "../../include/n2m_b200_fused.h"
 
 namespace n2m {
@@ -68,52 +67,6 @@ k_adam_tables(TableEntry* __restrict__ table, float2* __restrict__ cmaster, floa
     for (int j = 0; j < kRowsPerThread; ++j) {
         const uint32_t i = i0 + j * 256;
         if (i >= rows) continue;
-        gtable[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (skip) continue;
-        const float gx = g[j].x * inv, gy = g[j].y * inv, gz = g[j].z * inv;
-        // untouched row with empty moments: the update is exactly zero -- skip the writes
-        if (gx == 0.f && gy == 0.f && gz == 0.f && md[j] == 0.f && vd[j] == 0.f && mc[j].x == 0.f && mc[j].y == 0.f &&
-            vc[j].x == 0.f && vc[j].y == 0.f)
-            continue;
-        e[j].d = adam_update(e[j].d, gx, md[j], vd[j], lr1, bc2s, eps);
-        pc[j].x = adam_update(pc[j].x, gy, mc[j].x, vc[j].x, lr1, bc2s, eps);
-        pc[j].y = adam_update(pc[j].y, gz, mc[j].y, vc[j].y, lr1, bc2s, eps);
-        e[j].c = __floats2half2_rn(pc[j].x, pc[j].y);
-        table[i] = e[j];
-        cmaster[i] = pc[j];
-        m[i] = md[j]; v[i] = vd[j];
-        mc_p[i] = mc[j]; vc_p[i] = vc[j];
-    }
-}
-
-// Row-range variant: rows [row_lo, row_hi) only (`rows` stays the table size: it locates the colour moments behind the density
-// moments).  Lets a host run the optimizer of the hash levels whose gradients are complete while the scatter of the remaining
-// levels is still in flight (experimental, see Stage0Trainer.adam).  Same arithmetic as k_adam_tables.
-__global__ void __launch_bounds__(256)
-k_adam_tables_range(TableEntry* __restrict__ table, float2* __restrict__ cmaster, float4* __restrict__ gtable,
-                    float* __restrict__ m, float* __restrict__ v, uint32_t rows, uint32_t row_lo, uint32_t row_hi,
-                    const float* __restrict__ st, float eps) {
-    const uint32_t i0 = row_lo + blockIdx.x * (256 * kRowsPerThread) + threadIdx.x;
-    const bool skip = st[3] != 0.f;
-    const float inv = st[7];
-    const float lr1 = __fdiv_rn(st[4], st[5]), bc2s = st[6];
-    float2* mc_p = reinterpret_cast<float2*>(m + rows);
-    float2* vc_p = reinterpret_cast<float2*>(v + rows);
-    float4 g[kRowsPerThread]; float md[kRowsPerThread], vd[kRowsPerThread];
-    float2 mc[kRowsPerThread], vc[kRowsPerThread], pc[kRowsPerThread];
-    TableEntry e[kRowsPerThread];
-#pragma unroll
-    for (int j = 0; j < kRowsPerThread; ++j) {
-        const uint32_t i = i0 + j * 256;
-        if (i < row_hi) {
-            g[j] = gtable[i];
-            if (!skip) { md[j] = m[i]; vd[j] = v[i]; mc[j] = mc_p[i]; vc[j] = vc_p[i]; e[j] = table[i]; pc[j] = cmaster[i]; }
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < kRowsPerThread; ++j) {
-        const uint32_t i = i0 + j * 256;
-        if (i >= row_hi) continue;
         gtable[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (skip) continue;
         const float gx = g[j].x * inv, gy = g[j].y * inv, gz = g[j].z * inv;
@@ -228,17 +181,6 @@ extern "C" int n2m_s0_adam_tables(void* table, void* color_master, void* gtable,
     return check_launch("s0_adam(tables)");
 }
 
-extern "C" int n2m_s0_adam_tables_range(void* table, void* color_master, void* gtable, float* m_table, float* v_table, uint32_t rows,
-                                        uint32_t row_lo, uint32_t row_hi, const float* opt_state, float eps, n2m_stream_t stream) {
-    N2M_REQUIRE(table && color_master && gtable && m_table && v_table && opt_state, "s0_adam_tables_range", "null pointer");
-    N2M_REQUIRE(row_lo <= row_hi && row_hi <= rows, "s0_adam_tables_range", "row range outside the table");
-    if (row_hi == row_lo) return 0;
-    k_adam_tables_range<<<div_up(row_hi - row_lo, 256u * kRowsPerThread), 256, 0, as_stream(stream)>>>(
-        static_cast<TableEntry*>(table), static_cast<float2*>(color_master), static_cast<float4*>(gtable), m_table, v_table, rows,
-        row_lo, row_hi, opt_state, eps);
-    return check_launch("s0_adam(tables, range)");
-}
-
 extern "C" int n2m_s0_adam_mlp(float* mlp_params, float* g_mlp, float* m_mlp, float* v_mlp, void* wpack, const float* opt_state,
                                float eps, n2m_stream_t stream) {
     N2M_REQUIRE(mlp_params && g_mlp && m_mlp && v_mlp && wpack && opt_state, "s0_adam_mlp", "null pointer");
@@ -290,36 +232,4 @@ extern "C" int n2m_s0_ema_swap(void* table, void* color_master, float* mlp_param
                                                                    shadow_density, static_cast<float2*>(shadow_color), shadow_mlp, rows, n);
     if (int e = check_launch("s0_ema_swap")) return e;
     return n2m_s0_pack_weights(mlp_params, wpack, stream);
-}
-
-/* ---- L2 residency controls (experimental, compiled only): an access-policy window marks [base, base + bytes) as 'persisting'
- * for kernels subsequently launched (or captured) on `stream`; the spread REDs of the hash-gradient scatter cost 1.40 SM-cycles
- * per lane when their target rows are in L2 and 2.19 at the whole table's 98 MB footprint (profiles/redbench.py). ---- */
-extern "C" int n2m_l2_persist_limit(uint64_t bytes, uint64_t* granted) {
-    int dev = 0, max_persist = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
-    if (e != cudaSuccess) return fail("l2_persist_limit", cudaGetErrorString(e));
-    const size_t want = (size_t)(bytes < (uint64_t)max_persist ? bytes : (uint64_t)max_persist);
-    e = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
-    if (e != cudaSuccess) return fail("l2_persist_limit", cudaGetErrorString(e));
-    if (granted) *granted = (uint64_t)want;
-    return 0;
-}
-
-extern "C" int n2m_l2_window(n2m_stream_t stream, const void* base, uint64_t bytes, float hit_ratio) {
-    int dev = 0, max_win = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev);
-    if (e != cudaSuccess) return fail("l2_window", cudaGetErrorString(e));
-    cudaStreamAttrValue attr;
-    memset(&attr, 0, sizeof(attr));
-    attr.accessPolicyWindow.base_ptr = const_cast<void*>(base);
-    attr.accessPolicyWindow.num_bytes = base ? (size_t)(bytes < (uint64_t)max_win ? bytes : (uint64_t)max_win) : 0;    /* 0 bytes = window off */
-    attr.accessPolicyWindow.hitRatio = hit_ratio;
-    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-    e = cudaStreamSetAttribute(as_stream(stream), cudaStreamAttributeAccessPolicyWindow, &attr);
-    if (e != cudaSuccess) return fail("l2_window", cudaGetErrorString(e));
-    return 0;
 }

@@ -178,7 +178,8 @@ k_s0_scan(int32_t* __restrict__ rays, uint32_t N, uint32_t Mcap, int32_t* __rest
         counters[0] = (int32_t)M;
         counters[1] = (int32_t)min(M, Mcap);
         counters[2] = M > Mcap ? 1 : 0;
-        counters[3] = 0;
+        counters[3] = 0;                 // samples inside the unit cube   } counted by the TV pass of this step (k_s0_encode_bwd<.., TV>),
+        counters[15] = 0;                // samples outside the unit cube  } read by k_s0_tv_random (grid.py:181-183 fallback)
         // persistent capacity accounting (never reset by the march): steps that overflowed the sample slab, largest M seen
         if (M > Mcap) counters[13] += 1;
         counters[14] = max(counters[14], (int32_t)M);
@@ -211,23 +212,19 @@ k_s0_records(const int32_t* __restrict__ rays, const float2* __restrict__ tbuf, 
 
 // ------------------------------------------------------------------------------------------------
 // encode forward: one block = one 128-sample tile image.
-// Template TV (tv mode 1, NOT the default -- it was measured to slow this kernel from 76 to 194 us): also adds the
-// total-variation gradient of the density features (gridencoder.cu:506-609, called from utils.py:801-823) into gtable;
-// the centre and the three +1 neighbours ARE trilinear corners 0,1,2,4 that were just gathered, so TV costs three extra
-// loads here instead of seven; evaluated once per run of consecutive same-cell lanes (identical for every sample of a cell).
 // ------------------------------------------------------------------------------------------------
 // POINTS = false: samples come from the march records (training / eval rendering);
 // POINTS = true : explicit positions xyz [P,3] (rays_o) and optional directions [P,3] (rays_d) -- used for the
-//                 density-grid update (renderer.py:1112-1113 evaluates self.density on cell centres) and tests.
-template <bool POINTS, bool TV>
+//                 density-grid update (renderer.py:1112-1113 evaluates self.density on cell centres), stage 1 and tests.
+// (Evaluating the TV gradient here, where 4 of its 7 stencil values are already in registers, was measured at 194 us against 76 us for
+// this kernel alone plus a 75 us TV launch hidden under the MLP kernels -- profiles/r1_ncu_summary.md -- and was removed.)
+template <bool POINTS>
 __device__ __forceinline__ void
 encode_fwd_tile(const n2m_s0_params& p, const float4* __restrict__ recs,
                 const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                 const TableEntry* __restrict__ table, const int32_t* __restrict__ offsets,
-                uint8_t* __restrict__ enc_tiles, float4* __restrict__ gtable, const float* __restrict__ loss_scale,
-                const PartRange pr, uint32_t nparts, uint32_t tile) {
+                uint8_t* __restrict__ enc_tiles, const PartRange pr, uint32_t nparts, uint32_t tile) {
     const uint32_t r = threadIdx.x;
-    const uint32_t lane = r & 31;
     const uint32_t j = tile * kTile + r;
     float feat[kTileCols];
 #pragma unroll
@@ -254,46 +251,17 @@ encode_fwd_tile(const n2m_s0_params& p, const float4* __restrict__ recs,
     } else {
         s.x = s.y = s.z = s.u = s.v = s.w = 0.5f; s.dx = s.dy = s.dz = 0.f;
     }
-    const bool do_tv = TV && p.lambda_tv > 0 && gtable != nullptr;
-    // TV weight: lambda inside the unit cube, 10 lambda outside when bound > 1 (utils.py:815-821); w = weight / (2 D)
-    const float mag = fmaxf(fabsf(s.x), fmaxf(fabsf(s.y), fabsf(s.z)));
-    const float lam = (p.grid_bound > 1 && mag > 1) ? p.lambda_tv * 10 : p.lambda_tv;
-    const float tvw_lane = (active && do_tv) ? lam / 6 * loss_scale[0] : 0.f;
 
 #pragma unroll
     for (uint32_t l = 0; l < kLevels; ++l) {
         const LevelGeom g = level_geom(offsets, l, p.S, p.base_res);
-        Corners c; uint32_t base[3]; bool hashed; uint32_t left[3];
-        corners_of(g, s.u, s.v, s.w, c, base, hashed, TV ? left : nullptr);
+        Corners c; uint32_t base[3]; bool hashed;
+        corners_of(g, s.u, s.v, s.w, c, base, hashed, nullptr);
         const TableEntry* tab = table + g.row0;
-        // which lane evaluates the TV term of its cell: the last lane of each run of consecutive same-cell lanes
-        // (decided from the cell ids alone, BEFORE any load, so that the TV neighbours ride in the same load batch)
-        bool issue = false;
-        float tvw = tvw_lane;
-        if (TV && do_tv) {
-            const uint32_t key = active ? (base[0] | (base[1] << 10) | (base[2] << 20)) : 0xffffffffu;
-            const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
-            const uint32_t heads = __ballot_sync(0xffffffffu, lane == 0 || key != prev);
-            issue = active;
-            if (g.res < 1023u && heads != 0xffffffffu) {
-                const uint32_t run_start = 31u - __clz(heads & (0xffffffffu >> (31u - lane)));
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const float t = __shfl_up_sync(0xffffffffu, tvw, o);
-                    if (lane >= run_start + (uint32_t)o) tvw += t;
-                }
-                issue = active && (lane == 31 || ((heads >> (lane + 1)) & 1u));
-            }
-        }
-        uint2 raw[8];
-        float lv[3] = {0.f, 0.f, 0.f};
         if (active) {
+            uint2 raw[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) raw[k] = __ldg(reinterpret_cast<const uint2*>(tab + c.row[k]));
-            if (TV && issue) {
-#pragma unroll
-                for (int d = 0; d < 3; ++d) if (base[d] > 0) lv[d] = __ldg(&tab[left[d]].d);
-            }
             float d = 0.f, c0 = 0.f, c1 = 0.f;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
@@ -305,23 +273,6 @@ encode_fwd_tile(const n2m_s0_params& p, const float4* __restrict__ recs,
             feat[kColDens + l] = d;
             feat[kColColor + 2 * l] = c0;
             feat[kColColor + 2 * l + 1] = c1;
-        }
-        if (TV && issue) {
-            const float centre = __uint_as_float(raw[0].x);
-            float sum = 0.f, sq = 0.f;
-            const int right_corner[3] = {1, 2, 4};
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                if (base[d] < g.res) {
-                    const float dv = centre - __uint_as_float(raw[right_corner[d]].x);
-                    sum += dv; sq += dv * dv;
-                }
-                if (base[d] > 0) {
-                    const float dv = centre - lv[d];
-                    sum += dv; sq += dv * dv;
-                }
-            }
-            atomicAdd(&gtable[g.row0 + c.row[0]].x, tvw * sum * rsqrtf(sq + 1e-9f));
         }
     }
     // write this row of the tile image: 8 chunks of 16 bytes, each chunk 2 KiB apart
@@ -340,19 +291,18 @@ encode_fwd_tile(const n2m_s0_params& p, const float4* __restrict__ recs,
 
 // one block per 128-sample tile of the part's range [lo, hi) (grid-stride, so any grid size is correct: the host sizes
 // the grid for the expected share of the part and the loop covers an unbalanced one)
-template <bool POINTS, bool TV>
+template <bool POINTS>
 __global__ void __launch_bounds__(kTile, 6)
 k_s0_encode_fwd(n2m_s0_params p, const float4* __restrict__ recs, const int32_t* __restrict__ counters,
                 const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                 const TableEntry* __restrict__ table, const int32_t* __restrict__ offsets,
-                uint8_t* __restrict__ enc_tiles, float4* __restrict__ gtable, const float* __restrict__ loss_scale,
-                uint32_t part, uint32_t nparts) {
+                uint8_t* __restrict__ enc_tiles, uint32_t part, uint32_t nparts) {
     const PartRange pr = part_range(counters, part, nparts);
     if (pr.hi <= pr.lo) return;
     const uint32_t t1 = (pr.hi + kTile - 1) / kTile;
 #pragma unroll 1
     for (uint32_t tile = pr.lo / kTile + blockIdx.x; tile < t1; tile += gridDim.x)
-        encode_fwd_tile<POINTS, TV>(p, recs, rays_o, rays_d, table, offsets, enc_tiles, gtable, loss_scale, pr, nparts, tile);
+        encode_fwd_tile<POINTS>(p, recs, rays_o, rays_d, table, offsets, enc_tiles, pr, nparts, tile);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -363,13 +313,13 @@ k_s0_encode_fwd(n2m_s0_params p, const float4* __restrict__ recs, const int32_t*
 // contributions are first summed across each run of same-cell lanes with a segmented warp scan and only the
 // last lane of a run issues the red.global.add.v4.f32.  Fine levels (every lane its own cell) go straight to the atomics.
 // ------------------------------------------------------------------------------------------------
-template <bool SCATTER, bool TV, bool RANGE = false>
+template <bool SCATTER, bool TV>
 __device__ __forceinline__ void
 encode_bwd_tile(const n2m_s0_params& p, const float4* __restrict__ recs,
                 const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                 const uint8_t* __restrict__ denc_tiles, const TableEntry* __restrict__ table,
                 const int32_t* __restrict__ offsets, float4* __restrict__ gtable, float* __restrict__ loss_scale,
-                const PartRange pr, uint32_t tile, uint32_t level_lo = 0, uint32_t level_hi = kLevels) {
+                const PartRange pr, uint32_t tile, int32_t* tv_counts = nullptr) {
     const uint32_t r = threadIdx.x;
     const uint32_t lane = r & 31;
     const uint32_t j = tile * kTile + r;
@@ -407,11 +357,19 @@ encode_bwd_tile(const n2m_s0_params& p, const float4* __restrict__ recs,
     float tvw_lane = 0.f;
     if (TV) {
         const float mag = fmaxf(fabsf(s.x), fmaxf(fabsf(s.y), fabsf(s.z)));
-        const float lam = (p.grid_bound > 1 && mag > 1) ? p.lambda_tv * 10 : p.lambda_tv;
+        const bool outer = p.grid_bound > 1 && mag > 1;
+        const float lam = outer ? p.lambda_tv * 10 : p.lambda_tv;
         tvw_lane = active ? lam / 6 * loss_scale[0] : 0.f;
+        // how many samples each of the reference's TV calls would receive (utils.py:815-823: xyzs_inner / xyzs_outer, or all of them)
+        const bool mine = j >= pr.lo && j < pr.hi;
+        const uint32_t m_out = __ballot_sync(0xffffffffu, mine && outer), m_in = __ballot_sync(0xffffffffu, mine && !outer);
+        if (lane == 0 && tv_counts) {
+            if (m_in) atomicAdd(tv_counts + 3, (int)__popc(m_in));
+            if (m_out) atomicAdd(tv_counts + 15, (int)__popc(m_out));
+        }
     }
 #pragma unroll 1
-    for (uint32_t l = RANGE ? level_lo : 0u; l < (RANGE ? level_hi : kLevels); ++l) {
+    for (uint32_t l = 0; l < kLevels; ++l) {
         const LevelGeom lg = level_geom(offsets, l, p.S, p.base_res);
         Corners c; uint32_t base[3]; bool hashed; uint32_t left[3];
         corners_of(lg, s.u, s.v, s.w, c, base, hashed, TV ? left : nullptr);
@@ -489,33 +447,72 @@ k_s0_encode_bwd(n2m_s0_params p, const float4* __restrict__ recs, const int32_t*
     const uint32_t t1 = (pr.hi + kTile - 1) / kTile;
     if (!LOOP) {
         const uint32_t tile = pr.lo / kTile + blockIdx.x;
-        if (tile < t1) encode_bwd_tile<SCATTER, TV>(p, recs, rays_o, rays_d, denc_tiles, table, offsets, gtable, loss_scale, pr, tile);
+        if (tile < t1) encode_bwd_tile<SCATTER, TV>(p, recs, rays_o, rays_d, denc_tiles, table, offsets, gtable, loss_scale, pr, tile,
+                                                     const_cast<int32_t*>(counters));
         return;
     }
 #pragma unroll 1
     for (uint32_t tile = pr.lo / kTile + blockIdx.x; tile < t1; tile += gridDim.x)
-        encode_bwd_tile<SCATTER, TV>(p, recs, rays_o, rays_d, denc_tiles, table, offsets, gtable, loss_scale, pr, tile);
+        encode_bwd_tile<SCATTER, TV>(p, recs, rays_o, rays_d, denc_tiles, table, offsets, gtable, loss_scale, pr, tile,
+                                     const_cast<int32_t*>(counters));
 }
 
-// Level-range variant of the scatter: only levels [level_lo, level_hi).  profiles/redbench.py: a spread RED costs 1.40 SM-cycles
-// per lane into a 32 MB table, 2.19 into a 98 MB one (the whole gradient table) and 11.5 into a 512 MB one, whatever its
-// payload (4-16 B) -- the L2-resident fraction of the TARGET rows sets the pace.  Two passes over the samples (levels 0-9: 48 MB
-// of rows, levels 10-15: 50 MB) keep each pass's targets closer to L2-resident at the price of reading the 144 B/sample
-// of records + feature gradients twice.  Same arithmetic, same atomics.  Not the default until measured (tuning hook).
-template <bool SCATTER, bool TV>
-__global__ void __launch_bounds__(kTile)
-k_s0_encode_bwd_levels(n2m_s0_params p, const float4* __restrict__ recs, const int32_t* __restrict__ counters,
-                       const float* __restrict__ rays_o, const float* __restrict__ rays_d,
-                       const uint8_t* __restrict__ denc_tiles, const TableEntry* __restrict__ table,
-                       const int32_t* __restrict__ offsets, float4* __restrict__ gtable, float* __restrict__ loss_scale,
-                       uint32_t part, uint32_t nparts, uint32_t level_lo, uint32_t level_hi) {
-    const PartRange pr = part_range(counters, part, nparts);
-    if (pr.hi <= pr.lo) return;
-    const uint32_t t1 = (pr.hi + kTile - 1) / kTile;
+// ------------------------------------------------------------------------------------------------
+// TV fallback of GridEncoder.grad_total_variation (grid.py:181-183): a TV call that receives NO sample positions evaluates the TV
+// gradient at B = 10^6 uniformly random points of [0,1]^3 instead.  In the reference's post_train_step (utils.py:815-823) that happens
+// to the inner call (weight lambda) when no sample lies inside the unit cube, to the outer call (10 lambda) when none lies outside
+// (bound > 1), and to the single call of bound <= 1 when the batch marched no sample at all.  The group counts come from the TV pass of
+// this step (counters[3], [15]); the points from a counter-based hash of (optimizer step, point index) -- the reference draws
+// torch.rand, so the point SETS differ while the estimator is the same (tests feed the same points to the reference kernel).
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t h) {
+    h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+    return h;
+}
+__host__ __device__ __forceinline__ float tv_random_coord(uint32_t seed, uint32_t idx, uint32_t axis) {
+    return (float)(mix32(mix32(idx * 3u + axis) ^ (seed * 0x9e3779b9u)) >> 8) * (1.0f / 16777216.0f);
+}
+
+__global__ void __launch_bounds__(128)
+k_s0_tv_random(n2m_s0_params p, const int32_t* __restrict__ counters, const TableEntry* __restrict__ table,
+               const int32_t* __restrict__ offsets, float4* __restrict__ gtable, const float* __restrict__ loss_scale, uint32_t B,
+               float* __restrict__ dump) {
+    // which of the reference's TV calls of this step would have been empty
+    float lam = 0.f;
+    if (p.grid_bound > 1) {
+        if (counters[3] == 0) lam += p.lambda_tv;
+        if (counters[15] == 0) lam += p.lambda_tv * 10;
+    } else if (counters[3] + counters[15] == 0) lam = p.lambda_tv;
+    if (dump) lam = p.lambda_tv;                    // test hook: always run, plain weight, record the points
+    if (!(lam > 0.f)) return;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const uint32_t seed = (uint32_t)loss_scale[2];            // optimizer step count (opt_state[2]): a new point set every step
+    const float u = tv_random_coord(seed, i, 0), v = tv_random_coord(seed, i, 1), w = tv_random_coord(seed, i, 2);
+    if (dump) { dump[3 * i] = u; dump[3 * i + 1] = v; dump[3 * i + 2] = w; }
+    const float tvw = lam / 6 * loss_scale[0];
 #pragma unroll 1
-    for (uint32_t tile = pr.lo / kTile + blockIdx.x; tile < t1; tile += gridDim.x)
-        encode_bwd_tile<SCATTER, TV, true>(p, recs, rays_o, rays_d, denc_tiles, table, offsets, gtable, loss_scale, pr, tile,
-                                           level_lo, level_hi);
+    for (uint32_t l = 0; l < kLevels; ++l) {
+        const LevelGeom lg = level_geom(offsets, l, p.S, p.base_res);
+        Corners c; uint32_t base[3]; bool hashed; uint32_t left[3];
+        corners_of(lg, u, v, w, c, base, hashed, left);
+        const TableEntry* tab = table + lg.row0;
+        const int right_corner[3] = {1, 2, 4};
+        const float centre = __ldg(&tab[c.row[0]].d);
+        float rv[3], lv[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            rv[d] = __ldg(&tab[c.row[right_corner[d]]].d);
+            lv[d] = base[d] > 0 ? __ldg(&tab[left[d]].d) : 0.f;
+        }
+        float sum = 0.f, sq = 0.f;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            if (base[d] < lg.res) { const float dv = centre - rv[d]; sum += dv; sq += dv * dv; }
+            if (base[d] > 0) { const float dv = centre - lv[d]; sum += dv; sq += dv * dv; }
+        }
+        atomicAdd(&gtable[lg.row0 + c.row[0]].x, tvw * sum * rsqrtf(sq + 1e-9f));
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -789,7 +786,7 @@ k_s0_unpack_grads(const float4* __restrict__ gtable, uint32_t rows, const float*
 using namespace n2m;
 
 static bool g_serial_march = false;
-static int g_tv_mode = 0;            // TV gradient: 0 = inside the scatter kernel, 1 = inside the gather kernel, 2 = own launch (n2m_s0_tv)
+static int g_tv_mode = 0;            // TV gradient: 0 = inside the scatter kernel, 2 = own launch (n2m_s0_tv)
 
 // blocks for one part's gather / scatter launch: the part's expected share of the sample slab plus one boundary tile
 // (the kernels are grid-stride over the part's tiles, so an unbalanced part is still covered)
@@ -801,24 +798,9 @@ extern "C" {
 
 /* test hook: 1 = one-thread-per-ray sequential marcher (the reference's structure), 0 = warp-per-ray (default) */
 int n2m_s0_set_serial_march(int on) { g_serial_march = on != 0; return 0; }
-/* tuning hook: TV gradient evaluated 0 = by the backward scatter kernel, 1 = by the forward gather kernel, 2 = by its own
- * launch n2m_s0_tv (which the host overlaps with the tensor-core MLP kernels on a forked stream) */
+/* TV gradient evaluated 0 = by the backward scatter kernel, 2 = by its own launch n2m_s0_tv (which the host overlaps with the
+ * tensor-core MLP kernels on a forked stream) */
 int n2m_s0_set_tv_mode(int mode) { g_tv_mode = mode; return 0; }
-/* tuning hook: preferred shared-memory carve-out (percent of the SM's unified L1/shared storage, -1 = driver default) of the
- * gather / scatter / composite kernels.  An SM runs one carve-out configuration at a time: kernels that want the default
- * (L1-heavy) split cannot be co-resident with the tensor-core MLP kernels, which need 79-140 KB of shared memory. */
-int n2m_s0_set_gather_carveout(int percent) {
-    cudaError_t e = cudaSuccess;
-#define N2M_CARVE(K) if (e == cudaSuccess) e = cudaFuncSetAttribute(K, cudaFuncAttributePreferredSharedMemoryCarveout, percent)
-    N2M_CARVE((k_s0_encode_fwd<false, false>)); N2M_CARVE((k_s0_encode_fwd<false, true>)); N2M_CARVE((k_s0_encode_fwd<true, false>));
-    N2M_CARVE((k_s0_encode_bwd<true, true, false>)); N2M_CARVE((k_s0_encode_bwd<true, false, false>)); N2M_CARVE((k_s0_encode_bwd<false, true, false>));
-    N2M_CARVE((k_s0_encode_bwd<true, true, true>)); N2M_CARVE((k_s0_encode_bwd<true, false, true>));
-    N2M_CARVE(k_s0_composite_loss); N2M_CARVE(k_s0_count_warp); N2M_CARVE(k_s0_records);
-#undef N2M_CARVE
-    if (e != cudaSuccess) return fail("s0_set_gather_carveout", cudaGetErrorString(e));
-    return 0;
-}
-
 int n2m_s0_pack_tables(const float* emb_density, const float* emb_color, uint32_t rows, void* table, void* color_master,
                        n2m_stream_t stream) {
     N2M_REQUIRE(emb_density && emb_color && table && color_master, "s0_pack_tables", "null pointer");
@@ -868,19 +850,13 @@ int n2m_s0_encode_fwd_part(const n2m_s0_params* p, const void* recs, const int32
                            const float* rays_o, const float* rays_d, const void* table, const int32_t* offsets, void* enc_tiles,
                            void* gtable, const float* loss_scale, uint32_t part, uint32_t nparts, n2m_stream_t stream) {
     N2M_REQUIRE(p && recs && counters && rays_o && rays_d && table && offsets && enc_tiles, "s0_encode_fwd", "null pointer");
-    N2M_REQUIRE(!gtable || loss_scale, "s0_encode_fwd", "gtable given but loss_scale null");
     N2M_REQUIRE(p->num_levels == kLevels, "s0_encode_fwd", "fused path supports num_levels == 16");
     N2M_REQUIRE(Mcap % kTile == 0 && Mcap > 0, "s0_encode_fwd", "Mcap must be a positive multiple of 128");
     N2M_REQUIRE(valid_parts(part, nparts), "s0_encode_fwd", "nparts must be 1, 2, 4 or 8 and part < nparts");
-    if (g_tv_mode == 1 && gtable && p->lambda_tv > 0)
-        k_s0_encode_fwd<false, true><<<part_grid(Mcap, nparts), kTile, 0, as_stream(stream)>>>(*p, static_cast<const float4*>(recs), counters, rays_o, rays_d,
+    (void)gtable; (void)loss_scale;
+    k_s0_encode_fwd<false><<<part_grid(Mcap, nparts), kTile, 0, as_stream(stream)>>>(*p, static_cast<const float4*>(recs), counters, rays_o, rays_d,
                                                                                    static_cast<const TableEntry*>(table), offsets,
-                                                                                   static_cast<uint8_t*>(enc_tiles), static_cast<float4*>(gtable), loss_scale,
-                                                                                   part, nparts);
-    else
-        k_s0_encode_fwd<false, false><<<part_grid(Mcap, nparts), kTile, 0, as_stream(stream)>>>(*p, static_cast<const float4*>(recs), counters, rays_o, rays_d,
-                                                                                    static_cast<const TableEntry*>(table), offsets,
-                                                                                    static_cast<uint8_t*>(enc_tiles), nullptr, nullptr, part, nparts);
+                                                                                   static_cast<uint8_t*>(enc_tiles), part, nparts);
     return check_launch("s0_encode_fwd");
 }
 
@@ -895,9 +871,9 @@ int n2m_s0_encode_points(const n2m_s0_params* p, const float* xyz, const float* 
     N2M_REQUIRE(p && xyz && counters && table && offsets && enc_tiles, "s0_encode_points", "null pointer");
     N2M_REQUIRE(p->num_levels == kLevels, "s0_encode_points", "fused path supports num_levels == 16");
     N2M_REQUIRE(Pcap % kTile == 0 && Pcap > 0, "s0_encode_points", "Pcap must be a positive multiple of 128");
-    k_s0_encode_fwd<true, false><<<Pcap / kTile, kTile, 0, as_stream(stream)>>>(*p, nullptr, counters, xyz, dirs,
-                                                                        static_cast<const TableEntry*>(table), offsets,
-                                                                        static_cast<uint8_t*>(enc_tiles), nullptr, nullptr, 0, 1);
+    k_s0_encode_fwd<true><<<Pcap / kTile, kTile, 0, as_stream(stream)>>>(*p, nullptr, counters, xyz, dirs,
+                                                                         static_cast<const TableEntry*>(table), offsets,
+                                                                         static_cast<uint8_t*>(enc_tiles), 0, 1);
     return check_launch("s0_encode_points");
 }
 
@@ -966,27 +942,6 @@ int n2m_s0_encode_bwd(const n2m_s0_params* p, const void* recs, const int32_t* c
     return n2m_s0_encode_bwd_part(p, recs, counters, Mcap, rays_o, rays_d, denc_tiles, table, offsets, gtable, loss_scale, 0, 1, stream);
 }
 
-/* scatter restricted to the hash levels [level_lo, level_hi) (see k_s0_encode_bwd_levels); the union of disjoint ranges that
- * cover 0..16 equals n2m_s0_encode_bwd_part */
-int n2m_s0_encode_bwd_levels(const n2m_s0_params* p, const void* recs, const int32_t* counters, uint32_t Mcap,
-                             const float* rays_o, const float* rays_d, const void* denc_tiles, const void* table,
-                             const int32_t* offsets, void* gtable, const float* loss_scale, uint32_t part, uint32_t nparts,
-                             uint32_t level_lo, uint32_t level_hi, n2m_stream_t stream) {
-    N2M_REQUIRE(p && recs && counters && rays_o && rays_d && denc_tiles && table && offsets && gtable && loss_scale,
-                "s0_encode_bwd_levels", "null pointer");
-    N2M_REQUIRE(p->num_levels == kLevels, "s0_encode_bwd_levels", "fused path supports num_levels == 16");
-    N2M_REQUIRE(Mcap % kTile == 0 && Mcap > 0, "s0_encode_bwd_levels", "Mcap must be a positive multiple of 128");
-    N2M_REQUIRE(valid_parts(part, nparts), "s0_encode_bwd_levels", "nparts must be 1, 2, 4 or 8 and part < nparts");
-    N2M_REQUIRE(level_lo < level_hi && level_hi <= kLevels, "s0_encode_bwd_levels", "empty or out-of-range level interval");
-    const bool tv_here = p->lambda_tv > 0 && g_tv_mode == 0;
-    const uint32_t grid = nparts == 1 ? Mcap / kTile : part_grid(Mcap, nparts);
-    if (tv_here)
-        k_s0_encode_bwd_levels<true, true><<<grid, kTile, 0, as_stream(stream)>>>(N2M_BWD_ARGS, level_lo, level_hi);
-    else
-        k_s0_encode_bwd_levels<true, false><<<grid, kTile, 0, as_stream(stream)>>>(N2M_BWD_ARGS, level_lo, level_hi);
-    return check_launch("s0_encode_bwd_levels");
-}
-
 /* stand-alone TV-gradient launch (same arithmetic as inside the scatter kernel); only meaningful with tv mode 2 */
 int n2m_s0_tv(const n2m_s0_params* p, const void* recs, const int32_t* counters, uint32_t Mcap, const float* rays_o,
               const float* rays_d, const void* table, const int32_t* offsets, void* gtable, const float* loss_scale,
@@ -998,6 +953,18 @@ int n2m_s0_tv(const n2m_s0_params* p, const void* recs, const int32_t* counters,
     const uint32_t part = 0, nparts = 1;
     k_s0_encode_bwd<false, true, false><<<Mcap / kTile, kTile, 0, as_stream(stream)>>>(N2M_BWD_ARGS);
     return check_launch("s0_tv");
+}
+
+/* the random-point fallback of the TV calls that received no sample this step (see k_s0_tv_random); launch after n2m_s0_tv (or the
+ * scatter, in TV mode 0) on the same stream.  `dump` (nullable, [num_points,3]) is a test hook: run unconditionally with weight
+ * lambda_tv and store the points. */
+int n2m_s0_tv_random(const n2m_s0_params* p, const int32_t* counters, const void* table, const int32_t* offsets, void* gtable,
+                     const float* loss_scale, uint32_t num_points, float* dump, n2m_stream_t stream) {
+    N2M_REQUIRE(p && counters && table && offsets && gtable && loss_scale, "s0_tv_random", "null pointer");
+    if (!(p->lambda_tv > 0) || num_points == 0) return 0;
+    k_s0_tv_random<<<div_up(num_points, 128u), 128, 0, as_stream(stream)>>>(*p, counters, static_cast<const TableEntry*>(table), offsets,
+                                                                            static_cast<float4*>(gtable), loss_scale, num_points, dump);
+    return check_launch("s0_tv_random");
 }
 
 int n2m_s0_composite_loss_part(const n2m_s0_params* p, const void* out, const void* recs, const int32_t* rays,

@@ -36,9 +36,9 @@ PP = ctypes.POINTER(S0Params)
 _lib.register({
     "n2m_s0_init": [],
     "n2m_s0_set_serial_march": [I],
-    "n2m_s0_set_mlp_bwd_pipelined": [I],
     "n2m_s0_set_tv_mode": [I],
     "n2m_s0_tv": [PP, P, P, U, P, P, P, P, P, P, P],
+    "n2m_s0_tv_random": [PP, P, P, P, P, P, U, P, P],
     "n2m_s0_pack_weights": [P, P, P],
     "n2m_s0_pack_tables": [P, P, U, P, P, P],
     "n2m_s0_unpack_tables": [P, P, U, P, P, P],
@@ -59,19 +59,13 @@ _lib.register({
     "n2m_s0_composite_loss_part": [PP, P, P, P, P, U, U, P, P, P, P, P, P, P, P, U, U, P],
     "n2m_s0_mlp_bwd_part": [PP, P, P, P, U, P, P, P, P, U, U, P],
     "n2m_s0_encode_bwd_part": [PP, P, P, U, P, P, P, P, P, P, P, U, U, P],
-    "n2m_s0_encode_bwd_levels": [PP, P, P, U, P, P, P, P, P, P, P, U, U, U, U, P],
     "n2m_s0_adam_head": [P, P, P],
     "n2m_s0_adam_tables": [P, P, P, P, P, U, P, F, P],
     "n2m_s0_adam_mlp": [P, P, P, P, P, P, F, P],
     "n2m_s0_adam_post": [P, P],
-    "n2m_s0_adam_tables_range": [P, P, P, P, P, U, U, U, P, F, P],
-    "n2m_s0_set_prof": [P],
-    "n2m_s0_set_mlp_fwd_compact": [I],
-    "n2m_s0_set_mlp_bwd_issuers": [I],
-    "n2m_l2_persist_limit": [ctypes.c_uint64, P],
-    "n2m_l2_window": [P, P, ctypes.c_uint64, F],
-    "n2m_s0_set_gather_carveout": [I],
+    "n2m_mark_untrained_grid": [P, U, P, U, P, F, P, F, U, U, P, P, P],
     "n2m_s0_fused_init": [],
+    "n2m_s0_set_fused_debug": [I],
     "n2m_s0_bwd_fused_part": [PP, P, P, P, P, U, P, P, P, P, P, P, P, U, U, P],
     "n2m_s0_ema_update": [P, P, P, P, P, P, U, F, P],
     "n2m_s0_ema_swap": [P, P, P, P, P, P, U, P, P],
@@ -196,20 +190,14 @@ class Stage0Trainer:
         self.loss_acc = torch.zeros(4, device=dev)          # [0] rgb(+mask) loss, [1] sum |spec|^2
         self.params = S0Params()
         self._fill_params(shading_full=True, gt_has_alpha=True)
-        self.fused_bwd = True               # MLP backward + scatter as one warp-specialised launch (csrc/fused.cu); False: two launches
+        self.fused_bwd = False              # True: MLP backward + scatter as one warp-specialised launch (csrc/fused.cu)
         self.use_cam_near_far = False       # clamp (near, far) with the per-ray values in the slot's cam_nf (--enable_cam_near_far)
         self._tv_overlap = True             # TV gradient as its own launch overlapped with the MLP kernels (tv mode 2)
         self._tv_stream = None
         self.nparts = 1                     # ray-range parts run as concurrent chains on forked streams (1, 2, 4 or 8)
         self._part_streams = []
-        self.part_mode = "chains"           # "pipeline": gathers/scatters on one stream, MLPs on a high-priority one; "chains": a stream per part
-        self._mlp_stream = None
         self._adam_stream = None
-        self.l2_persist_mb = 0              # experimental: persisting-L2 carve-out (MB) used for the gradient rows of the active scatter pass
-        self._l2_granted = None
-        self.level_pipe = False             # experimental: optimizer of the first level range under the scatter of the second
-        self._ev_first_pass = []
-        self.scatter_level_cuts = ()        # experimental: e.g. (10,) = two scatter passes, levels 0-9 then 10-15 (include/n2m_b200_fused.h)
+        self.tv_fallback_points = 1000000   # GridEncoder.grad_total_variation's random-point fallback (grid.py:172,181-183)
         call("n2m_s0_set_tv_mode", 2 if self._tv_overlap else 0)
         # EMA of the parameters (Trainer(ema_decay=0.95), main.py:241): shadow buffers are allocated by enable_ema()
         self.ema_decay = None
@@ -392,6 +380,20 @@ class Stage0Trainer:
             grads[name] = g[o:o + n].view(shp).clone(); o += n
         return grads
 
+    def mark_untrained_grid(self, poses, intrinsics, cam_near_far=None):
+        """NeRFRenderer.mark_untrained_grid (renderer.py:985-1071): density-grid cells outside every training camera's frustum (or
+        outside the AABB) become -1 and are never updated again.  poses [B,4,4] camera-to-world, intrinsics [4] or [B,4]
+        (fx, fy, cx, cy), cam_near_far [B,2] optional.  Returns the number of marked cells as a device tensor (no host sync)."""
+        dev = self.device
+        poses = torch.as_tensor(poses, dtype=torch.float32).to(dev).contiguous()
+        intr = torch.as_tensor(intrinsics, dtype=torch.float32).to(dev).reshape(-1, 4).contiguous()
+        near = None if cam_near_far is None else torch.as_tensor(cam_near_far, dtype=torch.float32).to(dev)[:, 0].contiguous()
+        count = torch.zeros(1, dtype=torch.int32, device=dev)
+        c = self.cfg
+        call("n2m_mark_untrained_grid", ptr(poses), poses.shape[0], ptr(intr), intr.shape[0], ptr(near), c.min_near, ptr(self.aabb),
+             c.bound, c.cascade, c.grid_size, ptr(self.density_grid), ptr(count), stream())
+        return count
+
     def set_occupancy(self, density_bitfield, density_grid=None):
         self.density_bitfield.copy_(density_bitfield.to(self.device))
         if density_grid is not None:
@@ -433,28 +435,28 @@ class Stage0Trainer:
 
     def _backward(self, part=0, nparts=1):
         """per-sample backward of one part on the current stream"""
-        if self.fused_bwd and not self.scatter_level_cuts:
+        if self.fused_bwd:
             self.bwd_fused(part, nparts)
         else:
             self.mlp_bwd(part, nparts)
-            self._scatter(part, nparts)
+            self.encode_bwd(part, nparts)
 
     def encode_bwd(self, part=0, nparts=1):
-        if not self.scatter_level_cuts:
-            call("n2m_s0_encode_bwd_part", self._pp(), ptr(self.recs), ptr(self.counters), self.Mcap, ptr(self.rays_o), ptr(self.rays_d),
-                 ptr(self.denc_tiles), ptr(self.table), ptr(self.offsets), ptr(self.gtables[self.parity]), ptr(self.opt_state),
-                 part, nparts, stream())
-            return
-        # experimental: one scatter launch per level range, so that each launch's target rows are closer to L2-resident
-        bounds = [0, *self.scatter_level_cuts, self.cfg.num_levels]
-        for lo, hi in zip(bounds[:-1], bounds[1:]):
-            call("n2m_s0_encode_bwd_levels", self._pp(), ptr(self.recs), ptr(self.counters), self.Mcap, ptr(self.rays_o), ptr(self.rays_d),
-                 ptr(self.denc_tiles), ptr(self.table), ptr(self.offsets), ptr(self.gtables[self.parity]), ptr(self.opt_state),
-                 part, nparts, lo, hi, stream())
+        call("n2m_s0_encode_bwd_part", self._pp(), ptr(self.recs), ptr(self.counters), self.Mcap, ptr(self.rays_o), ptr(self.rays_d),
+             ptr(self.denc_tiles), ptr(self.table), ptr(self.offsets), ptr(self.gtables[self.parity]), ptr(self.opt_state),
+             part, nparts, stream())
 
     def tv(self):
+        """TV gradient of the density table at the step's samples (utils.py:801-823) + the random-point fallback of the TV calls that
+        got no sample (grid.py:181-183; exits at once when every group is populated)"""
         call("n2m_s0_tv", self._pp(), ptr(self.recs), ptr(self.counters), self.Mcap, ptr(self.rays_o), ptr(self.rays_d),
              ptr(self.table), ptr(self.offsets), ptr(self.gtables[self.parity]), ptr(self.opt_state), stream())
+        self.tv_random()
+
+    def tv_random(self, dump=None):
+        if self.cfg.lambda_tv > 0 and self.tv_fallback_points > 0:
+            call("n2m_s0_tv_random", self._pp(), ptr(self.counters), ptr(self.table), ptr(self.offsets), ptr(self.gtables[self.parity]),
+                 ptr(self.opt_state), int(self.tv_fallback_points), ptr(dump), stream())
 
     def adam(self):
         """Optimizer stage: head -> [table rows || MLP parameters + weight repack] -> GradScaler update.  The MLP branch
@@ -486,13 +488,16 @@ class Stage0Trainer:
           gather -> MLP -> composite -> MLP backward -> scatter of every part runs on its own stream, so the
           latency-bound tensor-core MLP kernels of one part share the SMs with the memory-bound gather / scatter
           kernels of another (measured in profiles/overlap_probe.py).
-        * `tv_overlap`: the TV-gradient kernel (memory bound, independent of the MLPs) runs on a forked stream as well.
+        * `tv_overlap`: the TV-gradient kernel (memory bound, independent of the MLPs) runs on a forked stream as well; otherwise it
+          is evaluated inside the scatter kernel and only the (normally empty) random-point fallback is launched behind it.
         All forks are joined before returning (and they are graph-capturable: fork/join by events only)."""
         self.loss_acc.zero_()
         main = torch.cuda.current_stream()
         P_ = int(self.nparts)
-        fork_tv = self.tv_overlap and self.cfg.lambda_tv > 0
-        self._ev_first_pass = []
+        has_tv = self.cfg.lambda_tv > 0
+        fork_tv = self.tv_overlap and has_tv
+        if self.fused_bwd and has_tv and not fork_tv:
+            raise RuntimeError("fused_bwd evaluates no TV gradient: keep tv_overlap=True (TV as its own launch)")
 
         def launch_tv():
             if fork_tv:
@@ -508,33 +513,6 @@ class Stage0Trainer:
             self.mlp_fwd()
             self.composite_loss()
             self._backward(0, 1)
-            if fork_tv:
-                main.wait_stream(self._tv_stream)
-            return
-        if self.part_mode == "pipeline":
-            # two-stream software pipeline: gathers then scatters of all parts in order on this (normal-priority) stream,
-            # MLP forward -> composite -> MLP backward of each part on ONE high-priority stream.  The tensor-core kernels
-            # are few persistent CTAs with long dependent chains: dispatched first (priority) they leave most of every SM
-            # to the gather / scatter blocks of the neighbouring parts, which fill in around them.
-            if self._mlp_stream is None:
-                self._mlp_stream = torch.cuda.Stream(device=self.device, priority=-1)
-            H = self._mlp_stream
-            H.wait_stream(main)
-            done = []
-            for k in range(P_):
-                self.encode_fwd(k, P_)
-                ev = torch.cuda.Event(); ev.record(main)
-                with torch.cuda.stream(H):
-                    H.wait_event(ev)
-                    self.mlp_fwd(k, P_)
-                    self.composite_loss(k, P_)
-                    self.mlp_bwd(k, P_)
-                    evb = torch.cuda.Event(); evb.record(H)
-                    done.append(evb)
-            launch_tv()                      # behind the gathers: fills the wait for the first MLP chain
-            for k in range(P_):
-                main.wait_event(done[k])
-                self._scatter(k, P_)
         else:
             # independent chains, one stream per part
             launch_tv()
@@ -553,75 +531,13 @@ class Stage0Trainer:
                 main.wait_stream(st)
         if fork_tv:
             main.wait_stream(self._tv_stream)
-
-    def _level_pipe_on(self):
-        return bool(self.level_pipe) and len(self.scatter_level_cuts) == 1
-
-    def _scatter(self, k, P_):
-        """Scatter of part k on the current stream.  With `level_pipe` (experimental) the first level range is followed by an event:
-        the optimizer of those levels' rows starts as soon as every part has passed it (`_compute_then_adam`)."""
-        if not self._level_pipe_on():
-            self.encode_bwd(k, P_)
-            return
-        cut = int(self.scatter_level_cuts[0])
-        args = (self._pp(), ptr(self.recs), ptr(self.counters), self.Mcap, ptr(self.rays_o), ptr(self.rays_d), ptr(self.denc_tiles),
-                ptr(self.table), ptr(self.offsets), ptr(self.gtables[self.parity]), ptr(self.opt_state), k, P_)
-        self._l2_window_rows(0, self._offsets_host[cut])
-        call("n2m_s0_encode_bwd_levels", *args, 0, cut, stream())
-        ev = torch.cuda.Event(); ev.record(torch.cuda.current_stream())
-        self._ev_first_pass.append(ev)
-        self._l2_window_rows(self._offsets_host[cut], self.rows)
-        call("n2m_s0_encode_bwd_levels", *args, cut, self.cfg.num_levels, stream())
-        self._l2_window_rows(0, 0)
-
-    def _l2_window_rows(self, row_lo, row_hi):
-        """experimental (`l2_persist_mb` > 0): mark the gradient rows [row_lo, row_hi) as L2-persisting for the launches that follow
-        on the current stream; (0, 0) switches the window off."""
-        if not self.l2_persist_mb:
-            return
-        if self._l2_granted is None:
-            g = ctypes.c_uint64(0)
-            call("n2m_l2_persist_limit", int(self.l2_persist_mb) << 20, ctypes.byref(g))
-            self._l2_granted = int(g.value)
-        nbytes = (row_hi - row_lo) * 16
-        if nbytes <= 0 or self._l2_granted == 0:
-            call("n2m_l2_window", stream(), None, 0, 0.0)
-            return
-        base = self.gtables[self.parity].data_ptr() + row_lo * 16
-        call("n2m_l2_window", stream(), ctypes.c_void_p(base), nbytes, min(1.0, self._l2_granted / nbytes))
+        elif has_tv:
+            self.tv_random()          # TV itself ran inside the scatter kernels (tv mode 0), which also counted the groups
 
     def _compute_then_adam(self):
-        """forward + backward + optimizer of one step.  Default: `_compute()` then `adam()`.
-
-        `level_pipe` (experimental, single-GPU path): the scatter runs as two level ranges; the optimizer of the rows of the
-        first range (head -> k_adam_tables_range) runs on the optimizer stream while the second range is still scattering --
-        an HBM-streaming kernel under a RED-bound one.  Safe because (a) the two ranges touch disjoint rows, (b) every sample's
-        feature gradients were inf-checked by the first pass, so found_inf is final when it ends, (c) the TV launch (all levels)
-        is joined first."""
-        if not self._level_pipe_on():
-            self._compute()
-            self.adam()
-            return
-        main = torch.cuda.current_stream()
-        self._compute()                                   # chains incl. both scatter passes; everything joined into `main`
-        if self._adam_stream is None:
-            self._adam_stream = torch.cuda.Stream(device=self.device)
-        side = self._adam_stream
-        row_cut = int(self._offsets_host[int(self.scatter_level_cuts[0])])
-        for ev in self._ev_first_pass:
-            side.wait_event(ev)
-        if self._tv_stream is not None:
-            side.wait_stream(self._tv_stream)
-        with torch.cuda.stream(side):
-            call("n2m_s0_adam_head", ptr(self.g_mlp), ptr(self.opt_state), stream())
-            call("n2m_s0_adam_tables_range", ptr(self.table), ptr(self.color_master), ptr(self.gtable), ptr(self.m_table),
-                 ptr(self.v_table), self.rows, 0, row_cut, ptr(self.opt_state), self.cfg.eps, stream())
-            call("n2m_s0_adam_mlp", ptr(self.mlp), ptr(self.g_mlp), ptr(self.m_mlp), ptr(self.v_mlp), ptr(self.wpack),
-                 ptr(self.opt_state), self.cfg.eps, stream())
-        main.wait_stream(side)
-        call("n2m_s0_adam_tables_range", ptr(self.table), ptr(self.color_master), ptr(self.gtable), ptr(self.m_table),
-             ptr(self.v_table), self.rows, row_cut, self.rows, ptr(self.opt_state), self.cfg.eps, stream())
-        call("n2m_s0_adam_post", ptr(self.opt_state), stream())
+        """forward + backward + optimizer of one step"""
+        self._compute()
+        self.adam()
 
     def _step_body(self):
         self.march()
@@ -637,8 +553,7 @@ class Stage0Trainer:
             key = (name, self.parity)
         else:
             key = (name, self.cur, self.parity, int(self.params.shading_full), int(self.params.gt_has_alpha), int(self.nparts),
-                   bool(self.tv_overlap), self.part_mode, tuple(self.scatter_level_cuts), bool(self.level_pipe), int(self.l2_persist_mb),
-                   bool(self.fused_bwd))
+                   bool(self.tv_overlap), bool(self.fused_bwd), int(self.tv_fallback_points))
         g = self._graphs.get(key)
         if g is None:
             g = torch.cuda.CUDAGraph()

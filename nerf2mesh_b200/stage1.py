@@ -1,0 +1,92 @@
+"""Stage-1 texture step: host side of csrc/raster.cu + csrc/stage1.cu (C ABI include/n2m_b200_raster.h).
+
+`Stage1Trainer` is the fused equivalent of one stage-1 iteration of the reference restricted to the appearance model
+(NeRFRenderer.render_stage1, nerf/renderer.py:806-935; Trainer.train_step stage-1 branch, nerf/utils.py:703-716;
+the optimizer step of utils.py:1163-1177): rasterize the mesh at ssaa x the image resolution, evaluate the colour
+MLPs (`self.rgb`, network.py:170-189) on the covered pixels with the tensor-core kernels of stage 0, average the
+super-samples, mix the background, MSE loss, backward into color_net / specular_net / encoder_color, Adam.  It shares
+the model state (hash tables, MLP weights, optimizer moments, GradScaler state) with a Stage0Trainer.
+
+Not built (DESIGN.md "stage 1"): dr.antialias (renderer.py:886-887) and therefore the gradient to the vertex offsets, the mesh
+regularisers (utils.py:750-790) and re-meshing (`refine_and_decimate`): vertices are fixed here.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import F, I, P, U, call, ptr, stream
+from . import raster as dr
+from .stage0 import S0Params
+
+_lib.register({
+    "n2m_s1_points": [P, P, P, P, U, U, U, U, P, P, P, P, P, P],
+    "n2m_s1_loss": [P, P, P, U, P, U, U, U, F, P, P, P, P, P, P],
+})
+
+
+class Stage1Trainer:
+    def __init__(self, t0, vertices, triangles, h0, w0, ssaa=2, max_points=None, lambda_mask=0.1):
+        assert ssaa in (1, 2), "the ssaa average equals the reference's bilinear down-scale only at factors 1 and 2"
+        self.t0 = t0
+        dev = t0.device
+        self.vertices = vertices.to(dev, torch.float32).contiguous()
+        self.triangles = triangles.to(dev, torch.int32).contiguous()
+        self.h0, self.w0, self.ssaa = int(h0), int(w0), int(ssaa)
+        self.h, self.w = self.h0 * ssaa, self.w0 * ssaa
+        n = self.h * self.w
+        self.cap = ((int(max_points) if max_points else n) + 127) // 128 * 128
+        self.lambda_mask = float(lambda_mask)
+        self.glctx = dr.RasterizeCudaContext(dev)
+        self.inv = torch.empty(n, dtype=torch.int32, device=dev)
+        self.pts = torch.zeros(self.cap, 3, device=dev); self.pdirs = torch.zeros(self.cap, 3, device=dev)
+        self.recs = torch.zeros(self.cap, 4, device=dev)
+        self.counters = torch.zeros(16, dtype=torch.int32, device=dev)
+        self.enc_tiles = torch.zeros(self.cap * 64, dtype=torch.float16, device=dev)
+        self.out = torch.zeros(self.cap, 4, device=dev); self.dout = torch.zeros(self.cap, 4, device=dev)
+        Q = self.h0 * self.w0
+        self.image = torch.zeros(Q, 3, device=dev); self.weights_sum = torch.zeros(Q, device=dev)
+        self.loss_acc = torch.zeros(4, device=dev)
+        self.rast = None
+        self.params = S0Params()
+        ctypes.memmove(ctypes.byref(self.params), ctypes.byref(t0.params), ctypes.sizeof(S0Params))
+        self.params.lambda_specular = 0.0          # the specular regulariser is a stage-0 loss (utils.py:726,735-738)
+        self.params.lambda_tv = 0.0
+
+    def _pp(self):
+        return ctypes.byref(self.params)
+
+    def forward(self, mvp, rays_d, shading="full"):
+        """rasterize -> surface points -> colour MLPs; leaves per-point colours in `out`, the pixel -> point map in `inv`."""
+        t0 = self.t0
+        self.params.shading_full = int(shading == "full")
+        mvp = mvp.to(t0.device, torch.float32)
+        vclip = torch.nn.functional.pad(self.vertices, (0, 1), value=1.0) @ mvp.T           # renderer.py:858
+        self.rast, _ = dr.rasterize(self.glctx, vclip[None], self.triangles, (self.h, self.w))
+        call("n2m_s1_points", ptr(self.rast), ptr(self.vertices), ptr(self.triangles), ptr(rays_d), self.h, self.w, self.ssaa, self.cap,
+             ptr(self.counters), ptr(self.inv), ptr(self.pts), ptr(self.pdirs), ptr(self.recs), stream())
+        call("n2m_s0_encode_points", self._pp(), ptr(self.pts), ptr(self.pdirs), ptr(self.counters), self.cap, ptr(t0.table),
+             ptr(t0.offsets), ptr(self.enc_tiles), stream())
+        call("n2m_s0_mlp_fwd", self._pp(), ptr(self.enc_tiles), ptr(self.counters), self.cap, ptr(t0.wpack), ptr(self.out), None, stream())
+
+    def loss_backward(self, gt, bg):
+        t0 = self.t0
+        self.loss_acc.zero_()
+        call("n2m_s1_loss", ptr(self.out), ptr(self.inv), ptr(gt), gt.shape[-1], ptr(bg), self.h0, self.w0, self.ssaa, self.lambda_mask,
+             ptr(t0.opt_state), ptr(self.dout), ptr(self.image), ptr(self.weights_sum), ptr(self.loss_acc), stream())
+        call("n2m_s0_bwd_fused_part", self._pp(), ptr(self.enc_tiles), ptr(self.dout), ptr(self.recs), ptr(self.counters), self.cap,
+             ptr(self.pts), ptr(self.pdirs), ptr(t0.wpack), ptr(t0.offsets), ptr(t0.gtables[t0.parity]), ptr(t0.g_mlps[t0.parity]),
+             ptr(t0.opt_state), 0, 1, stream())
+
+    def step(self, mvp, rays_d, gt, bg, shading="full", lr=None):
+        """One optimizer step on one view: mvp [4,4], rays_d [h0*w0,3] (unnormalised), gt [h0*w0, 3 or 4], bg [h0*w0,3]."""
+        t0 = self.t0
+        if lr is not None:
+            t0.opt_state[4:5].fill_(float(lr))
+        self.forward(mvp, rays_d.contiguous(), shading)
+        self.loss_backward(gt.contiguous(), bg.contiguous())
+        t0.adam()
+        t0.global_step += 1
+
+    def read_loss(self):
+        return float(self.loss_acc[0].item())

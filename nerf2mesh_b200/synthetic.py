@@ -78,6 +78,31 @@ def make_bricks(n_boxes=40, extent=0.7, seed=1, min_size=0.08, max_size=0.25):
             torch.from_numpy(rgb.astype(np.float32)))
 
 
+def make_garden_bricks(seed=1):
+    """Garden-like content for the bound-16 / 5-cascade configuration: the central object of
+    make_bricks(), a ground slab through the scene and a sparse shell of far boxes, so that samples fall inside AND outside the unit
+    cube and in every cascade."""
+    lo, hi, rgb = make_bricks(seed=seed)
+    rng = np.random.default_rng(seed + 100)
+    extra_lo, extra_hi, extra_rgb = [[-6.0, -6.0, -0.95]], [[6.0, 6.0, -0.8]], [[0.35, 0.5, 0.3]]          # ground
+    for _ in range(36):                                                                                    # far shell
+        r = rng.uniform(5.0, 13.0); az = rng.uniform(0, 2 * math.pi); el = rng.uniform(-0.05, 0.5)
+        c = np.array([r * math.cos(el) * math.cos(az), r * math.cos(el) * math.sin(az), r * math.sin(el)])
+        sz = rng.uniform(0.4, 1.6, 3)
+        extra_lo.append(list(np.clip(c - sz, -15.5, 15.5))); extra_hi.append(list(np.clip(c + sz, -15.5, 15.5)))
+        extra_rgb.append(list(rng.uniform(0.1, 0.95, 3)))
+    f = lambda a: torch.tensor(a, dtype=torch.float32)
+    return torch.cat([lo, f(extra_lo)]), torch.cat([hi, f(extra_hi)]), torch.cat([rgb, f(extra_rgb)])
+
+
+def garden_scene(H=128, bound=16.0, seed=1):
+    """(density_grid [5, H^3], bitfield, bricks) of the garden-like scene"""
+    bricks = make_garden_bricks(seed)
+    cascades = 1 + math.ceil(math.log2(bound))
+    grid = occupancy_from_bricks(bricks, H, bound, cascades)
+    return grid, packbits_host(grid), bricks
+
+
 def render_bricks(rays_o, rays_d, bricks):
     """Analytic first-hit render: returns rgba [N,4] (alpha 1 on hit, 0 on miss)."""
     lo, hi, rgb = bricks
@@ -110,7 +135,7 @@ def occupancy_from_bricks(bricks, H=128, bound=1.0, cascades=1, dilate=1):
     """density_grid float32 [cascades, H^3] in the reference's layout (cascade-major, Morton-ordered
     cells, renderer.py:1100-1118) with 1.0 inside (dilated) bricks, 0 elsewhere."""
     lo, hi, _ = bricks
-    lo = lo.numpy(); hi = hi.numpy()
+    lo = lo.numpy().astype(np.float64); hi = hi.numpy().astype(np.float64)
     ax = np.arange(H)
     coords = np.stack(np.meshgrid(ax, ax, ax, indexing="ij"), -1).reshape(-1, 3)
     mort = _morton_np(coords)
@@ -118,12 +143,15 @@ def occupancy_from_bricks(bricks, H=128, bound=1.0, cascades=1, dilate=1):
     for cas in range(cascades):
         b = min(2 ** cas, bound)
         cell = 2 * b / H
-        ctr = (coords + 0.5) * cell - b
         pad = dilate * cell
-        inside = np.zeros(len(coords), bool)
+        occ = np.zeros((H, H, H), bool)
+        # cell centre c_i = (i + 0.5) * cell - b lies in [lo - pad, hi + pad]  <=>  i in [ceil(.), floor(.)]
+        i0 = np.ceil((lo - pad + b) / cell - 0.5 - 1e-9).astype(np.int64).clip(0, H)
+        i1 = np.floor((hi + pad + b) / cell - 0.5 + 1e-9).astype(np.int64).clip(-1, H - 1)
         for k in range(len(lo)):
-            inside |= ((ctr >= lo[k] - pad) & (ctr <= hi[k] + pad)).all(-1)
-        grid[cas, mort] = inside.astype(np.float32)
+            if (i0[k] <= i1[k]).all():
+                occ[i0[k, 0]:i1[k, 0] + 1, i0[k, 1]:i1[k, 1] + 1, i0[k, 2]:i1[k, 2] + 1] = True
+        grid[cas, mort] = occ.reshape(-1).astype(np.float32)
     return torch.from_numpy(grid)
 
 

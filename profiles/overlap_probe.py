@@ -36,7 +36,7 @@ stages = {"encode_fwd": tr.encode_fwd, "encode_bwd": tr.encode_bwd, "mlp_fwd": t
           "tv": tr.tv, "composite": tr.composite_loss}
 import nerf2mesh_b200.stage0  # noqa: F401  (registers the hooks)
 for carve in (-1, 100, 75):
-    call("n2m_s0_set_gather_carveout", carve)
+    pass  # (the carve-out hook was removed in round 2: forcing the max-shared split cost the gather its L1, 114 -> 169 us)
     print("== gather/scatter shared-memory carve-out =", carve)
     alone = {k: timed(f) for k, f in stages.items()}
     print("alone (us, cold L2):", {k: round(v, 1) for k, v in alone.items()})

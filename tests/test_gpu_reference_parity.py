@@ -54,9 +54,9 @@ def _batch(c, seed):
 
 
 def _scene(c):
-    cas = 1 + int(np.ceil(np.log2(c["bound"])))
-    grid, bits, bricks = S.occupancy_regime("converged", cascades=cas, bound=c["bound"])
-    return grid, bits, bricks
+    if c["bound"] > 1:
+        return S.garden_scene(bound=c["bound"])      # central object + ground slab + far shell: samples inside and outside the unit cube
+    return S.occupancy_regime("converged", cascades=1, bound=c["bound"])
 
 
 def _gt(c, ro, rd, bricks):
@@ -70,7 +70,7 @@ def _cam_nf(c, ro):
     if not c["cam_nf"]:
         return None
     d = ro.norm(dim=-1)
-    return torch.stack([(d - 1.1).clamp(min=0.05), d + 1.3], -1).contiguous()   # per-view near/far as colmap_provider derives them
+    return torch.stack([(d - 1.1).clamp(min=0.05), d + 14.0], -1).contiguous()  # per-view near/far as colmap_provider derives them
 
 
 def _make_ours(c, bits, grid):
@@ -233,6 +233,13 @@ def test_fused_step_matches_reference_cuda_path(name):
         ga, gb, g32 = r16a["grads"][nm], r16b["grads"][nm], r32["grads"][nm]
         rep["grads"][nm] = {"ours_vs_ref16": _cmp(g_ours[nm], ga), "ref16_run_to_run": _cmp(gb, ga), "ref16_vs_ref32": _cmp(ga, g32),
                             "ours_vs_ref32": _cmp(g_ours[nm], g32)}
+    # per-level breakdown of the density-table gradient (rows of level l: offsets[l] .. offsets[l+1])
+    offs = tr.offsets.cpu().tolist()
+    rep["density_grad_by_level"] = []
+    for l in range(16):
+        a, r = g_ours["encoder.embeddings"][offs[l]:offs[l + 1]], r32["grads"]["encoder.embeddings"][offs[l]:offs[l + 1]]
+        r16 = r16a["grads"]["encoder.embeddings"][offs[l]:offs[l + 1]]
+        rep["density_grad_by_level"].append({"level": l, "ours_vs_ref32": _cmp(a, r), "ref16_vs_ref32": _cmp(r16, r)})
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", f"parity_{name}.json"), "w") as f:
         json.dump(rep, f, indent=1, default=float)
@@ -273,13 +280,18 @@ def test_unmodified_reference_model_runs_over_the_drop_in_operators():
     ro, rd = ro.cuda(), rd.cuda()
     bg = torch.rand(n, 3, device="cuda")
     outs = []
+    shared = None
     for ns in (ns_ref, ns_our):
         opt = ref_stage.default_opt(bound=1.0, dt_gamma=0.0, adaptive_num_rays=False)
         torch.manual_seed(0)
         model = ns.make_model(opt).cuda()
-        with torch.no_grad():       # same parameters on both sides (seeded init), a visible density
-            model.sigma_net.net[1].weight.mul_(30.0)
-            model.density_bitfield.copy_(bits.cuda()); model.density_grid.copy_(grid.cuda())
+        with torch.no_grad():       # same parameters on both sides, a visible density
+            if shared is None:
+                model.sigma_net.net[1].weight.mul_(30.0)
+                model.density_bitfield.copy_(bits.cuda()); model.density_grid.copy_(grid.cuda())
+                shared = {k: v.clone() for k, v in model.state_dict().items()}
+            else:
+                model.load_state_dict(shared, strict=True)          # the drop-in GridEncoder exposes the reference's state-dict keys
         model.train()
         torch.manual_seed(1)
         res = model.render(ro, rd, bg_color=bg, perturb=True, **{k: v for k, v in vars(opt).items() if k not in ("bg_color", "perturb")})
@@ -296,13 +308,17 @@ def test_unmodified_reference_model_runs_over_the_drop_in_operators():
     assert a["enc"] == "gridencoder.grid" and b["enc"].startswith("nerf2mesh_b200")
     assert a["M"] == b["M"] and a["M"] > 20000
     for k in ("ev_image", "ev_depth"):      # inference: deterministic kernels and identical row order on both sides => bit-exact
-        assert torch.equal(a[k], b[k]), k
+        assert torch.equal(a[k], b[k]), (k, (a[k] - b[k]).abs().max().item())
     for k in ("image", "ws", "depth"):      # training: the reference's sample offsets follow atomic order, ours the ray order --
         # same per-ray arithmetic, but a cuBLAS row may round differently at another position in the batch
-        assert torch.equal(a[k], b[k]) or (a[k] - b[k]).abs().max().item() <= 1e-5 * max(1.0, a[k].abs().max().item()), k
+        assert torch.equal(a[k], b[k]) or (a[k] - b[k]).abs().max().item() <= 1e-5 * max(1.0, a[k].abs().max().item()), \
+            (k, (a[k] - b[k]).abs().max().item())
     for k in a["grads"]:                                               # atomics: order-dependent rounding only
         x, y = a["grads"][k].double(), b["grads"][k].double()
-        assert (x - y).abs().max().item() <= 2e-3 * x.abs().max().item(), k
+        # the colour table's gradient is accumulated with fp16x2 atomics on both sides (grid.py:45-46 casts the table to half): two runs of
+        # the REFERENCE differ by up to 0.6 % / 1.2 % of the scale there (profiles/r2_parity_lego.json / _garden.json, ref16_run_to_run)
+        tol = 3e-2 if k == "encoder_color.embeddings" else 2e-3
+        assert (x - y).abs().max().item() <= tol * x.abs().max().item(), (k, (x - y).abs().max().item(), x.abs().max().item())
 
 
 # ------------------------------------------------------------------------------------------------
@@ -449,3 +465,39 @@ def test_checkpoint_is_accepted_by_the_reference_trainer_and_ema_matches(tmp_pat
                               **{k: v for k, v in vars(opt).items() if k not in ("bg_color", "perturb")})
     img, ws, _ = tr.render(ro.cuda(), rd.cuda(), bg_color=1.0)
     assert (img - ev["image"]).abs().max().item() <= 2e-3
+
+
+@pytest.mark.parametrize("name", ["lego", "garden"])
+def test_mark_untrained_grid_matches_reference(name):
+    """Stage0Trainer.mark_untrained_grid (one kernel, csrc/grid_aux.cu) vs the unmodified
+    NeRFRenderer.mark_untrained_grid (renderer.py:985-1071) on the same camera set; cells may differ only where a frustum plane
+    passes within fp32 rounding of the cell position (the reference's batched matmul and the kernel round differently)."""
+    import types
+    c = CASES[name]
+    ref_stage, ns = _ref_stack()
+    poses = S.orbit_cameras(23, radius=c["radius"], seed=4)
+    intr = S.lego_intrinsics()
+    cnf = None
+    if c["cam_nf"]:
+        d = poses[:, :3, 3].norm(dim=-1)
+        cnf = torch.stack([(d - 1.0).clamp(min=0.05), d + 14.0], -1)
+    opt = ref_stage.default_opt(bound=c["bound"], dt_gamma=c["dt_gamma"], adaptive_num_rays=False)
+    model = ns.make_model(opt).cuda()
+    dataset = types.SimpleNamespace(poses=poses.numpy(), intrinsics=intr)
+    if cnf is not None:
+        dataset.cam_near_far = cnf.cuda()
+    with ns.context():
+        model.mark_untrained_grid(dataset)
+    ref = model.density_grid < 0
+    cfg = Stage0Config(bound=c["bound"], dt_gamma=c["dt_gamma"], num_rays=128, max_samples=128 * 128)
+    tr = Stage0Trainer(cfg, seed=0)
+    cnt = tr.mark_untrained_grid(poses, intr, cnf)
+    ours = tr.density_grid < 0
+    assert int(cnt.item()) == int(ours.sum().item())
+    frac_marked = ref.float().mean().item()
+    assert 0.01 < frac_marked < 0.99, frac_marked
+    mism = (ours != ref).float().mean().item()
+    assert mism < 2e-5, (mism, frac_marked)
+    # every cascade has marked and unmarked cells where the reference has
+    for cas in range(ref.shape[0]):
+        assert abs(ours[cas].float().mean().item() - ref[cas].float().mean().item()) < 1e-4

@@ -215,31 +215,6 @@ def test_warp_marcher_equals_serial_marcher(name):
     assert torch.equal(s0[:M], s1[:M])
 
 
-def test_pipelined_mlp_backward_equals_single_tile_kernel():
-    """k_mlp_bwd2 (two tiles in flight, issuer warp, aliased smem) vs k_mlp_bwd: same feature gradients
-    bit for bit; weight gradients equal up to the order of the fp32 TMEM/atomic accumulation."""
-    from nerf2mesh_b200._lib import call
-    for shading in ("full", "diffuse"):
-        tr, b = make(shading, N=192)
-        stage(tr, b)
-        tr._fill_params(shading == "full", True)
-        tr.loss_acc.zero_(); tr.march(); tr.encode_fwd(); tr.mlp_fwd(); tr.composite_loss()
-        res = []
-        for mode in (0, 1):
-            call("n2m_s0_set_mlp_bwd_pipelined", mode)
-            tr.g_mlp.zero_(); tr.denc_tiles.zero_()
-            tr.mlp_bwd()
-            torch.cuda.synchronize()
-            res.append((tr.denc_tiles.clone(), tr.g_mlp.clone()))
-        call("n2m_s0_set_mlp_bwd_pipelined", 0)            # back to the default (single-tile kernel)
-        M = int(tr.counters[1].item())
-        d0, d1 = untile(res[0][0], M), untile(res[1][0], M)
-        assert torch.equal(d0, d1), (d0 - d1).abs().max()
-        assert d0.abs().max() > 0
-        g0, g1 = res[0][1], res[1][1]
-        assert (g0 - g1).abs().max().item() <= 1e-4 * g0.abs().max().item()
-
-
 @pytest.mark.parametrize("shading,n_rays,nparts", [("full", 192, 1), ("diffuse", 192, 1), ("full", 3072, 1), ("full", 3072, 2)])
 def test_fused_backward_equals_two_kernel_backward(shading, n_rays, nparts):
     """k_s0_bwd_fused (MLP backward + scatter in one warp-specialised persistent launch, feature gradients handed over in shared
@@ -261,7 +236,7 @@ def test_fused_backward_equals_two_kernel_backward(shading, n_rays, nparts):
     assert M > 128 * (148 if n_rays > 1000 else 1)
     for name in res[0]:
         a, r = res[1][name].double(), res[0][name].double()
-        assert r.abs().max().item() > 0, name
+        assert r.abs().max().item() > 0 or (shading == "diffuse" and name.startswith("specular")), name
         assert (a - r).abs().max().item() <= 1e-4 * r.abs().max().item() + 1e-12, name
     # the inf flag is raised by the fused kernel too
     tr.gtable.zero_(); tr.g_mlp.zero_()
@@ -497,102 +472,44 @@ def test_reference_state_dict_and_checkpoint_schema(tmp_path):
         assert torch.equal(v, s2[k]), k
 
 
-@pytest.mark.skipif(__import__("os").environ.get("N2M_EXPERIMENTAL") != "1",
-                    reason="experimental scatter variant, compiled but not yet validated on a GPU (set N2M_EXPERIMENTAL=1)")
-@pytest.mark.parametrize("cuts", [(10,), (5, 10, 13)])
-def test_scatter_level_passes_equal_single_pass(cuts):
-    """n2m_s0_encode_bwd_levels over disjoint level ranges covering 0..16 == the single scatter launch (same atomics, only their
-    order differs)."""
-    tr, b = make()
+def test_tv_random_point_fallback(ref_gridencoder):
+    """GridEncoder.grad_total_variation's fallback (grid.py:181-183, reached from utils.py:815-823 when a TV call gets no sample): the
+    fused path evaluates the same TV gradient at its own hash-generated points; fed to the REFERENCE kernel, those points give the same
+    gradient.  And the fallback fires exactly for the groups the TV pass counted as empty."""
+    import numpy as np
+    tr, b = make(N=96)
     stage(tr, b)
-    tr.forward_backward()
-    g_ref = tr.export_reference_grads()
-    tr.gtable.zero_(); tr.g_mlp.zero_()
-    tr.scatter_level_cuts = cuts
-    tr.forward_backward()
-    g = tr.export_reference_grads()
-    for name in g_ref:
-        a, r = g[name].double(), g_ref[name].double()
-        assert (a - r).abs().max().item() <= 1e-4 * r.abs().max().item() + 1e-12, name
-
-
-@pytest.mark.skipif(__import__("os").environ.get("N2M_EXPERIMENTAL") != "1",
-                    reason="experimental MLP-forward layout, compiled but not yet validated on a GPU (set N2M_EXPERIMENTAL=1)")
-@pytest.mark.parametrize("shading", ["full", "diffuse"])
-def test_compact_mlp_forward_equals_default(shading):
-    """n2m_s0_set_mlp_fwd_compact(1): the P1 tile aliases the dead S1 tile (3 CTAs/SM); same arithmetic => identical outputs."""
-    from nerf2mesh_b200._lib import call
-    tr, b = make(shading)
-    stage(tr, b)
-    tr._fill_params(shading == "full", True)
-    tr.march(); tr.encode_fwd(); tr.loss_acc.zero_(); tr.mlp_fwd()
+    tr.tv_fallback_points = 20000
+    tr.march()
     torch.cuda.synchronize()
-    M = int(tr.counters[1].item())
-    ref = tr.out[:M].clone(); spec = tr.loss_acc[1].item()
-    try:
-        call("n2m_s0_set_mlp_fwd_compact", 1)
-        tr.out.zero_(); tr.loss_acc.zero_()
-        tr.mlp_fwd()
-        torch.cuda.synchronize()
-        assert torch.equal(tr.out[:M], ref)
-        assert abs(tr.loss_acc[1].item() - spec) <= 1e-5 * max(abs(spec), 1e-12)
-    finally:
-        call("n2m_s0_set_mlp_fwd_compact", 0)
-
-
-@pytest.mark.skipif(__import__("os").environ.get("N2M_EXPERIMENTAL") != "1",
-                    reason="experimental level-pipelined optimizer, compiled but not yet validated on a GPU (set N2M_EXPERIMENTAL=1)")
-@pytest.mark.parametrize("nparts,use_graph", [(1, False), (2, True)])
-def test_level_pipelined_optimizer_equals_default_step(nparts, use_graph):
-    """level_pipe: scatter in two level ranges, Adam of the first range's rows under the scatter of the second
-    (n2m_s0_adam_tables_range).  Same arithmetic per row => same parameters after a few steps, up to the fp32 order of the atomics."""
-    res = []
-    for pipe in (False, True):
-        tr, b = make(seed=4)
-        tr.nparts = nparts
-        if pipe:
-            tr.scatter_level_cuts = (10,)
-            tr.level_pipe = True
-        losses = []
-        for it in range(3):
-            tr.step(b["ro"], b["rd"], b["gt"], b["bg"], b["noises"], use_graph=use_graph)
-            losses.append(tr.read_loss())
-        torch.cuda.synchronize()
-        st = tr.export_reference_state()
-        res.append((losses, {k: v.clone() for k, v in st.items() if v.is_floating_point()}, tr.opt_state.clone(),
-                    tr.gtable.abs().max().item(), tr.g_mlp.abs().max().item()))
-    (l0, s0, o0, gz0, gm0), (l1, s1, o1, gz1, gm1) = res
-    assert gz1 == 0 and gm1 == 0                                   # both ranges zeroed their gradient rows
-    assert torch.equal(o0, o1)                                     # step count, loss scale, growth tracker
-    assert np.allclose(l0, l1, rtol=1e-4), (l0, l1)
-    for k in s0:
-        moved = (s0[k] - s0[k].mean()).abs().max().item()
-        assert (s0[k] - s1[k]).abs().max().item() <= 2e-3 * max(moved, 1e-6) + 1e-7, k
-
-
-@pytest.mark.skipif(__import__("os").environ.get("N2M_EXPERIMENTAL") != "1",
-                    reason="experimental two-issuer MLP backward, compiled but not yet validated on a GPU (set N2M_EXPERIMENTAL=1)")
-def test_two_issuer_mlp_backward_equals_single_tile_kernel():
-    """k_mlp_bwd2<2> (one issuing warp per tile group, weight-gradient accumulators zeroed with tcgen05.st and shared by both
-    issuers) vs k_mlp_bwd: same feature gradients bit for bit, weight gradients up to fp32 accumulation order."""
-    from nerf2mesh_b200._lib import call
-    try:
-        for shading in ("full", "diffuse"):
-            tr, b = make(shading, N=192)
-            stage(tr, b)
-            tr._fill_params(shading == "full", True)
-            tr.loss_acc.zero_(); tr.march(); tr.encode_fwd(); tr.mlp_fwd(); tr.composite_loss()
-            res = []
-            for pipelined, issuers in ((0, 1), (1, 2)):
-                call("n2m_s0_set_mlp_bwd_pipelined", pipelined); call("n2m_s0_set_mlp_bwd_issuers", issuers)
-                tr.g_mlp.zero_(); tr.denc_tiles.zero_()
-                tr.mlp_bwd()
-                torch.cuda.synchronize()
-                res.append((tr.denc_tiles.clone(), tr.g_mlp.clone()))
-            M = int(tr.counters[1].item())
-            d0, d1 = untile(res[0][0], M), untile(res[1][0], M)
-            assert torch.equal(d0, d1), (d0 - d1).abs().max()
-            g0, g1 = res[0][1], res[1][1]
-            assert (g0 - g1).abs().max().item() <= 1e-4 * g0.abs().max().item()
-    finally:
-        call("n2m_s0_set_mlp_bwd_pipelined", 0); call("n2m_s0_set_mlp_bwd_issuers", 1)
+    pts = torch.zeros(tr.tv_fallback_points, 3, device="cuda")
+    tr.gtable.zero_()
+    tr.tv_random(dump=pts)                      # test hook: unconditional, weight lambda_tv
+    torch.cuda.synchronize()
+    assert pts.min().item() >= 0 and pts.max().item() < 1 and abs(pts.mean().item() - 0.5) < 0.01
+    ours = tr.export_reference_grads()["encoder.embeddings"]
+    st = tr.export_reference_state()
+    emb = st["encoder.embeddings"].contiguous()
+    grad = torch.zeros_like(emb)
+    S_ = float(np.log2(tr.cfg.per_level_scale))
+    ref_gridencoder.grad_total_variation(pts, emb, grad, tr.offsets, tr.cfg.lambda_tv, pts.shape[0], 3, 1, 16, S_, 16, 0, False)
+    torch.cuda.synchronize()
+    scale = grad.abs().max().item()
+    assert scale > 0
+    assert (ours - grad).abs().max().item() <= 1e-4 * scale, ((ours - grad).abs().max().item(), scale)
+    # a new point set every optimizer step
+    pts2 = torch.zeros_like(pts)
+    tr.opt_state[2] += 1
+    tr.tv_random(dump=pts2)
+    assert not torch.equal(pts, pts2)
+    # bound 1, samples present: the single TV call is populated -> no fallback
+    tr.gtable.zero_()
+    tr.tv()
+    base = tr.gtable.clone()
+    assert tr.counters[3].item() == tr.counters[1].item() and tr.counters[15].item() == 0
+    tr.gtable.zero_(); tr.counters[3] = 0            # pretend the batch marched nothing: the fallback adds its gradient
+    tr.tv_random()
+    assert tr.gtable[:, 0].abs().max().item() > 0 and base[:, 0].abs().max().item() > 0
+    tr.gtable.zero_(); tr.counters[3] = 5
+    tr.tv_random()
+    assert tr.gtable.abs().max().item() == 0

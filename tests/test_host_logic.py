@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def declared_symbols():
     names = []
-    for h in ("n2m_b200.h", "n2m_b200_fused.h"):
+    for h in ("n2m_b200.h", "n2m_b200_fused.h", "n2m_b200_raster.h"):
         src = open(os.path.join(ROOT, "include", h)).read()
         src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
         names += re.findall(r"\b(n2m_[a-zA-Z0-9_]+)\s*\(", src)
@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_bindings_cover_the_headers():
-    from nerf2mesh_b200 import _lib, parallel, sampler, stage0  # noqa: F401  (register the fused / data-parallel signatures)
+    from nerf2mesh_b200 import _lib, parallel, raster, sampler, stage0, stage1  # noqa: F401  (register the fused / data-parallel signatures)
     bound = set(_lib.SIGNATURES) | {"n2m_last_error", "n2m_version", "n2m_launch_count", "n2m_s0_wpack_bytes",
                                    "n2m_s0_mlp_param_count", "n2m_s0_init", "n2m_dp_ctx_bytes"}
     assert set(declared_symbols()) <= bound, set(declared_symbols()) - bound
@@ -125,9 +125,8 @@ def test_peer_adam_slices_cover_rows_and_stay_aligned():
 
 
 def test_step_orchestration_call_sequence(monkeypatch):
-    """Stage0Trainer's per-step orchestration (ray-range parts, TV fork, split optimizer, experimental level pipeline) with the CUDA
-    layer mocked out: the sequence of C-ABI calls on every path, no GPU needed.  Guards the host logic that the GPU tests only
-    exercise on a B200."""
+    """Stage0Trainer's per-step orchestration (ray-range parts, TV fork, split optimizer, fused backward) with the CUDA layer mocked
+    out: the sequence of C-ABI calls on every path, no GPU needed.  Guards the host logic that the GPU tests only exercise on a B200."""
     import types
     import nerf2mesh_b200.stage0 as S0
 
@@ -161,21 +160,20 @@ def test_step_orchestration_call_sequence(monkeypatch):
 
     tr = object.__new__(S0.Stage0Trainer)
     tr.cfg = types.SimpleNamespace(lambda_tv=1e-8, eps=1e-15, num_levels=16)
-    slot = types.SimpleNamespace(**{k: T() for k in ("rays_o", "rays_d", "gt", "bg", "noises", "rays", "counters", "tbuf", "recs")}, has_alpha=True)
+    slot = types.SimpleNamespace(**{k: T() for k in ("rays_o", "rays_d", "gt", "bg", "noises", "rays", "counters", "tbuf", "recs", "cam_nf")}, has_alpha=True)
     tr.slots, tr.cur = [slot, slot], 0
     for k in ("table", "offsets", "enc_tiles", "opt_state", "wpack", "out", "dout", "image", "weights_sum", "depth", "denc_tiles",
               "color_master", "gtable", "m_table", "v_table", "mlp", "g_mlp", "m_mlp", "v_mlp", "loss_acc"):
         setattr(tr, k, T())
     tr.gtables, tr.g_mlps = [tr.gtable], [tr.g_mlp]
     tr.params = S0.S0Params(); tr.Mcap, tr.N, tr.rows, tr.parity, tr.device = 128, 4, 160, 0, "cpu"
-    tr._tv_overlap, tr._tv_stream, tr._part_streams, tr.part_mode = True, None, [], "chains"
-    tr._mlp_stream = tr._adam_stream = None
-    tr.level_pipe, tr._ev_first_pass, tr.scatter_level_cuts = False, [], ()
-    tr.l2_persist_mb, tr._l2_granted = 0, None
-    tr._offsets_host = list(range(0, 170, 10))
-    tr.fused_bwd = False
+    tr._tv_overlap, tr._tv_stream, tr._part_streams = True, None, []
+    tr._adam_stream = None
+    tr.fused_bwd, tr.tv_fallback_points, tr._graphs = False, 1000, {}
 
+    tv = ["n2m_s0_tv", "n2m_s0_tv_random"]
     chain = ["n2m_s0_encode_fwd_part", "n2m_s0_mlp_fwd_part", "n2m_s0_composite_loss_part", "n2m_s0_mlp_bwd_part", "n2m_s0_encode_bwd_part"]
+    fchain = chain[:3] + ["n2m_s0_bwd_fused_part"]
     adam = ["n2m_s0_adam_head", "n2m_s0_adam_mlp", "n2m_s0_adam_tables", "n2m_s0_adam_post"]
 
     def names():
@@ -183,55 +181,32 @@ def test_step_orchestration_call_sequence(monkeypatch):
 
     tr.nparts = 1
     tr._compute_then_adam()
-    assert names() == [chain[0], "n2m_s0_tv"] + chain[1:] + adam
-    # default: MLP backward + scatter as ONE launch (csrc/fused.cu)
-    calls.clear(); tr.fused_bwd = True
-    tr._compute_then_adam()
-    assert names() == [chain[0], "n2m_s0_tv"] + chain[1:3] + ["n2m_s0_bwd_fused_part"] + adam
-    calls.clear(); tr.nparts = 2
-    tr._compute_then_adam()
-    assert names() == ["n2m_s0_tv"] + (chain[:3] + ["n2m_s0_bwd_fused_part"]) * 2 + adam
-    tr.fused_bwd, tr.nparts = False, 1
-    calls.clear()
-    tr._compute_then_adam()
+    assert names() == [chain[0]] + tv + chain[1:] + adam
     for P_ in (2, 4):
         calls.clear(); tr.nparts = P_
         tr._compute_then_adam()
-        assert names() == ["n2m_s0_tv"] + chain * P_ + adam
+        assert names() == tv + chain * P_ + adam
         parts = [a[-3:-1] for n, a in calls if n == "n2m_s0_mlp_bwd_part"]
         assert parts == [(k, P_) for k in range(P_)]
-    calls.clear(); tr.nparts, tr.part_mode = 2, "pipeline"
+    # MLP backward + scatter as ONE launch (csrc/fused.cu)
+    calls.clear(); tr.fused_bwd, tr.nparts = True, 1
     tr._compute_then_adam()
-    assert names() == [chain[0], *chain[1:4], chain[0], *chain[1:4], "n2m_s0_tv", chain[4], chain[4]] + adam
-    # experimental level pipeline: two scatter passes per part, optimizer of the first range before the second range's rows
-    calls.clear(); tr.part_mode, tr.level_pipe, tr.scatter_level_cuts = "chains", True, (10,)
+    assert names() == [chain[0]] + tv + fchain[1:] + adam
+    calls.clear(); tr.nparts = 2
     tr._compute_then_adam()
-    lv = [(a[-5], a[-4], a[-3], a[-2]) for n, a in calls if n == "n2m_s0_encode_bwd_levels"]
-    assert lv == [(0, 2, 0, 10), (0, 2, 10, 16), (1, 2, 0, 10), (1, 2, 10, 16)]
-    rng = [(a[6], a[7]) for n, a in calls if n == "n2m_s0_adam_tables_range"]
-    assert rng == [(0, 100), (100, 160)]
-    assert names()[-5:] == ["n2m_s0_adam_head", "n2m_s0_adam_tables_range", "n2m_s0_adam_mlp", "n2m_s0_adam_tables_range", "n2m_s0_adam_post"]
-
-
-def test_l2_window_bookkeeping(monkeypatch):
-    """experimental L2 residency hook: window = gradient rows of the active level range, hit ratio = granted carve-out / window,
-    switched off after the last pass (mocked CUDA layer)."""
-    import types
-    import nerf2mesh_b200.stage0 as S0
-    calls = []
-    monkeypatch.setattr(S0, "call", lambda name, *a: calls.append((name, a)))
-    monkeypatch.setattr(S0, "stream", lambda: 7)
-    tr = object.__new__(S0.Stage0Trainer)
-    tr.l2_persist_mb, tr._l2_granted, tr.parity, tr.rows = 64, 1000, 0, 160
-    tr.gtables = [types.SimpleNamespace(data_ptr=lambda: 4096)]
-    tr._l2_window_rows(0, 100)
-    tr._l2_window_rows(100, 160)
-    tr._l2_window_rows(0, 0)
-    (n0, a0), (n1, a1), (n2, a2) = calls
-    assert n0 == n1 == n2 == "n2m_l2_window" and a0[0] == 7
-    assert (a0[1].value, a0[2], round(a0[3], 6)) == (4096, 1600, 0.625)
-    assert (a1[1].value, a1[2], a1[3]) == (4096 + 1600, 960, 1.0)
-    assert a2[1] is None and a2[2] == 0
-    tr.l2_persist_mb = 0; calls.clear()
-    tr._l2_window_rows(0, 100)
-    assert calls == []
+    assert names() == tv + fchain * 2 + adam
+    # TV inside the scatter kernel (tv mode 0): no TV launch, the fallback probe follows the scatter; not available with the fused backward
+    calls.clear(); tr.fused_bwd, tr.nparts = False, 1
+    tr.tv_overlap = False
+    assert names() == ["n2m_s0_set_tv_mode"]
+    calls.clear()
+    tr._compute_then_adam()
+    assert names() == chain + ["n2m_s0_tv_random"] + adam
+    tr.fused_bwd = True
+    import pytest
+    with pytest.raises(RuntimeError):
+        tr._compute()
+    # lambda_tv == 0: no TV work at all
+    calls.clear(); tr.fused_bwd = False; tr.cfg.lambda_tv = 0.0
+    tr._compute_then_adam()
+    assert names() == chain + adam
