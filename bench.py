@@ -29,7 +29,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 NUM_RAYS = 4096
-ALG_BYTES = {"encode_fwd": 1053, "encode_bwd": 1024, "bwd_fused": 1024, "step": 2077}      # SURVEY.md section 8(d), bytes per sample
+ALG_BYTES = {"encode_fwd": 1053, "fwd_fused": 1053, "encode_bwd": 1024, "bwd_fused": 1024, "step": 2077}      # SURVEY.md section 8(d), bytes per sample
 
 WORKLOADS = {
     # BASELINE config 2: lego recipe (readme.md:64): bound 1, dt_gamma 0, RGBA targets + mask loss, TV 1e-8
@@ -363,6 +363,50 @@ def psnr_leg(iters, eval_res=100, eval_views=2, seed=0):
         return {"unavailable": repr(e)[:300]}
 
 
+def dp_divergence_check(workload, mode, rank, world, rays=512, steps=4):
+    """N > 1: the fused data-parallel optimizer actually used (`mode`: nvls / peer) against the library baseline (NCCL all-reduce +
+    replicated Adam) on small identical replicas: after `steps` steps every rank must hold bit-identical parameters, and they must agree
+    with the NCCL path up to the summation order of the reduction."""
+    import torch.distributed as dist
+    from nerf2mesh_b200 import synthetic as S
+    from nerf2mesh_b200.parallel import GradSync, make_grad_sync
+    from nerf2mesh_b200.stage0 import Stage0Config, Stage0Trainer
+    if mode == "nccl":
+        return {"mode": "nccl", "note": "library path in use; nothing to compare"}
+    w = WORKLOADS[workload]
+    grid, bits, bricks = scene(workload)
+    g = torch.Generator().manual_seed(77 + rank)
+    poses = S.orbit_cameras(100, radius=w["radius"] or S.LEGO_RADIUS, seed=0)
+    ro, rd, _, _ = S.sample_rays(poses, S.lego_intrinsics(), 800, 800, rays, g)
+    gt = S.render_bricks(ro, rd, bricks)
+    if not w["alpha"]:
+        gt = (gt[:, :3] * gt[:, 3:] + (1 - gt[:, 3:])).contiguous()
+    bg = torch.rand(rays, 3, generator=g); noises = torch.rand(rays, generator=g)
+    res = {}
+    for which in (mode, "nccl"):
+        cfg = Stage0Config(bound=w["bound"], dt_gamma=w["dt_gamma"], lambda_entropy=w["lambda_entropy"], num_rays=rays, max_samples=rays * 1024)
+        t = Stage0Trainer(cfg, seed=0)
+        t.set_occupancy(bits, grid)
+        sync = GradSync(t) if which == "nccl" else make_grad_sync(t, which)[0]
+        for it in range(steps):
+            t.step(ro, rd, gt, bg, noises, grad_sync=sync, use_graph=False)
+        torch.cuda.synchronize()
+        st = t.export_reference_state()
+        res[which] = torch.cat([st[k].reshape(-1) for k in ("encoder.embeddings", "encoder_color.embeddings", "color_net.net.0.weight", "sigma_net.net.0.weight")])
+        del t, sync
+        torch.cuda.empty_cache()
+        dist.barrier()
+    mine = res[mode]
+    ref0 = mine.clone()
+    dist.broadcast(ref0, src=0)
+    spread = (mine - ref0).abs().max().reshape(1)
+    dist.all_reduce(spread, op=dist.ReduceOp.MAX)
+    moved = (res["nccl"] - res["nccl"].mean()).abs().max().item()
+    return {"mode": mode, "steps": steps, "rays_per_rank": rays, "replicas_bit_identical": bool(spread.item() == 0.0),
+            "max_abs_diff_vs_nccl": (mine - res["nccl"]).abs().max().item(), "param_spread": moved,
+            "rel_diff_vs_nccl": (mine - res["nccl"]).abs().max().item() / max(moved, 1e-12)}
+
+
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
@@ -377,28 +421,18 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from nerf2mesh_b200 import _lib
-    from nerf2mesh_b200.parallel import GradSync, PeerAdam
 
     workload = args.workload
     tr = make_trainer(workload)
     tr.nparts = args.parts
     tr.fused_bwd = bool(args.fused_bwd)
-    sync = None
-    dp_used = args.dp
+    tr.fused_fwd = bool(args.fused_fwd)
+    if tr.fused_fwd:
+        tr.nparts = 1
+    sync, dp_used = None, args.dp
     if world > 1:
-        if args.dp == "peer":
-            # all ranks must agree on the path: fall back to the NCCL all-reduce if any rank cannot map its peers
-            ok = torch.ones(1, device="cuda")
-            try:
-                sync = PeerAdam(tr)
-            except Exception as e:      # noqa: BLE001
-                print(f"[rank {rank}] PeerAdam unavailable ({e}); falling back to NCCL all-reduce", file=sys.stderr)
-                ok.zero_()
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-            if ok.item() == 0:
-                sync, dp_used = None, "nccl"
-        if sync is None:
-            sync = GradSync(tr)
+        from nerf2mesh_b200.parallel import make_grad_sync
+        sync, dp_used = make_grad_sync(tr, args.dp)
     n_batches = 8
     host_batches, grid, bits = make_batches(n_batches, 1000 + rank, True, workload)
     dev_batches = [{k: v.cuda(non_blocking=True) for k, v in b.items()} for b in host_batches]
@@ -482,7 +516,8 @@ def run_ours(args):
     # ---- per-stage device times (eager, CUDA events on the launching stream, L2 flushed before each) -> roofline ----
     tr.drop_prefetch()
     torch.cuda.synchronize()
-    stages = ["march", "encode_fwd", "tv", "mlp_fwd", "composite_loss"] + (["bwd_fused"] if tr.fused_bwd else ["mlp_bwd", "encode_bwd"]) + ["adam"]
+    stages = ["march"] + (["fwd_fused", "tv"] if tr.fused_fwd else ["encode_fwd", "tv", "mlp_fwd"]) + ["composite_loss"] + \
+             (["bwd_fused"] if tr.fused_bwd else ["mlp_bwd", "encode_bwd"]) + ["adam"]
     acc = {s: 0.0 for s in stages}
     reps = 5
     flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda")     # > 126 MB L2
@@ -508,15 +543,19 @@ def run_ours(args):
             upd_ms += a.elapsed_time(z) / 2
     tr.set_occupancy(keep_bits, keep_grid)
     peak, peak_kind = load_peaks()
-    dom = max(("encode_fwd", "bwd_fused" if tr.fused_bwd else "encode_bwd"), key=lambda s: acc[s])
+    dom = max(("fwd_fused" if tr.fused_fwd else "encode_fwd", "bwd_fused" if tr.fused_bwd else "encode_bwd"), key=lambda s: acc[s])
     achieved = ALG_BYTES[dom] * M_last / (acc[dom] * 1e-3) / 1e9
-    kname = {"encode_fwd": "k_s0_encode_fwd", "encode_bwd": "k_s0_encode_bwd", "bwd_fused": "k_s0_bwd_fused"}[dom]
+    kname = {"encode_fwd": "k_s0_encode_fwd", "encode_bwd": "k_s0_encode_bwd", "bwd_fused": "k_s0_bwd_fused", "fwd_fused": "k_s0_fwd_fused"}[dom]
     traffic = ncu_traffic(kname)
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None if traffic is None else traffic["bytes"],
                 "traffic_capture": None if traffic is None else traffic["capture"], "alg_bytes_per_sample": ALG_BYTES[dom],
                 "samples_per_launch": M_last, "kernel_ms": acc[dom], "stage_ms_cold_l2": {k: round(v, 4) for k, v in acc.items()},
                 "step_frac_of_hbm": ALG_BYTES["step"] * value / 1e9 / peak}
+
+    dp_check = None
+    if world > 1:
+        dp_check = dp_divergence_check(workload, dp_used, rank, world)
 
     if rank == 0:
         cpu = None
@@ -537,7 +576,7 @@ def run_ours(args):
                 "data": "synthetic",
                 "config": {"workload": workload, "rays_per_batch": NUM_RAYS, "global_rays": NUM_RAYS * world,
                            "samples_per_step": samples_total / K, "parallelism": f"dp{world}" + ("" if world == 1 else f"-{dp_used}"),
-                           "cuda_graph": not args.no_graph, "ray_range_parts": args.parts, "fused_bwd": bool(tr.fused_bwd),
+                           "cuda_graph": not args.no_graph, "ray_range_parts": int(tr.nparts), "fused_bwd": bool(tr.fused_bwd), "fused_fwd": bool(tr.fused_fwd),
                            "march_prefetch": not args.no_prefetch, **{k: v for k, v in WORKLOADS[workload].items() if k != "cap"},
                            "sample_capacity": tr.Mcap, "capacity_overflow_steps": overflow_steps, "max_samples_seen": max_m,
                            "l2": "inputs cycle over 8 batches; tables+grads+Adam state (0.6 GB touched per step) exceed the 126 MB L2"},
@@ -548,7 +587,7 @@ def run_ours(args):
                 "roofline": roofline, "cpu_baseline": cpu,
                 "density_update": {"ms_per_call": upd_ms, "every_steps": 16, "cells": int(tr.density_grid.numel()),
                                    "value_with_update": samples_total / K / ((step_ms + upd_ms / 16) * 1e-3)},
-                "reference_cuda": refc, "psnr": ps}
+                "reference_cuda": refc, "psnr": ps, "dp_check": dp_check}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -634,11 +673,13 @@ def main():
     ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="--impl reference: wall-clock budget of the whole CPU run")
     ap.add_argument("--skip-reference", action="store_true", help="skip the same-box reference-CUDA leg")
     ap.add_argument("--psnr-iters", type=int, default=300, help="training steps of the PSNR-vs-reference pair (0 = skip)")
+    ap.add_argument("--fused-fwd", type=int, default=0, help="1: gather + MLP forward as one warp-specialised launch (implies --parts 1)")
     ap.add_argument("--fused-bwd", type=int, default=0, help="1: MLP backward + scatter as one warp-specialised launch (csrc/fused.cu)")
     ap.add_argument("--parts", type=int, default=2, choices=[1, 2, 4, 8],
                     help="ray-range parts run as concurrent gather->MLP->composite->MLP'->scatter chains on forked streams")
-    ap.add_argument("--dp", default="peer", choices=["peer", "nccl"],
-                    help="N > 1: 'peer' = fused reduce-scatter+Adam+all-gather over NVLink peer memory, 'nccl' = all-reduce + replicated Adam")
+    ap.add_argument("--dp", default="auto", choices=["auto", "nvls", "peer", "nccl"],
+                    help="N > 1: 'nvls' = reduce-scatter inside the NVSwitch (multimem) + sharded Adam + multicast all-gather, 'peer' = the "
+                         "same with P2P loads / stores over NVLink, 'nccl' = all-reduce + replicated Adam, 'auto' = first that sets up")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

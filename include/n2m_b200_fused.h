@@ -233,6 +233,14 @@ int n2m_s0_adam_mlp(float* mlp_params, float* g_mlp, float* m_mlp, float* v_mlp,
                     n2m_stream_t stream);
 int n2m_s0_adam_post(float* opt_state, n2m_stream_t stream);
 
+/* Fused forward (csrc/fused.cu): hash-grid gather + MLP forward of the WHOLE batch (nparts == 1) in one persistent, warp-specialised
+ * launch -- two gather groups of four warps fill double-buffered tile images in shared memory, warps 0-3 run the tensor-core MLP rounds on
+ * them; a copy of every image is stored to enc_tiles by the TMA unit for the backward pass.  Same arithmetic as n2m_s0_encode_fwd followed
+ * by n2m_s0_mlp_fwd (bit-identical enc_tiles / out). */
+int n2m_s0_fwd_fused(const n2m_s0_params* p, const void* recs, const int32_t* counters, uint32_t Mcap, const float* rays_o,
+                     const float* rays_d, const void* table, const int32_t* offsets, const void* wpack, void* enc_tiles, void* out,
+                     float* spec_sq_sum, n2m_stream_t stream);
+
 /* EMA of the parameters = torch_ema.ExponentialMovingAverage as the reference's Trainer holds it (nerf/utils.py:544-545, decay 0.95
  * from main.py:241): `update` once per EPOCH (utils.py:1213-1214), parameters swapped with the shadow for evaluation
  * (utils.py:1250-1252,1340-1341) and for the 'best' checkpoint (utils.py:1389-1401).  shadow_density [rows] f32, shadow_color [rows] float2,
@@ -262,6 +270,13 @@ int n2m_dp_barrier(const void* ctx, n2m_stream_t stream);
 int n2m_dp_adam(const void* ctx, uint32_t parity, uint32_t world, uint32_t rows, uint32_t n_mlp, void* color_master_slice,
                 float* m_slice, float* v_slice, float* mlp_params, float* m_mlp, float* v_mlp, void* wpack,
                 void* gtab_next, float* gmlp_next, float* opt_state, float eps, n2m_stream_t stream);
+
+/* NVLS variant: the table gradients are reduced INSIDE the NVSwitch (multimem.ld_reduce on a multicast address that maps the gradient
+ * table of every rank) and the refreshed 8-byte entries are broadcast with one multimem.st; mc_gtab / mc_table are the multicast addresses
+ * (torch.distributed._symmetric_memory) of this parity's gradient table and of the working table.  Everything else as n2m_dp_adam. */
+int n2m_dp_adam_nvls(const void* ctx, const void* mc_gtab, void* mc_table, uint32_t parity, uint32_t world, uint32_t rows, uint32_t n_mlp,
+                     void* color_master_slice, float* m_slice, float* v_slice, float* mlp_params, float* m_mlp, float* v_mlp, void* wpack,
+                     void* gtab_next, float* gmlp_next, float* opt_state, float eps, n2m_stream_t stream);
 
 #ifdef __cplusplus
 }

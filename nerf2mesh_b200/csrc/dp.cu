@@ -151,6 +151,71 @@ k_dp_adam_tables(const DpCtx* __restrict__ ctx, uint32_t parity, float2* __restr
     }
 }
 
+// ---- NVLS variant: the same reduce-scatter + Adam + all-gather with the reduction done INSIDE the NVSwitch -----------------------
+// `mc_gtab` / `mc_table` are multicast addresses (one virtual address mapped onto the same buffer of every rank, created by
+// torch.distributed._symmetric_memory): multimem.ld_reduce returns the sum of the W ranks' copies of a 16-byte row in one load -- the
+// switch adds them, each GPU's link carries 1/W of the traffic of the peer-load version -- and multimem.st stores the refreshed 8-byte
+// table entry into all W tables with one store.  NVLink bytes per rank per step: 16 B x rows / W in, 8 B x rows / W out, instead of
+// (W-1)/W x 16 B x rows in and (W-1)/W x 8 B x rows out.
+__device__ __forceinline__ float4 mc_ld_reduce_add(const float4* mc) {
+    float4 r;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(mc) : "memory");
+    return r;
+}
+__device__ __forceinline__ void mc_st_entry(TableEntry* mc, TableEntry e) {
+    const float lo = e.d, hi = __uint_as_float(*reinterpret_cast<const uint32_t*>(&e.c));
+    asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" :: "l"(mc), "f"(lo), "f"(hi) : "memory");
+}
+
+constexpr int kMcRowsPerThread = 4;
+
+__global__ void __launch_bounds__(256)
+k_dp_adam_tables_mc(const DpCtx* __restrict__ ctx, const float4* __restrict__ mc_gtab, TableEntry* __restrict__ mc_table,
+                    float2* __restrict__ cmaster, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ st, float eps) {
+    const uint32_t W = ctx->world, r = ctx->rank, rows = ctx->rows;
+    const uint32_t per = slice_rows(rows, W);
+    const uint32_t lo = min(rows, r * per), hi = min(rows, lo + per);
+    const bool skip = st[3] != 0.f;
+    const float inv = st[7];
+    const float lr1 = __fdiv_rn(st[4], st[5]), bc2s = st[6];
+    float2* mc_p = reinterpret_cast<float2*>(m + per);
+    float2* vc_p = reinterpret_cast<float2*>(v + per);
+    const uint32_t i0 = lo + blockIdx.x * (256 * kMcRowsPerThread) + threadIdx.x;
+    float4 g[kMcRowsPerThread]; float md[kMcRowsPerThread], vd[kMcRowsPerThread];
+    float2 mcv[kMcRowsPerThread], vcv[kMcRowsPerThread], pc[kMcRowsPerThread];
+    TableEntry e[kMcRowsPerThread];
+#pragma unroll
+    for (int j = 0; j < kMcRowsPerThread; ++j) {          // all loads first: the in-switch reductions and the local state stream together
+        const uint32_t i = i0 + j * 256;
+        if (i < hi) {
+            g[j] = mc_ld_reduce_add(mc_gtab + i);
+            if (!skip) {
+                const uint32_t k = i - lo;
+                md[j] = m[k]; vd[j] = v[k]; mcv[j] = mc_p[k]; vcv[j] = vc_p[k]; e[j] = ctx->table[r][i]; pc[j] = cmaster[k];
+            }
+        }
+    }
+    if (skip) return;
+#pragma unroll
+    for (int j = 0; j < kMcRowsPerThread; ++j) {
+        const uint32_t i = i0 + j * 256;
+        if (i >= hi) continue;
+        const uint32_t k = i - lo;
+        const float gx = g[j].x * inv, gy = g[j].y * inv, gz = g[j].z * inv;
+        if (gx == 0.f && gy == 0.f && gz == 0.f && md[j] == 0.f && vd[j] == 0.f && mcv[j].x == 0.f && mcv[j].y == 0.f && vcv[j].x == 0.f &&
+            vcv[j].y == 0.f)
+            continue;
+        e[j].d = adam_update(e[j].d, gx, md[j], vd[j], lr1, bc2s, eps);
+        pc[j].x = adam_update(pc[j].x, gy, mcv[j].x, vcv[j].x, lr1, bc2s, eps);
+        pc[j].y = adam_update(pc[j].y, gz, mcv[j].y, vcv[j].y, lr1, bc2s, eps);
+        e[j].c = __floats2half2_rn(pc[j].x, pc[j].y);
+        cmaster[k] = pc[j];
+        m[k] = md[j]; v[k] = vd[j]; mc_p[k] = mcv[j]; vc_p[k] = vcv[j];
+        mc_st_entry(mc_table + i, e[j]);                                            // all-gather: one multicast store
+    }
+}
+
 // zero the local gradient buffers of the next parity (full size, local HBM only)
 __global__ void __launch_bounds__(256)
 k_dp_zero(float4* __restrict__ gtab, uint32_t rows, float* __restrict__ gmlp, uint32_t n_mlp) {
@@ -254,11 +319,32 @@ int n2m_dp_barrier(const void* ctx, n2m_stream_t stream) {
     return check_launch("dp_barrier");
 }
 
+static int dp_adam_impl(const void* ctx, const void* mc_gtab, void* mc_table, uint32_t parity, uint32_t world, uint32_t rows, uint32_t n_mlp,
+                        void* color_master_slice, float* m_slice, float* v_slice, float* mlp_params, float* m_mlp, float* v_mlp, void* wpack,
+                        void* gtab_next, float* gmlp_next, float* opt_state, float eps, n2m_stream_t stream);
+
 /* barrier -> [found_inf OR, step constants] -> reduce-scatter + Adam + all-gather (tables) -> MLP -> repack ->
  * zero next-parity gradients -> scaler update -> barrier.   m/v/color_master are SLICE-sized (ceil(rows/world) rows). */
 int n2m_dp_adam(const void* ctx, uint32_t parity, uint32_t world, uint32_t rows, uint32_t n_mlp, void* color_master_slice,
                 float* m_slice, float* v_slice, float* mlp_params, float* m_mlp, float* v_mlp, void* wpack,
                 void* gtab_next, float* gmlp_next, float* opt_state, float eps, n2m_stream_t stream) {
+    return dp_adam_impl(ctx, nullptr, nullptr, parity, world, rows, n_mlp, color_master_slice, m_slice, v_slice, mlp_params, m_mlp, v_mlp, wpack,
+                        gtab_next, gmlp_next, opt_state, eps, stream);
+}
+
+/* the same with the table reduce / broadcast through NVSwitch multicast (NVLS): mc_gtab = multicast address of THIS parity's gradient
+ * table, mc_table = multicast address of the working table (both mapped on every rank's buffer) */
+int n2m_dp_adam_nvls(const void* ctx, const void* mc_gtab, void* mc_table, uint32_t parity, uint32_t world, uint32_t rows, uint32_t n_mlp,
+                     void* color_master_slice, float* m_slice, float* v_slice, float* mlp_params, float* m_mlp, float* v_mlp, void* wpack,
+                     void* gtab_next, float* gmlp_next, float* opt_state, float eps, n2m_stream_t stream) {
+    N2M_REQUIRE(mc_gtab && mc_table, "dp_adam_nvls", "null multicast pointer");
+    return dp_adam_impl(ctx, mc_gtab, mc_table, parity, world, rows, n_mlp, color_master_slice, m_slice, v_slice, mlp_params, m_mlp, v_mlp, wpack,
+                        gtab_next, gmlp_next, opt_state, eps, stream);
+}
+
+static int dp_adam_impl(const void* ctx, const void* mc_gtab, void* mc_table, uint32_t parity, uint32_t world, uint32_t rows, uint32_t n_mlp,
+                        void* color_master_slice, float* m_slice, float* v_slice, float* mlp_params, float* m_mlp, float* v_mlp, void* wpack,
+                        void* gtab_next, float* gmlp_next, float* opt_state, float eps, n2m_stream_t stream) {
     N2M_REQUIRE(ctx && color_master_slice && m_slice && v_slice && mlp_params && m_mlp && v_mlp && wpack && gtab_next && gmlp_next && opt_state,
                 "dp_adam", "null pointer");
     cudaStream_t st = as_stream(stream);
@@ -270,6 +356,10 @@ int n2m_dp_adam(const void* ctx, uint32_t parity, uint32_t world, uint32_t rows,
     k_dp_prep<<<1, 32, 0, st>>>(c, parity, opt_state);
     if (int e = check_launch("dp_adam(prep)")) return e;
     const uint32_t per = slice_rows(rows, world);
+    if (mc_gtab)
+        k_dp_adam_tables_mc<<<div_up(per, 256u * kMcRowsPerThread), 256, 0, st>>>(c, static_cast<const float4*>(mc_gtab), static_cast<TableEntry*>(mc_table),
+                                                                                  static_cast<float2*>(color_master_slice), m_slice, v_slice, opt_state, eps);
+    else
     k_dp_adam_tables<<<div_up(per, 256u * kRowsPerThread), 256, 0, st>>>(c, parity, static_cast<float2*>(color_master_slice), m_slice, v_slice,
                                                                        opt_state, eps);
     if (int e = check_launch("dp_adam(tables)")) return e;

@@ -22,8 +22,11 @@ namespace n2m {
 namespace {
 
 constexpr uint32_t kMlpThreads = 128, kScatWarps = 16, kFusedThreads = kMlpThreads + 32 * kScatWarps;     // 640
-// register budget (setmaxnreg, multiples of 8): 128 x kMlpRegs + 512 x kScatRegs <= 65536
-constexpr uint32_t kMlpRegs = 200, kScatRegs = 72;
+// register budget (setmaxnreg, multiples of 8).  The kernel starts with 96 registers per thread; setmaxnreg.inc can only take what
+// setmaxnreg.dec of the other warps returned to the CTA pool: 512 x (96 - 72) = 12 288 >= 128 x (184 - 96) = 11 264.  (200 for the
+// MLP warps asked for more than the pool held: the inc never completed and the hand-over barriers timed out.)
+constexpr uint32_t kMlpRegs = 184, kScatRegs = 72;
+static_assert(kScatWarps * 32 * (96 - kScatRegs) >= kMlpThreads * (kMlpRegs - 96), "setmaxnreg.inc must fit in what setmaxnreg.dec releases");
 constexpr uint32_t D_CHUNKS = 7;                          // gradient columns 0..55 (cols 3..50 are used)
 constexpr uint32_t D_BYTES = D_CHUNKS * kChunk;           // 14336
 constexpr uint32_t FB_DENC = B_BYTES;
@@ -474,6 +477,189 @@ k_s0_bwd_fused(n2m_s0_params p, const uint8_t* __restrict__ enc_tiles, const flo
     if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
+
+// ================================================================================================================================
+// k_s0_fwd_fused: hash-grid gather + the three MLPs' forward in ONE persistent kernel (north_star's "fused march+encode+MLP"; the march
+// itself stays a separate, prefetched launch: it does not depend on the parameters and runs under the previous step).
+//   warps 0-3   : the MLP forward of k_mlp_fwd on the tile image in shared memory (thread = sample, thread 0 issues the tcgen05.mma rounds),
+//   warps 4-7   : gather group 0, warps 8-11: gather group 1.  A group gathers one 128-sample tile (thread = sample, all 16 levels: the
+//                 code of the stand-alone gather), writes the UMMA-layout rows straight into ITS shared-memory buffer -- the image never
+//                 makes the HBM round trip -- and has the TMA unit store a copy to `enc_tiles` for the backward pass (cp.async.bulk
+//                 shared -> global, 16 KiB per instruction).
+// Two CTAs per SM (86 KB of shared memory, 128 TMEM columns, 85 registers each): 16 gather warps per SM keep the L1 / L2 gather pipe
+// busy while two tensor-core chains run underneath.  Whole-batch only (nparts == 1): the bulk store writes complete tiles.
+// ================================================================================================================================
+constexpr uint32_t kFwdThreads = 384;
+constexpr uint32_t FF_W = 0, FF_A0 = FF_W + W_BYTES, FF_A1 = FF_A0 + kTileBytes, FF_H = FF_A1 + kTileBytes, FF_S1 = FF_H + kTileBytes,
+                   FF_AS2 = FF_S1 + 8192, FF_BYTES = FF_AS2 + 4096;          // 86,528 B
+
+__device__ __forceinline__ void bar_group(uint32_t g) {          // named barriers 2 / 3 (immediate ids: a register id makes ptxas reserve all 16)
+    if (g == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
+    else asm volatile("bar.sync 3, 128;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(kFwdThreads, 2)
+k_s0_fwd_fused(n2m_s0_params p, const float4* __restrict__ recs, const int32_t* __restrict__ counters, const float* __restrict__ rays_o,
+               const float* __restrict__ rays_d, const TableEntry* __restrict__ table, const int32_t* __restrict__ offsets,
+               const uint8_t* __restrict__ wpack, uint8_t* __restrict__ enc_tiles, float4* __restrict__ out, float* __restrict__ spec_sq_sum) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar_mma, bar_full[2], bar_empty[2];
+    __shared__ uint32_t tmem_s;
+    __shared__ float red[4];
+    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    const PartRange pr = part_range(counters, 0, 1);
+    const uint32_t t1 = (pr.hi + kTile - 1) / kTile;
+    if (pr.hi == 0 || blockIdx.x >= t1) return;
+    const uint32_t my_tiles = (t1 - blockIdx.x + gridDim.x - 1) / gridDim.x;        // tiles blockIdx.x, + gridDim.x, ...
+
+    if (tid == 0) {
+        tc::mbar_init(&bar_mma, 1);
+        tc::mbar_init(&bar_full[0], 1); tc::mbar_init(&bar_full[1], 1);
+        tc::mbar_init(&bar_empty[0], 1); tc::mbar_init(&bar_empty[1], 1);
+        tc::mbar_init_fence();
+    }
+    if (warp == 0) tc::tmem_alloc(&tmem_s, 128);
+    for (uint32_t i = tid; i < W_BYTES / 16; i += kFwdThreads)
+        reinterpret_cast<uint4*>(smem + FF_W)[i] = __ldg(reinterpret_cast<const uint4*>(wpack) + i);
+    if (tid < 128) *reinterpret_cast<uint4*>(smem + FF_AS2 + kChunk + tid * 16) = make_uint4(0, 0, 0, 0);     // second K chunk of the specular input: zero
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+
+    if (warp >= 4) {
+        // =========================================== gather groups ===========================================
+        const uint32_t g = (warp - 4) >> 2, r = tid - 128 - g * 128;
+        uint8_t* buf = smem + (g ? FF_A1 : FF_A0);
+        uint32_t k = 0;
+        for (uint32_t it = g; it < my_tiles; it += 2, ++k) {
+            const uint32_t tile = blockIdx.x + it * gridDim.x;
+            float feat[kTileCols];
+            encode_fwd_features<false>(p, recs, rays_o, rays_d, table, offsets, pr, tile * kTile + r, feat);
+            // the buffer is free once the TMA store of its previous image has read it and the MLP warps are done with that tile
+            if (r == 0) {
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                tc::mbar_wait(&bar_empty[g], (k & 1) ^ 1);
+            }
+            bar_group(g);
+            store_tile_row(buf, r, feat);
+            tc::fence_async_smem();                  // generic-proxy writes -> visible to the tensor core and to the bulk copy engine
+            bar_group(g);
+            if (r == 0) {
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             :: "l"(enc_tiles + (size_t)tile * kTileBytes), "r"(tc::smem_u32(buf)), "r"(kTileBytes) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                mbar_arrive1(&bar_full[g]);
+            }
+        }
+        if (r == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");        // the last stores complete before the CTA exits
+    } else {
+        // =========================================== MLP warps (k_mlp_fwd) ===========================================
+        const uint32_t tmem = tmem_s, D0 = tmem, D1 = tmem + 64;
+        const uint32_t lane_t = (warp * 32u) << 16;
+        uint32_t ph_mma = 0;
+        float spec_sq = 0.f;
+        uint8_t* sW = smem + FF_W; uint8_t* sH = smem + FF_H; uint8_t* sS1 = smem + FF_S1; uint8_t* sP1 = smem + FF_S1;
+        uint8_t* sAs2 = smem + FF_AS2;
+        const tc::OpDesc dA0 = tc::make_opdesc(opK(smem + FF_A0, 128)), dA1 = tc::make_opdesc(opK(smem + FF_A1, 128)),
+                         dH = tc::make_opdesc(opK(sH, 128)), dS1 = tc::make_opdesc(opK(sS1, 128)), dP1 = tc::make_opdesc(opK(sP1, 128)),
+                         dAs2 = tc::make_opdesc(opK(sAs2, 128));
+        const tc::OpDesc wC1 = tc::make_opdesc(opK(sW + W_C1, 64)), wC2 = tc::make_opdesc(opK(sW + W_C2, 64)),
+                         wC3 = tc::make_opdesc(opK(sW + W_C3, 16)), wS1 = tc::make_opdesc(opK(sW + W_S1, 32)),
+                         wS2 = tc::make_opdesc(opK(sW + W_S2, 16)), wP1 = tc::make_opdesc(opK(sW + W_P1, 32)),
+                         wP2 = tc::make_opdesc(opK(sW + W_P2, 16));
+        for (uint32_t it = 0; it < my_tiles; ++it) {
+            const uint32_t tile = blockIdx.x + it * gridDim.x, g = it & 1;
+            const uint8_t* sA = smem + (g ? FF_A1 : FF_A0);
+            const tc::OpDesc& dA = g ? dA1 : dA0;
+            tc::mbar_wait(&bar_full[g], (it >> 1) & 1);
+            tc::fence_after_sync();
+            // round 1: first layers of color_net and sigma_net
+            if (tid == 0) {
+                tc::gemm_issue_fast<64, 4, false, false>(D0, dA, wC1, false);
+                tc::gemm_issue_fast<32, 4, false, false>(D1, dA, wS1, false);
+                tc::mma_commit(&bar_mma);
+            }
+            tc::mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1; tc::fence_after_sync();
+            epi_store_row<64, true>(D0 + lane_t, sH, tid, nullptr);
+            epi_store_row<32, true>(D1 + lane_t, sS1, tid, nullptr);
+            sync_mlp();
+            // round 2: color_net.1, sigma_net.1
+            if (tid == 0) {
+                tc::gemm_issue_fast<64, 4, false, false>(D0, dH, wC2, false);
+                tc::gemm_issue_fast<16, 2, false, false>(D1, dS1, wS2, false);
+                tc::mma_commit(&bar_mma);
+            }
+            tc::mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1; tc::fence_after_sync();
+            float sigma;
+            {
+                float v[8];
+                tc::tmem_ld8(D1 + lane_t, v);
+                sigma = __expf(round_h(v[0]));                 // trunc_exp forward (activation.py:5-11)
+            }
+            epi_store_row<64, true>(D0 + lane_t, sH, tid, nullptr);
+            sync_mlp();
+            // round 3: color_net.2
+            if (tid == 0) {
+                tc::gemm_issue_fast<16, 4, false, false>(D0, dH, wC3, false);
+                tc::mma_commit(&bar_mma);
+            }
+            tc::mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1; tc::fence_after_sync();
+            float feat[6];
+            {
+                float v[8];
+                tc::tmem_ld8(D0 + lane_t, v);
+#pragma unroll
+                for (int i = 0; i < 6; ++i) feat[i] = sigmoid_h(v[i]);
+            }
+            float cr = feat[0], cg = feat[1], cb = feat[2];
+            float sp[3] = {0.f, 0.f, 0.f};
+            if (p.shading_full) {
+                const uint4 dq = *reinterpret_cast<const uint4*>(sA + 6 * kChunk + tid * 16);
+                const __half2 d01 = *reinterpret_cast<const __half2*>(&dq.y);
+                const __half2 d23 = *reinterpret_cast<const __half2*>(&dq.z);
+                const float in[8] = {__high2float(d01), __low2float(d23), __high2float(d23), feat[3], feat[4], feat[5], 0.f, 0.f};
+                store_chunk(sAs2, 0, tid, in);
+                sync_mlp();
+                if (tid == 0) {
+                    tc::gemm_issue_fast<32, 1, false, false>(D1, dAs2, wP1, false);
+                    tc::mma_commit(&bar_mma);
+                }
+                tc::mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1; tc::fence_after_sync();
+                epi_store_row<32, true>(D1 + lane_t, sP1, tid, nullptr);
+                sync_mlp();
+                if (tid == 0) {
+                    tc::gemm_issue_fast<16, 2, false, false>(D0, dP1, wP2, false);
+                    tc::mma_commit(&bar_mma);
+                }
+                tc::mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1; tc::fence_after_sync();
+                float v[8];
+                tc::tmem_ld8(D0 + lane_t, v);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) sp[i] = sigmoid_h(v[i]);
+                cr = fminf(fmaxf(round_h(sp[0] + cr), 0.f), 1.f);
+                cg = fminf(fmaxf(round_h(sp[1] + cg), 0.f), 1.f);
+                cb = fminf(fmaxf(round_h(sp[2] + cb), 0.f), 1.f);
+            }
+            const uint32_t j = tile * kTile + tid;
+            if (j < pr.hi) {
+                out[j] = make_float4(sigma, cr, cg, cb);
+                spec_sq += sp[0] * sp[0] + sp[1] * sp[1] + sp[2] * sp[2];
+            }
+            sync_mlp();                                   // every read of this tile's image / TMEM columns is done
+            if (tid == 0) mbar_arrive1(&bar_empty[g]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) spec_sq += __shfl_xor_sync(0xffffffffu, spec_sq, o);
+        if ((tid & 31) == 0) red[warp] = spec_sq;
+        bar_mlp();
+        if (tid == 0 && spec_sq_sum) atomicAdd(spec_sq_sum, red[0] + red[1] + red[2] + red[3]);
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_s, 128);
+}
+
 }  // namespace
 }  // namespace n2m
 
@@ -495,6 +681,7 @@ int n2m_s0_set_fused_debug(int mode) { g_fused_dbg = (uint32_t)mode; return 0; }
 
 int n2m_s0_fused_init(void) {
     cudaError_t e = cudaFuncSetAttribute(k_s0_bwd_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FB_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_s0_fwd_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FF_BYTES);
     if (e != cudaSuccess) return fail("s0_fused_init", cudaGetErrorString(e));
     fused_num_sms();
     return 0;
@@ -515,6 +702,22 @@ int n2m_s0_bwd_fused_part(const n2m_s0_params* p, const void* enc_tiles, const v
         *p, static_cast<const uint8_t*>(enc_tiles), static_cast<const float4*>(dout), static_cast<const float4*>(recs), counters,
         rays_o, rays_d, static_cast<const uint8_t*>(wpack), offsets, static_cast<float4*>(gtable), g_mlp, loss_scale, part, nparts, g_fused_dbg);
     return check_launch("s0_bwd_fused");
+}
+
+/* hash-grid gather + MLP forward of the WHOLE batch in one persistent launch (replaces n2m_s0_encode_fwd followed by n2m_s0_mlp_fwd):
+ * the tile images go from the gather warps to the tensor core through shared memory; a copy is stored to enc_tiles (TMA bulk store) for
+ * the backward pass */
+int n2m_s0_fwd_fused(const n2m_s0_params* p, const void* recs, const int32_t* counters, uint32_t Mcap, const float* rays_o,
+                     const float* rays_d, const void* table, const int32_t* offsets, const void* wpack, void* enc_tiles, void* out,
+                     float* spec_sq_sum, n2m_stream_t stream) {
+    N2M_REQUIRE(p && recs && counters && rays_o && rays_d && table && offsets && wpack && enc_tiles && out, "s0_fwd_fused", "null pointer");
+    N2M_REQUIRE(p->num_levels == kLevels, "s0_fwd_fused", "fused path supports num_levels == 16");
+    N2M_REQUIRE(Mcap % kTile == 0 && Mcap > 0, "s0_fwd_fused", "Mcap must be a positive multiple of 128");
+    const uint32_t grid = min(Mcap / kTile, (uint32_t)(2 * fused_num_sms()));
+    k_s0_fwd_fused<<<grid, kFwdThreads, FF_BYTES, as_stream(stream)>>>(
+        *p, static_cast<const float4*>(recs), counters, rays_o, rays_d, static_cast<const TableEntry*>(table), offsets,
+        static_cast<const uint8_t*>(wpack), static_cast<uint8_t*>(enc_tiles), static_cast<float4*>(out), spec_sq_sum);
+    return check_launch("s0_fwd_fused");
 }
 
 }  // extern "C"

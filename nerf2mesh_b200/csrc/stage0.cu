@@ -224,69 +224,10 @@ encode_fwd_tile(const n2m_s0_params& p, const float4* __restrict__ recs,
                 const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                 const TableEntry* __restrict__ table, const int32_t* __restrict__ offsets,
                 uint8_t* __restrict__ enc_tiles, const PartRange pr, uint32_t nparts, uint32_t tile) {
-    const uint32_t r = threadIdx.x;
-    const uint32_t j = tile * kTile + r;
     float feat[kTileCols];
-#pragma unroll
-    for (uint32_t i = 0; i < kTileCols; ++i) feat[i] = 0.f;
-
-    Sample s;
-    const bool own = j >= pr.lo && j < pr.hi;        // rows of a boundary tile outside [lo, hi) belong to another part
-    bool active = own;
-    if (own) {
-        if (POINTS) {
-            s.x = rays_o[3 * j]; s.y = rays_o[3 * j + 1]; s.z = rays_o[3 * j + 2];
-            s.u = __fmul_rn(__fadd_rn(s.x, p.grid_bound), p.inv_2gb);
-            s.v = __fmul_rn(__fadd_rn(s.y, p.grid_bound), p.inv_2gb);
-            s.w = __fmul_rn(__fadd_rn(s.z, p.grid_bound), p.inv_2gb);
-            s.dx = rays_d ? rays_d[3 * j] : 0.f; s.dy = rays_d ? rays_d[3 * j + 1] : 0.f; s.dz = rays_d ? rays_d[3 * j + 2] : 1.f;
-        } else
-        s = sample_of(recs[j], rays_o, rays_d, p);
-        feat[kColXyz] = s.x; feat[kColXyz + 1] = s.y; feat[kColXyz + 2] = s.z;
-        // safe_normalize (utils.py:41-42): d / sqrt(clamp(sum d^2, 1e-20))
-        const float n2 = __fadd_rn(__fadd_rn(__fmul_rn(s.dx, s.dx), __fmul_rn(s.dy, s.dy)), __fmul_rn(s.dz, s.dz));
-        const float nrm = __fsqrt_rn(fmaxf(n2, 1e-20f));
-        feat[kColDir] = __fdiv_rn(s.dx, nrm); feat[kColDir + 1] = __fdiv_rn(s.dy, nrm); feat[kColDir + 2] = __fdiv_rn(s.dz, nrm);
-        active = !((s.u < 0 || s.u > 1) || (s.v < 0 || s.v > 1) || (s.w < 0 || s.w > 1));
-    } else {
-        s.x = s.y = s.z = s.u = s.v = s.w = 0.5f; s.dx = s.dy = s.dz = 0.f;
-    }
-
-#pragma unroll
-    for (uint32_t l = 0; l < kLevels; ++l) {
-        const LevelGeom g = level_geom(offsets, l, p.S, p.base_res);
-        Corners c; uint32_t base[3]; bool hashed;
-        corners_of(g, s.u, s.v, s.w, c, base, hashed, nullptr);
-        const TableEntry* tab = table + g.row0;
-        if (active) {
-            uint2 raw[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) raw[k] = __ldg(reinterpret_cast<const uint2*>(tab + c.row[k]));
-            float d = 0.f, c0 = 0.f, c1 = 0.f;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const float2 cc = __half22float2(*reinterpret_cast<const __half2*>(&raw[k].y));
-                d += c.w[k] * __uint_as_float(raw[k].x);
-                c0 += c.w[k] * cc.x;
-                c1 += c.w[k] * cc.y;
-            }
-            feat[kColDens + l] = d;
-            feat[kColColor + 2 * l] = c0;
-            feat[kColColor + 2 * l + 1] = c1;
-        }
-    }
-    // write this row of the tile image: 8 chunks of 16 bytes, each chunk 2 KiB apart
+    const bool own = encode_fwd_features<POINTS>(p, recs, rays_o, rays_d, table, offsets, pr, tile * kTile + threadIdx.x, feat);
     if (nparts > 1 && !own) return;                  // (whole-batch mode also zero-fills the rows past M of the last tile)
-    uint8_t* img = enc_tiles + (size_t)tile * kTileBytes + r * 16;
-#pragma unroll
-    for (uint32_t ch = 0; ch < 8; ++ch) {
-        uint4 q;
-        q.x = pack2(feat[8 * ch + 0], feat[8 * ch + 1]);
-        q.y = pack2(feat[8 * ch + 2], feat[8 * ch + 3]);
-        q.z = pack2(feat[8 * ch + 4], feat[8 * ch + 5]);
-        q.w = pack2(feat[8 * ch + 6], feat[8 * ch + 7]);
-        *reinterpret_cast<uint4*>(img + ch * kChunkBytes) = q;
-    }
+    store_tile_row(enc_tiles + (size_t)tile * kTileBytes, threadIdx.x, feat);
 }
 
 // one block per 128-sample tile of the part's range [lo, hi) (grid-stride, so any grid size is correct: the host sizes

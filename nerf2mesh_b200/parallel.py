@@ -50,6 +50,7 @@ _lib.register({
     "n2m_dp_ctx_fill": [P, U, U, U, U, P, P, P, P, P, P, P, P],
     "n2m_dp_barrier": [P, P],
     "n2m_dp_adam": [P, U, U, U, U, P, P, P, P, P, P, P, P, P, P, F, P],
+    "n2m_dp_adam_nvls": [P, P, P, U, U, U, U, P, P, P, P, P, P, P, P, P, P, F, P],
 })
 _lib.lib.n2m_dp_ctx_bytes.restype = ctypes.c_uint32
 
@@ -152,3 +153,105 @@ class PeerAdam:
         parts = [torch.zeros_like(self.cm) for _ in range(self.world)]
         dist.all_gather(parts, self.cm, group=self.group)
         return torch.cat(parts)[: self.t.rows]
+
+
+class NvlsAdam(PeerAdam):
+    """PeerAdam with the gradient reduce-scatter done INSIDE the NVSwitch and the table all-gather as multicast stores
+    (csrc/dp.cu k_dp_adam_tables_mc: multimem.ld_reduce / multimem.st on multicast addresses).  The buffers the peers touch (both
+    gradient-table parities, the working table, the MLP gradient vectors, the barrier flags) are re-allocated as
+    torch.distributed._symmetric_memory tensors -- PyTorch does the VMM / multicast-object plumbing, the data path is this repo's
+    kernel.  Raises when the fabric / driver offers no multicast (callers fall back to PeerAdam, then to NCCL)."""
+
+    def __init__(self, trainer, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        t = self.t = trainer
+        self.group = group
+        pg = group if group is not None else dist.group.WORLD
+        self.world = W = dist.get_world_size(group)
+        self.rank = r = dist.get_rank(group)
+        assert W <= 8, "one NVSwitch domain"
+        dev = t.device
+        R = t.rows
+        self.per = per = slice_rows(R, W)
+        lo, hi = min(R, r * per), min(R, (r + 1) * per)
+        try:
+            symm_mem.enable_symm_mem_for_group(pg.group_name)
+        except Exception:      # noqa: BLE001  (newer torch enables it implicitly)
+            pass
+
+        def sym(src):
+            buf = symm_mem.empty(tuple(src.shape), dtype=src.dtype, device=dev)
+            buf.copy_(src)
+            return buf, symm_mem.rendezvous(buf, pg)
+
+        gt0, h_gt0 = sym(t.gtable)
+        gt1, h_gt1 = sym(torch.zeros_like(t.gtable))
+        table, h_tab = sym(t.table)
+        gm0, h_gm0 = sym(t.g_mlp)
+        gm1, h_gm1 = sym(torch.zeros_like(t.g_mlp))
+        flags, h_fl = sym(torch.zeros(16, dtype=torch.int32, device=dev))
+        mc = [int(h_gt0.multicast_ptr), int(h_gt1.multicast_ptr), int(h_tab.multicast_ptr)]
+        if not all(mc):
+            raise RuntimeError("symmetric memory without multicast support (no NVLS on this fabric / driver)")
+        self.mc_gtab, self.mc_table = mc[:2], mc[2]
+        self._handles = (h_gt0, h_gt1, h_tab, h_gm0, h_gm1, h_fl)
+        # the trainer now works on the symmetric buffers
+        t.gtable, t.gtables, t.table = gt0, [gt0, gt1], table
+        t.g_mlp, t.g_mlps = gm0, [gm0, gm1]
+        t._graphs = {}
+        self.flags = flags
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.cm = torch.zeros(per, 2, device=dev)
+        self.cm[: hi - lo].copy_(t.color_master[lo:hi])
+        self.m = torch.zeros(per * 3, device=dev)
+        self.v = torch.zeros(per * 3, device=dev)
+
+        def arr(vals):
+            a = (ctypes.c_void_p * W)(*[int(v) for v in vals])
+            return ctypes.cast(a, ctypes.c_void_p), a
+
+        keep, args = [], []
+        for h in (h_gt0, h_gt1, h_tab, h_gm0, h_gm1):
+            c, a = arr(list(h.buffer_ptrs)); keep.append(a); args.append(c)
+        c, a = arr([t.opt_state.data_ptr()] * W); keep.append(a); args.append(c)          # peers never read opt_state (found_inf goes through the flags)
+        c, a = arr(list(h_fl.buffer_ptrs)); keep.append(a); args.append(c)
+        nbytes = int(_lib.lib.n2m_dp_ctx_bytes())
+        host = ctypes.create_string_buffer(nbytes)
+        call("n2m_dp_ctx_fill", ctypes.cast(host, ctypes.c_void_p), W, r, R, t.n_mlp, *args, ptr(self.epoch))
+        self.ctx = torch.frombuffer(bytearray(host.raw), dtype=torch.uint8).to(dev)
+        torch.cuda.synchronize()
+        dist.barrier(group=group)
+        t._color_master_provider = self.gather_color_master
+
+    def run(self, parity):
+        t = self.t
+        nxt = parity ^ 1
+        call("n2m_dp_adam_nvls", ptr(self.ctx), ctypes.c_void_p(self.mc_gtab[parity]), ctypes.c_void_p(self.mc_table), parity, self.world,
+             t.rows, t.n_mlp, ptr(self.cm), ptr(self.m), ptr(self.v), ptr(t.mlp), ptr(t.m_mlp), ptr(t.v_mlp), ptr(t.wpack),
+             ptr(t.gtables[nxt]), ptr(t.g_mlps[nxt]), ptr(t.opt_state), t.cfg.eps, stream())
+
+    def nvlink_bytes_per_step(self):
+        return int(self.per * (16 + 8) + (self.world - 1) * self.t.n_mlp * 4)
+
+
+def make_grad_sync(trainer, mode="auto", group=None):
+    """Data-parallel optimizer for `trainer`: 'nvls' (in-switch reduce), 'peer' (P2P loads over NVLink), 'nccl' (all-reduce + replicated
+    Adam) or 'auto' = the first of those that every rank can set up.  Collective: all ranks must call it with the same mode.
+    Returns (sync, mode_used)."""
+    order = {"auto": ["nvls", "peer", "nccl"], "nvls": ["nvls", "peer", "nccl"], "peer": ["peer", "nccl"], "nccl": ["nccl"]}[mode]
+    for m in order:
+        if m == "nccl":
+            return GradSync(trainer, group), "nccl"
+        ok = torch.ones(1, device=trainer.device)
+        sync = None
+        try:
+            sync = NvlsAdam(trainer, group) if m == "nvls" else PeerAdam(trainer, group)
+        except Exception as e:      # noqa: BLE001
+            import sys
+            print(f"[rank {dist.get_rank(group)}] {m} data-parallel optimizer unavailable ({str(e)[:200]})", file=sys.stderr)
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if ok.item() == 1:
+            return sync, m
+        del sync
+    raise RuntimeError("unreachable")

@@ -67,6 +67,7 @@ _lib.register({
     "n2m_s0_fused_init": [],
     "n2m_s0_set_fused_debug": [I],
     "n2m_s0_bwd_fused_part": [PP, P, P, P, P, U, P, P, P, P, P, P, P, U, U, P],
+    "n2m_s0_fwd_fused": [PP, P, P, U, P, P, P, P, P, P, P, P, P],
     "n2m_s0_ema_update": [P, P, P, P, P, P, U, F, P],
     "n2m_s0_ema_swap": [P, P, P, P, P, P, U, P, P],
 })
@@ -191,6 +192,7 @@ class Stage0Trainer:
         self.params = S0Params()
         self._fill_params(shading_full=True, gt_has_alpha=True)
         self.fused_bwd = False              # True: MLP backward + scatter as one warp-specialised launch (csrc/fused.cu)
+        self.fused_fwd = False              # True: gather + MLP forward as one warp-specialised launch (whole batch: needs nparts == 1)
         self.use_cam_near_far = False       # clamp (near, far) with the per-ray values in the slot's cam_nf (--enable_cam_near_far)
         self._tv_overlap = True             # TV gradient as its own launch overlapped with the MLP kernels (tv mode 2)
         self._tv_stream = None
@@ -428,6 +430,10 @@ class Stage0Trainer:
         call("n2m_s0_mlp_bwd_part", self._pp(), ptr(self.enc_tiles), ptr(self.dout), ptr(self.counters), self.Mcap, ptr(self.wpack),
              ptr(self.denc_tiles), ptr(self.g_mlps[self.parity]), ptr(self.opt_state), part, nparts, stream())
 
+    def fwd_fused(self):
+        call("n2m_s0_fwd_fused", self._pp(), ptr(self.recs), ptr(self.counters), self.Mcap, ptr(self.rays_o), ptr(self.rays_d),
+             ptr(self.table), ptr(self.offsets), ptr(self.wpack), ptr(self.enc_tiles), ptr(self.out), self.loss_acc.data_ptr() + 4, stream())
+
     def bwd_fused(self, part=0, nparts=1):
         call("n2m_s0_bwd_fused_part", self._pp(), ptr(self.enc_tiles), ptr(self.dout), ptr(self.recs), ptr(self.counters), self.Mcap,
              ptr(self.rays_o), ptr(self.rays_d), ptr(self.wpack), ptr(self.offsets), ptr(self.gtables[self.parity]),
@@ -507,10 +513,16 @@ class Stage0Trainer:
                 with torch.cuda.stream(self._tv_stream):
                     self.tv()
 
+        if self.fused_fwd and P_ > 1:
+            raise RuntimeError("fused_fwd works on the whole batch: set nparts = 1")
         if P_ <= 1:
-            self.encode_fwd()
-            launch_tv()
-            self.mlp_fwd()
+            if self.fused_fwd:
+                launch_tv()
+                self.fwd_fused()
+            else:
+                self.encode_fwd()
+                launch_tv()
+                self.mlp_fwd()
             self.composite_loss()
             self._backward(0, 1)
         else:
@@ -553,7 +565,7 @@ class Stage0Trainer:
             key = (name, self.parity)
         else:
             key = (name, self.cur, self.parity, int(self.params.shading_full), int(self.params.gt_has_alpha), int(self.nparts),
-                   bool(self.tv_overlap), bool(self.fused_bwd), int(self.tv_fallback_points))
+                   bool(self.tv_overlap), bool(self.fused_bwd), bool(self.fused_fwd), int(self.tv_fallback_points))
         g = self._graphs.get(key)
         if g is None:
             g = torch.cuda.CUDAGraph()

@@ -1,5 +1,5 @@
 """Turns the ncu artefacts of a gpurun call into the markdown tables of profiles/*_ncu_summary.md:
-    python profiles/summarize_ncu.py <launches.csv> <full.ncu-rep>
+    python profiles/summarize_ncu.py <launches.csv> <full.ncu-rep> [<capture note>]      # with the note: also writes profiles/ncu_traffic.json
 (launch list: `--metrics gpu__time_duration.sum`; full capture: `--set full`, read back with `ncu -i ... --page raw --csv`)."""
 import csv, io, re, subprocess, sys
 from collections import OrderedDict
@@ -83,3 +83,10 @@ if __name__ == "__main__":
         print("| metric | " + " | ".join(f"`{k}`" for k in keys) + " |\n|---|" + "---|" * len(keys))
         for lab in labels:
             print(f"| {lab} | " + " | ".join(f"{res[k].get(lab, float('nan')):.4g}" for k in keys) + " |")
+        if len(sys.argv) > 3:
+            # profiles/ncu_traffic.json: DRAM bytes per launch of every captured kernel, read by bench.py (`roofline.traffic`)
+            import json, os
+            out = {"capture": os.path.basename(sys.argv[2]) + " (" + sys.argv[3] + ")",
+                   "kernels": {k: {"dram_bytes": (v.get("DRAM rd MB", 0.0) + v.get("DRAM wr MB", 0.0)) * 1e6, "dur_us": v.get("dur us")} for k, v in res.items()}}
+            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "ncu_traffic.json"), "w") as f:
+                json.dump(out, f, indent=1)

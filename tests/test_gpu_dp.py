@@ -1,6 +1,7 @@
-"""GPU, >= 2 devices: the fused reduce-scatter + Adam + all-gather over NVLink peer memory (csrc/dp.cu,
-parallel.PeerAdam) against the library baseline (NCCL all-reduce + replicated Adam, parallel.GradSync):
-same parameters after several steps on every rank, ranks bit-identical among themselves."""
+"""GPU, >= 2 devices: the fused reduce-scatter + Adam + all-gather over NVLink peer memory (csrc/dp.cu, parallel.PeerAdam) and its
+NVLS variant (in-switch reduction with multimem.ld_reduce, multicast all-gather; parallel.NvlsAdam, skipped where the fabric offers no
+multicast) against the library baseline (NCCL all-reduce + replicated Adam, parallel.GradSync): same parameters after several steps
+on every rank, ranks bit-identical among themselves."""
 import os
 import socket
 
@@ -21,7 +22,7 @@ def _worker(rank, world, port, q):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     import cases
     from nerf2mesh_b200 import synthetic as S
-    from nerf2mesh_b200.parallel import GradSync, PeerAdam
+    from nerf2mesh_b200.parallel import GradSync, NvlsAdam, PeerAdam
     from nerf2mesh_b200.stage0 import Stage0Config, Stage0Trainer
     N = 128
     grid, bits, bricks = S.occupancy_regime("converged")
@@ -30,10 +31,22 @@ def _worker(rank, world, port, q):
     g = torch.Generator().manual_seed(rank)
     bg = torch.rand(N, 3, generator=g); noises = torch.rand(N, generator=g)
     out = {}
-    for mode in ("nccl", "peer"):
+    for mode in ("nccl", "peer", "nvls"):
         tr = Stage0Trainer(Stage0Config(bound=1.0, num_rays=N, max_samples=N * 256), seed=0)     # identical replicas
         tr.set_occupancy(bits, grid)
-        sync = GradSync(tr) if mode == "nccl" else PeerAdam(tr)
+        if mode == "nvls":
+            ok = torch.ones(1, device="cuda")
+            try:
+                sync = NvlsAdam(tr)
+            except Exception as e:      # noqa: BLE001
+                out["nvls_unavailable"] = repr(e)[:200]
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if ok.item() == 0:
+                out.setdefault("nvls_unavailable", "a peer could not set it up")
+                continue
+        else:
+            sync = GradSync(tr) if mode == "nccl" else PeerAdam(tr)
         for it in range(4):
             tr.step(ro, rd, gt, bg, noises, grad_sync=sync, use_graph=(it > 0))
         torch.cuda.synchronize()
@@ -56,11 +69,15 @@ def test_peer_adam_matches_nccl_allreduce_world2():
     res = dict(q.get(timeout=600) for _ in range(2))
     [p.join(120) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
-    for name in res[0]["peer"]:
-        a0, a1 = res[0]["peer"][name], res[1]["peer"][name]
-        assert torch.equal(a0, a1), f"ranks diverged on {name}"
-        b0 = res[0]["nccl"][name]
-        d = (a0 - b0).abs().max().item()
-        moved = (b0 - b0.mean()).abs().max().item()
-        assert d <= 2e-3 * max(moved, 1e-6) + 1e-7, f"{name}: peer vs nccl differ by {d}"
-    assert abs(res[0]["peer_loss"] - res[0]["nccl_loss"]) <= 1e-3 * abs(res[0]["nccl_loss"])
+    modes = ["peer"] + (["nvls"] if "nvls" in res[0] else [])
+    for mode in modes:
+        for name in res[0][mode]:
+            a0, a1 = res[0][mode][name], res[1][mode][name]
+            assert torch.equal(a0, a1), f"{mode}: ranks diverged on {name}"
+            b0 = res[0]["nccl"][name]
+            d = (a0 - b0).abs().max().item()
+            moved = (b0 - b0.mean()).abs().max().item()
+            assert d <= 2e-3 * max(moved, 1e-6) + 1e-7, f"{name}: {mode} vs nccl differ by {d}"
+        assert abs(res[0][mode + "_loss"] - res[0]["nccl_loss"]) <= 1e-3 * abs(res[0]["nccl_loss"])
+    if "nvls" not in res[0]:
+        print("NVLS path not exercised:", res[0].get("nvls_unavailable"))

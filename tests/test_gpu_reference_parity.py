@@ -36,6 +36,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CASES = {
     "lego": dict(bound=1.0, dt_gamma=0.0, lambda_entropy=0.0, radius=S.LEGO_RADIUS, alpha=True, cam_nf=False, cap=160),
     "garden": dict(bound=16.0, dt_gamma=1.0 / 256, lambda_entropy=1e-3, radius=1.2, alpha=False, cam_nf=True, cap=256),
+    "garden_notv": dict(bound=16.0, dt_gamma=1.0 / 256, lambda_entropy=1e-3, radius=1.2, alpha=False, cam_nf=True, cap=256, lambda_tv=0.0),
 }
 
 
@@ -74,7 +75,8 @@ def _cam_nf(c, ro):
 
 
 def _make_ours(c, bits, grid):
-    cfg = Stage0Config(bound=c["bound"], dt_gamma=c["dt_gamma"], num_rays=N, max_samples=N * c["cap"], lambda_entropy=c["lambda_entropy"])
+    cfg = Stage0Config(bound=c["bound"], dt_gamma=c["dt_gamma"], num_rays=N, max_samples=N * c["cap"], lambda_entropy=c["lambda_entropy"],
+                       lambda_tv=c.get("lambda_tv", 1e-8))
     tr = Stage0Trainer(cfg, seed=3)
     tr.set_occupancy(bits, grid)
     tr.use_cam_near_far = c["cam_nf"]
@@ -94,7 +96,7 @@ def _warm_up(tr, c, bricks, steps=40):
 
 def _ref_trainer(ref_stage, ns, c, state, fp16, loss_scale=None):
     opt = ref_stage.default_opt(bound=c["bound"], dt_gamma=c["dt_gamma"], lambda_entropy=c["lambda_entropy"], fp16=fp16,
-                                adaptive_num_rays=False, num_rays=N, enable_cam_near_far=c["cam_nf"])
+                                adaptive_num_rays=False, num_rays=N, enable_cam_near_far=c["cam_nf"], lambda_tv=c.get("lambda_tv", 1e-8))
     model = ns.make_model(opt)
     model.load_state_dict({k: v.clone() for k, v in state.items()}, strict=True)       # the complete key set, strict
     model.cuda().train()
@@ -163,7 +165,7 @@ def _cmp(a, r):
                 cos=(torch.dot(a, r) / (a.norm() * r.norm() + 1e-300)).item(), scale=scale)
 
 
-@pytest.mark.parametrize("name", ["lego", "garden"])
+@pytest.mark.parametrize("name", ["lego", "garden", "garden_notv"])
 def test_fused_step_matches_reference_cuda_path(name):
     c = CASES[name]
     ref_stage, ns = _ref_stack()
@@ -495,7 +497,8 @@ def test_mark_untrained_grid_matches_reference(name):
     ours = tr.density_grid < 0
     assert int(cnt.item()) == int(ours.sum().item())
     frac_marked = ref.float().mean().item()
-    assert 0.01 < frac_marked < 0.99, frac_marked
+    if c["bound"] > 1:          # (orbit cameras looking at the origin see every cell of the bound-1 cube: nothing is marked there)
+        assert 0.01 < frac_marked < 0.99, frac_marked
     mism = (ours != ref).float().mean().item()
     assert mism < 2e-5, (mism, frac_marked)
     # every cascade has marked and unmarked cells where the reference has

@@ -513,3 +513,41 @@ def test_tv_random_point_fallback(ref_gridencoder):
     tr.gtable.zero_(); tr.counters[3] = 5
     tr.tv_random()
     assert tr.gtable.abs().max().item() == 0
+
+
+@pytest.mark.parametrize("shading,n_rays", [("full", 96), ("diffuse", 96), ("full", 4096)])
+def test_fused_forward_equals_two_kernel_forward(shading, n_rays):
+    """k_s0_fwd_fused (gather groups -> shared-memory tile image -> tcgen05 MLP rounds, TMA store of the image for the backward) vs
+    k_s0_encode_fwd followed by k_mlp_fwd: bit-identical tile images and outputs (same per-sample arithmetic); 4096 rays give every CTA
+    several tiles per gather group (buffer reuse, both barrier phases, the bulk-store read fence)."""
+    tr, b = make(shading, N=n_rays)
+    stage(tr, b)
+    tr._fill_params(shading == "full", True)
+    tr.march()
+    res = []
+    for fused in (False, True):
+        tr.enc_tiles.zero_(); tr.out.zero_(); tr.loss_acc.zero_()
+        if fused:
+            tr.fwd_fused()
+        else:
+            tr.encode_fwd(); tr.mlp_fwd()
+        torch.cuda.synchronize()
+        res.append((tr.enc_tiles.clone(), tr.out.clone(), tr.loss_acc[1].item()))
+    M = int(tr.counters[1].item())
+    assert M > (128 * 296 * 2 if n_rays > 1000 else 1000)
+    nt = (M + 127) // 128
+    assert torch.equal(res[0][0][: nt * 128 * 64], res[1][0][: nt * 128 * 64])
+    assert torch.equal(res[0][1][:M], res[1][1][:M])
+    assert abs(res[0][2] - res[1][2]) <= 1e-5 * max(abs(res[0][2]), 1e-12)
+    # and a whole step through the fused forward (+ fused backward) trains like the default path
+    losses = []
+    for ff in (False, True):
+        t2, b2 = make(seed=1, N=n_rays if n_rays < 1000 else 512)
+        t2.nparts = 1
+        t2.fused_fwd = ff; t2.fused_bwd = ff
+        ls = []
+        for it in range(3):
+            t2.step(b2["ro"], b2["rd"], b2["gt"], b2["bg"], b2["noises"], use_graph=True)
+            ls.append(t2.read_loss())
+        losses.append(ls)
+    assert np.allclose(losses[0], losses[1], rtol=1e-3), losses

@@ -169,7 +169,7 @@ def test_step_orchestration_call_sequence(monkeypatch):
     tr.params = S0.S0Params(); tr.Mcap, tr.N, tr.rows, tr.parity, tr.device = 128, 4, 160, 0, "cpu"
     tr._tv_overlap, tr._tv_stream, tr._part_streams = True, None, []
     tr._adam_stream = None
-    tr.fused_bwd, tr.tv_fallback_points, tr._graphs = False, 1000, {}
+    tr.fused_bwd, tr.fused_fwd, tr.tv_fallback_points, tr._graphs = False, False, 1000, {}
 
     tv = ["n2m_s0_tv", "n2m_s0_tv_random"]
     chain = ["n2m_s0_encode_fwd_part", "n2m_s0_mlp_fwd_part", "n2m_s0_composite_loss_part", "n2m_s0_mlp_bwd_part", "n2m_s0_encode_bwd_part"]
@@ -195,6 +195,15 @@ def test_step_orchestration_call_sequence(monkeypatch):
     calls.clear(); tr.nparts = 2
     tr._compute_then_adam()
     assert names() == tv + fchain * 2 + adam
+    # gather + MLP forward as one launch (whole batch only)
+    calls.clear(); tr.fused_fwd, tr.nparts = True, 1
+    tr._compute_then_adam()
+    assert names() == tv + ["n2m_s0_fwd_fused", chain[2], "n2m_s0_bwd_fused_part"] + adam
+    tr.nparts = 2
+    import pytest
+    with pytest.raises(RuntimeError):
+        tr._compute()
+    tr.fused_fwd = False
     # TV inside the scatter kernel (tv mode 0): no TV launch, the fallback probe follows the scatter; not available with the fused backward
     calls.clear(); tr.fused_bwd, tr.nparts = False, 1
     tr.tv_overlap = False
