@@ -17,6 +17,7 @@
 #include "n2m_common.cuh"
 #include "../../include/n2m_b200_fused.h"
 #include <cuda.h>
+#include <cstdlib>
 
 namespace n2m {
 namespace {
@@ -95,11 +96,19 @@ __host__ __device__ __forceinline__ uint32_t slice_rows(uint32_t rows, uint32_t 
     return ((rows + world - 1) / world + 3u) & ~3u;
 }
 
-// reduce-scatter + Adam + all-gather on this rank's row slice; also zeroes the local gradient table of the
-// other parity (the one the next step's backward accumulates into).
+__device__ __forceinline__ void mc_st_entry(TableEntry* mc, TableEntry e) {
+    const float lo = e.d, hi = __uint_as_float(*reinterpret_cast<const uint32_t*>(&e.c));
+    asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" :: "l"(mc), "f"(lo), "f"(hi) : "memory");
+}
+
+
+// reduce-scatter + Adam + all-gather on this rank's row slice.  All 2 x W peer loads of a thread are issued before the first use (a
+// 128-bit load over NVLink has ~2-3 us of latency; the slice is streamed with 16 of them in flight per thread).  `mc_table` != NULL:
+// the refreshed entry goes to every rank with ONE multimem.st on the multicast address of the working table (NVSwitch replicates it)
+// instead of W peer stores -- the all-gather's outbound NVLink traffic drops from (W-1) x 8 B to 8 B per row.
 __global__ void __launch_bounds__(256)
-k_dp_adam_tables(const DpCtx* __restrict__ ctx, uint32_t parity, float2* __restrict__ cmaster, float* __restrict__ m,
-                 float* __restrict__ v, const float* __restrict__ st, float eps) {
+k_dp_adam_tables(const DpCtx* __restrict__ ctx, uint32_t parity, TableEntry* __restrict__ mc_table, float2* __restrict__ cmaster,
+                 float* __restrict__ m, float* __restrict__ v, const float* __restrict__ st, float eps) {
     const uint32_t W = ctx->world, r = ctx->rank, rows = ctx->rows;
     const uint32_t per = slice_rows(rows, W);
     const uint32_t lo = min(rows, r * per), hi = min(rows, lo + per);
@@ -111,28 +120,25 @@ k_dp_adam_tables(const DpCtx* __restrict__ ctx, uint32_t parity, float2* __restr
     float2* vc_p = reinterpret_cast<float2*>(v + per);
     const uint32_t i0 = lo + blockIdx.x * (256 * kRowsPerThread) + threadIdx.x;
 
-    float4 g[kRowsPerThread];
+    float4 q[kRowsPerThread][kMaxWorld];
 #pragma unroll
     for (int j = 0; j < kRowsPerThread; ++j) {
         const uint32_t i = i0 + j * 256;
-        g[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < hi) {
-            float4 q[kMaxWorld];
 #pragma unroll
-            for (int p = 0; p < kMaxWorld; ++p)
-                if (p < (int)W) q[p] = __ldcv(ctx->gtab[p][parity] + i);       // peer HBM over NVLink (L2-bypassing on the reader)
-#pragma unroll
-            for (int p = 0; p < kMaxWorld; ++p)
-                if (p < (int)W) { g[j].x += q[p].x; g[j].y += q[p].y; g[j].z += q[p].z; }
-        }
+        for (int p = 0; p < kMaxWorld; ++p)
+            if (p < (int)W && i < hi) q[j][p] = __ldcv(ctx->gtab[p][parity] + i);       // peer HBM over NVLink (L2-bypassing on the reader)
     }
     if (skip) return;
 #pragma unroll
     for (int j = 0; j < kRowsPerThread; ++j) {
         const uint32_t i = i0 + j * 256;
         if (i >= hi) continue;
+        float gx = 0.f, gy = 0.f, gz = 0.f;
+#pragma unroll
+        for (int p = 0; p < kMaxWorld; ++p)
+            if (p < (int)W) { gx += q[j][p].x; gy += q[j][p].y; gz += q[j][p].z; }
+        gx *= inv; gy *= inv; gz *= inv;
         const uint32_t k = i - lo;
-        const float gx = g[j].x * inv, gy = g[j].y * inv, gz = g[j].z * inv;
         float md = m[k], vd = v[k];
         float2 mc = mc_p[k], vc = vc_p[k];
         if (gx == 0.f && gy == 0.f && gz == 0.f && md == 0.f && vd == 0.f && mc.x == 0.f && mc.y == 0.f && vc.x == 0.f && vc.y == 0.f)
@@ -145,9 +151,12 @@ k_dp_adam_tables(const DpCtx* __restrict__ ctx, uint32_t parity, float2* __restr
         e.c = __floats2half2_rn(pc.x, pc.y);
         cmaster[k] = pc;
         m[k] = md; v[k] = vd; mc_p[k] = mc; vc_p[k] = vc;
+        if (mc_table) mc_st_entry(mc_table + i, e);                                     // all-gather: one multicast store
+        else {
 #pragma unroll
-        for (int p = 0; p < kMaxWorld; ++p)
-            if (p < (int)W) ctx->table[p][i] = e;                               // all-gather: P2P stores
+            for (int p = 0; p < kMaxWorld; ++p)
+                if (p < (int)W) ctx->table[p][i] = e;                                   // all-gather: P2P stores
+        }
     }
 }
 
@@ -163,11 +172,6 @@ __device__ __forceinline__ float4 mc_ld_reduce_add(const float4* mc) {
                  : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(mc) : "memory");
     return r;
 }
-__device__ __forceinline__ void mc_st_entry(TableEntry* mc, TableEntry e) {
-    const float lo = e.d, hi = __uint_as_float(*reinterpret_cast<const uint32_t*>(&e.c));
-    asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" :: "l"(mc), "f"(lo), "f"(hi) : "memory");
-}
-
 constexpr int kMcRowsPerThread = 4;
 
 __global__ void __launch_bounds__(256)
@@ -337,7 +341,7 @@ int n2m_dp_adam(const void* ctx, uint32_t parity, uint32_t world, uint32_t rows,
 int n2m_dp_adam_nvls(const void* ctx, const void* mc_gtab, void* mc_table, uint32_t parity, uint32_t world, uint32_t rows, uint32_t n_mlp,
                      void* color_master_slice, float* m_slice, float* v_slice, float* mlp_params, float* m_mlp, float* v_mlp, void* wpack,
                      void* gtab_next, float* gmlp_next, float* opt_state, float eps, n2m_stream_t stream) {
-    N2M_REQUIRE(mc_gtab && mc_table, "dp_adam_nvls", "null multicast pointer");
+    N2M_REQUIRE(mc_table, "dp_adam_nvls", "null multicast pointer");      /* mc_gtab NULL: peer-load reduce + multicast all-gather */
     return dp_adam_impl(ctx, mc_gtab, mc_table, parity, world, rows, n_mlp, color_master_slice, m_slice, v_slice, mlp_params, m_mlp, v_mlp, wpack,
                         gtab_next, gmlp_next, opt_state, eps, stream);
 }
@@ -345,33 +349,55 @@ int n2m_dp_adam_nvls(const void* ctx, const void* mc_gtab, void* mc_table, uint3
 static int dp_adam_impl(const void* ctx, const void* mc_gtab, void* mc_table, uint32_t parity, uint32_t world, uint32_t rows, uint32_t n_mlp,
                         void* color_master_slice, float* m_slice, float* v_slice, float* mlp_params, float* m_mlp, float* v_mlp, void* wpack,
                         void* gtab_next, float* gmlp_next, float* opt_state, float eps, n2m_stream_t stream) {
-    N2M_REQUIRE(ctx && color_master_slice && m_slice && v_slice && mlp_params && m_mlp && v_mlp && wpack && gtab_next && gmlp_next && opt_state,
-                "dp_adam", "null pointer");
+    N2M_REQUIRE(ctx && color_master_slice && m_slice && v_slice && mlp_params && m_mlp && v_mlp && wpack && opt_state, "dp_adam", "null pointer");
+    N2M_REQUIRE((gtab_next == nullptr) == (gmlp_next == nullptr), "dp_adam", "gtab_next and gmlp_next must both be given or both be NULL");
     cudaStream_t st = as_stream(stream);
     const DpCtx* c = static_cast<const DpCtx*>(ctx);
+    // N2M_DP_TRACE=1 (eager launches only, never under graph capture): CUDA events between the sub-launches, printed per call
+    static const bool trace = getenv("N2M_DP_TRACE") != nullptr;
+    cudaEvent_t ev[8];
+    int nev = 0;
+    auto mark = [&]() { if (trace && nev < 8) { cudaEventCreate(&ev[nev]); cudaEventRecord(ev[nev], st); ++nev; } };
+    mark();
     k_dp_publish_inf<<<1, 32, 0, st>>>(c, parity, opt_state);
     if (int e = check_launch("dp_adam(publish)")) return e;
     k_dp_barrier<<<1, 32, 0, st>>>(c);
     if (int e = check_launch("dp_adam(barrier A)")) return e;
     k_dp_prep<<<1, 32, 0, st>>>(c, parity, opt_state);
     if (int e = check_launch("dp_adam(prep)")) return e;
+    mark();
     const uint32_t per = slice_rows(rows, world);
     if (mc_gtab)
         k_dp_adam_tables_mc<<<div_up(per, 256u * kMcRowsPerThread), 256, 0, st>>>(c, static_cast<const float4*>(mc_gtab), static_cast<TableEntry*>(mc_table),
                                                                                   static_cast<float2*>(color_master_slice), m_slice, v_slice, opt_state, eps);
     else
-    k_dp_adam_tables<<<div_up(per, 256u * kRowsPerThread), 256, 0, st>>>(c, parity, static_cast<float2*>(color_master_slice), m_slice, v_slice,
-                                                                       opt_state, eps);
+        k_dp_adam_tables<<<div_up(per, 256u * kRowsPerThread), 256, 0, st>>>(c, parity, static_cast<TableEntry*>(mc_table),
+                                                                           static_cast<float2*>(color_master_slice), m_slice, v_slice, opt_state, eps);
     if (int e = check_launch("dp_adam(tables)")) return e;
+    mark();
     k_dp_adam_mlp<<<div_up(n_mlp, 256u), 256, 0, st>>>(c, parity, mlp_params, m_mlp, v_mlp, opt_state, eps);
     if (int e = check_launch("dp_adam(mlp)")) return e;
     if (int e = n2m_s0_pack_weights(mlp_params, wpack, stream)) return e;
-    k_dp_zero<<<div_up(rows, 256u), 256, 0, st>>>(static_cast<float4*>(gtab_next), rows, gmlp_next, n_mlp);
-    if (int e = check_launch("dp_adam(zero)")) return e;
+    if (gtab_next) {          // NULL: the caller zeroes the next-parity gradient buffers off the critical path
+        k_dp_zero<<<div_up(rows, 256u), 256, 0, st>>>(static_cast<float4*>(gtab_next), rows, gmlp_next, n_mlp);
+        if (int e = check_launch("dp_adam(zero)")) return e;
+    }
     k_dp_post<<<1, 32, 0, st>>>(opt_state);
     if (int e = check_launch("dp_adam(post)")) return e;
+    mark();
     k_dp_barrier<<<1, 32, 0, st>>>(c);
-    return check_launch("dp_adam(barrier B)");
+    if (int e = check_launch("dp_adam(barrier B)")) return e;
+    mark();
+    if (trace && nev == 5) {
+        cudaEventSynchronize(ev[4]);
+        float a = 0, b = 0, cc = 0, d = 0;
+        cudaEventElapsedTime(&a, ev[0], ev[1]); cudaEventElapsedTime(&b, ev[1], ev[2]); cudaEventElapsedTime(&cc, ev[2], ev[3]);
+        cudaEventElapsedTime(&d, ev[3], ev[4]);
+        fprintf(stderr, "[n2m dp trace] publish+barrierA+prep %.1f us | tables %.1f us | mlp+pack(+zero)+post %.1f us | barrierB %.1f us\n",
+                a * 1e3f, b * 1e3f, cc * 1e3f, d * 1e3f);
+        for (int i = 0; i < nev; ++i) cudaEventDestroy(ev[i]);
+    }
+    return 0;
 }
 
 }  // extern "C"

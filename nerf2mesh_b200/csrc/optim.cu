@@ -43,6 +43,9 @@ __device__ __forceinline__ float adam_update(float p, float g, float& m, float& 
 // at 1.6 TB/s (profiles/r1_ncu_summary.md).
 constexpr int kRowsPerThread = 4;
 
+// ZERO = false: the gradient rows are left as they are; the host zeroes that table on a side stream while the NEXT step (which
+// accumulates into the other gradient-table parity) runs its forward pass -- 16 of the 112 bytes per row leave the critical path.
+template <bool ZERO>
 __global__ void __launch_bounds__(256)
 k_adam_tables(TableEntry* __restrict__ table, float2* __restrict__ cmaster, float4* __restrict__ gtable,
               float* __restrict__ m, float* __restrict__ v, uint32_t rows, const float* __restrict__ st, float eps) {
@@ -67,7 +70,7 @@ k_adam_tables(TableEntry* __restrict__ table, float2* __restrict__ cmaster, floa
     for (int j = 0; j < kRowsPerThread; ++j) {
         const uint32_t i = i0 + j * 256;
         if (i >= rows) continue;
-        gtable[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ZERO) gtable[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (skip) continue;
         const float gx = g[j].x * inv, gy = g[j].y * inv, gz = g[j].z * inv;
         // untouched row with empty moments: the update is exactly zero -- skip the writes
@@ -175,10 +178,21 @@ extern "C" int n2m_s0_adam_tables(void* table, void* color_master, void* gtable,
                                   const float* opt_state, float eps, n2m_stream_t stream) {
     N2M_REQUIRE(table && color_master && gtable && m_table && v_table && opt_state, "s0_adam_tables", "null pointer");
     if (rows == 0) return 0;
-    k_adam_tables<<<div_up(rows, 256u * kRowsPerThread), 256, 0, as_stream(stream)>>>(
+    k_adam_tables<true><<<div_up(rows, 256u * kRowsPerThread), 256, 0, as_stream(stream)>>>(
         static_cast<TableEntry*>(table), static_cast<float2*>(color_master), static_cast<float4*>(gtable), m_table, v_table, rows,
         opt_state, eps);
     return check_launch("s0_adam(tables)");
+}
+
+/* the same without zeroing the gradient rows (the caller zeroes that table off the critical path, see k_adam_tables) */
+extern "C" int n2m_s0_adam_tables_keep(void* table, void* color_master, const void* gtable, float* m_table, float* v_table, uint32_t rows,
+                                       const float* opt_state, float eps, n2m_stream_t stream) {
+    N2M_REQUIRE(table && color_master && gtable && m_table && v_table && opt_state, "s0_adam_tables_keep", "null pointer");
+    if (rows == 0) return 0;
+    k_adam_tables<false><<<div_up(rows, 256u * kRowsPerThread), 256, 0, as_stream(stream)>>>(
+        static_cast<TableEntry*>(table), static_cast<float2*>(color_master), static_cast<float4*>(const_cast<void*>(gtable)), m_table, v_table,
+        rows, opt_state, eps);
+    return check_launch("s0_adam(tables, keep)");
 }
 
 extern "C" int n2m_s0_adam_mlp(float* mlp_params, float* g_mlp, float* m_mlp, float* v_mlp, void* wpack, const float* opt_state,

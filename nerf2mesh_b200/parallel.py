@@ -80,9 +80,11 @@ class PeerAdam:
         R = t.rows
         self.per = per = slice_rows(R, W)
         lo, hi = min(R, r * per), min(R, (r + 1) * per)
-        # second-parity gradient buffers (peers may still be reading parity p while parity p^1 is being zeroed)
-        t.gtables = [t.gtable, torch.zeros_like(t.gtable)]
-        t.g_mlps = [t.g_mlp, torch.zeros_like(t.g_mlp)]
+        # two gradient-buffer parities (peers may still be reading parity p while parity p^1 is being zeroed): the trainer already owns
+        # two tables; the MLP gradient vector gets its second copy here
+        assert t.parity == 0
+        t.gtables = [t.gtables[0], t.gtables[1]]
+        t.g_mlps = [t.g_mlps[0], torch.zeros_like(t.g_mlps[0])]
         self.flags = torch.zeros(16, dtype=torch.int32, device=dev)
         self.epoch = torch.zeros(1, dtype=torch.int32, device=dev)
         # slice-sized optimizer state, initialised from the replicated parameters
@@ -136,13 +138,16 @@ class PeerAdam:
         # from here on trainer.color_master is stale (the masters live in the per-rank slices): exports must gather them
         t._color_master_provider = self.gather_color_master
 
+    zero_inside = False        # False: the trainer zeroes the next-parity gradient buffers on a side stream under the step (Stage0Trainer.step)
+
     def run(self, parity):
         """Enqueue barrier -> reduce-scatter + Adam + all-gather -> barrier for gradient parity `parity`."""
         t = self.t
         nxt = parity ^ 1
+        zi = self.zero_inside
         call("n2m_dp_adam", ptr(self.ctx), parity, self.world, t.rows, t.n_mlp, ptr(self.cm), ptr(self.m), ptr(self.v),
-             ptr(t.mlp), ptr(t.m_mlp), ptr(t.v_mlp), ptr(t.wpack), ptr(t.gtables[nxt]), ptr(t.g_mlps[nxt]), ptr(t.opt_state),
-             t.cfg.eps, stream())
+             ptr(t.mlp), ptr(t.m_mlp), ptr(t.v_mlp), ptr(t.wpack), ptr(t.gtables[nxt]) if zi else None, ptr(t.g_mlps[nxt]) if zi else None,
+             ptr(t.opt_state), t.cfg.eps, stream())
 
     def nvlink_bytes_per_step(self):
         W = self.world
@@ -162,8 +167,12 @@ class NvlsAdam(PeerAdam):
     torch.distributed._symmetric_memory tensors -- PyTorch does the VMM / multicast-object plumbing, the data path is this repo's
     kernel.  Raises when the fabric / driver offers no multicast (callers fall back to PeerAdam, then to NCCL)."""
 
-    def __init__(self, trainer, group=None):
+    def __init__(self, trainer, group=None, reduce="switch"):
+        """reduce="switch": multimem.ld_reduce (in-switch); reduce="peer": P2P loads for the reduction, multicast store for the
+        all-gather only (the in-switch reduction saves inbound bytes, not outbound ones -- every rank still sends its whole table)."""
         import torch.distributed._symmetric_memory as symm_mem
+        assert reduce in ("switch", "peer")
+        self.reduce = reduce
         t = self.t = trainer
         self.group = group
         pg = group if group is not None else dist.group.WORLD
@@ -184,11 +193,12 @@ class NvlsAdam(PeerAdam):
             buf.copy_(src)
             return buf, symm_mem.rendezvous(buf, pg)
 
-        gt0, h_gt0 = sym(t.gtable)
-        gt1, h_gt1 = sym(torch.zeros_like(t.gtable))
+        assert t.parity == 0
+        gt0, h_gt0 = sym(t.gtables[0])
+        gt1, h_gt1 = sym(t.gtables[1])
         table, h_tab = sym(t.table)
-        gm0, h_gm0 = sym(t.g_mlp)
-        gm1, h_gm1 = sym(torch.zeros_like(t.g_mlp))
+        gm0, h_gm0 = sym(t.g_mlps[0])
+        gm1, h_gm1 = sym(torch.zeros_like(t.g_mlps[0]))
         flags, h_fl = sym(torch.zeros(16, dtype=torch.int32, device=dev))
         mc = [int(h_gt0.multicast_ptr), int(h_gt1.multicast_ptr), int(h_tab.multicast_ptr)]
         if not all(mc):
@@ -196,8 +206,8 @@ class NvlsAdam(PeerAdam):
         self.mc_gtab, self.mc_table = mc[:2], mc[2]
         self._handles = (h_gt0, h_gt1, h_tab, h_gm0, h_gm1, h_fl)
         # the trainer now works on the symmetric buffers
-        t.gtable, t.gtables, t.table = gt0, [gt0, gt1], table
-        t.g_mlp, t.g_mlps = gm0, [gm0, gm1]
+        t.gtables, t.table = [gt0, gt1], table
+        t.g_mlps = [gm0, gm1]
         t._graphs = {}
         self.flags = flags
         self.epoch = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -226,9 +236,11 @@ class NvlsAdam(PeerAdam):
     def run(self, parity):
         t = self.t
         nxt = parity ^ 1
-        call("n2m_dp_adam_nvls", ptr(self.ctx), ctypes.c_void_p(self.mc_gtab[parity]), ctypes.c_void_p(self.mc_table), parity, self.world,
+        zi = self.zero_inside
+        mc_g = ctypes.c_void_p(self.mc_gtab[parity]) if self.reduce == "switch" else None
+        call("n2m_dp_adam_nvls", ptr(self.ctx), mc_g, ctypes.c_void_p(self.mc_table), parity, self.world,
              t.rows, t.n_mlp, ptr(self.cm), ptr(self.m), ptr(self.v), ptr(t.mlp), ptr(t.m_mlp), ptr(t.v_mlp), ptr(t.wpack),
-             ptr(t.gtables[nxt]), ptr(t.g_mlps[nxt]), ptr(t.opt_state), t.cfg.eps, stream())
+             ptr(t.gtables[nxt]) if zi else None, ptr(t.g_mlps[nxt]) if zi else None, ptr(t.opt_state), t.cfg.eps, stream())
 
     def nvlink_bytes_per_step(self):
         return int(self.per * (16 + 8) + (self.world - 1) * self.t.n_mlp * 4)
@@ -238,14 +250,17 @@ def make_grad_sync(trainer, mode="auto", group=None):
     """Data-parallel optimizer for `trainer`: 'nvls' (in-switch reduce), 'peer' (P2P loads over NVLink), 'nccl' (all-reduce + replicated
     Adam) or 'auto' = the first of those that every rank can set up.  Collective: all ranks must call it with the same mode.
     Returns (sync, mode_used)."""
-    order = {"auto": ["nvls", "peer", "nccl"], "nvls": ["nvls", "peer", "nccl"], "peer": ["peer", "nccl"], "nccl": ["nccl"]}[mode]
+    # measured (profiles/r2_scaling.md): the in-switch reduction is no faster than P2P loads for a reduce-SCATTER (it saves inbound, not
+    # outbound bytes), and the multicast all-gather does not beat direct P2P stores either -- so 'auto' is the plain peer kernel
+    order = {"auto": ["peer", "nccl"], "hybrid": ["hybrid", "peer", "nccl"], "nvls": ["nvls", "peer", "nccl"],
+             "peer": ["peer", "nccl"], "nccl": ["nccl"]}[mode]
     for m in order:
         if m == "nccl":
             return GradSync(trainer, group), "nccl"
         ok = torch.ones(1, device=trainer.device)
         sync = None
         try:
-            sync = NvlsAdam(trainer, group) if m == "nvls" else PeerAdam(trainer, group)
+            sync = NvlsAdam(trainer, group, "switch") if m == "nvls" else NvlsAdam(trainer, group, "peer") if m == "hybrid" else PeerAdam(trainer, group)
         except Exception as e:      # noqa: BLE001
             import sys
             print(f"[rank {dist.get_rank(group)}] {m} data-parallel optimizer unavailable ({str(e)[:200]})", file=sys.stderr)

@@ -129,17 +129,18 @@ flatten_rays = _flatten_rays.apply
 # ----------------------------------------------------------------------------------------------
 # train
 # ----------------------------------------------------------------------------------------------
-_scratch = {}
+
+
+# (t, dt) slab of the two-call march protocol: N * max_steps float2.  Allocated per call through torch's caching allocator (so that
+# concurrent callers on different streams never share it) and only while it stays below this budget -- with --adaptive_num_rays N can
+# reach 10^5-10^6 rays; beyond the budget the native side re-walks the rays in the second call instead (k_march_train_rewalk).
+SLAB_BUDGET_BYTES = 512 << 20
 
 
 def _tbuf(device, n_floats):
-    """(t, dt) scratch slab reused across calls (never shrinks)."""
-    key = (device.type, device.index)
-    buf = _scratch.get(key)
-    if buf is None or buf.numel() < n_floats:
-        buf = torch.empty(n_floats, dtype=torch.float32, device=device)
-        _scratch[key] = buf
-    return buf
+    if n_floats * 4 > SLAB_BUDGET_BYTES:
+        return None
+    return torch.empty(n_floats, dtype=torch.float32, device=device)
 
 
 class _march_rays_train(Function):

@@ -61,6 +61,7 @@ _lib.register({
     "n2m_s0_encode_bwd_part": [PP, P, P, U, P, P, P, P, P, P, P, U, U, P],
     "n2m_s0_adam_head": [P, P, P],
     "n2m_s0_adam_tables": [P, P, P, P, P, U, P, F, P],
+    "n2m_s0_adam_tables_keep": [P, P, P, P, P, U, P, F, P],
     "n2m_s0_adam_mlp": [P, P, P, P, P, P, F, P],
     "n2m_s0_adam_post": [P, P],
     "n2m_mark_untrained_grid": [P, U, P, U, P, F, P, F, U, U, P, P, P],
@@ -158,11 +159,13 @@ class Stage0Trainer:
         # ---- model state (B200 layout) ----
         self.table = torch.zeros(R, 2, dtype=torch.float32, device=dev)          # 8-byte entries {f32, half2}
         self.color_master = torch.zeros(R, 2, dtype=torch.float32, device=dev)
-        self.gtable = torch.zeros(R, 4, dtype=torch.float32, device=dev)
+        self.gtables = [torch.zeros(R, 4, dtype=torch.float32, device=dev), torch.zeros(R, 4, dtype=torch.float32, device=dev)]
+        self.parity = 0                     # which gradient table the current step accumulates into (see defer_zero / PeerAdam)
         self.m_table = torch.zeros(R * 3, dtype=torch.float32, device=dev)
         self.v_table = torch.zeros(R * 3, dtype=torch.float32, device=dev)
         self.mlp = torch.zeros(self.n_mlp, dtype=torch.float32, device=dev)
-        self.g_mlp = torch.zeros_like(self.mlp); self.m_mlp = torch.zeros_like(self.mlp); self.v_mlp = torch.zeros_like(self.mlp)
+        self.g_mlps = [torch.zeros_like(self.mlp)]
+        self.m_mlp = torch.zeros_like(self.mlp); self.v_mlp = torch.zeros_like(self.mlp)
         self.wpack = torch.zeros(int(_lib.lib.n2m_s0_wpack_bytes()), dtype=torch.uint8, device=dev)
         self.opt_state = torch.zeros(8, dtype=torch.float32, device=dev)
         self.opt_state[0] = c.loss_scale
@@ -191,7 +194,8 @@ class Stage0Trainer:
         self.loss_acc = torch.zeros(4, device=dev)          # [0] rgb(+mask) loss, [1] sum |spec|^2
         self.params = S0Params()
         self._fill_params(shading_full=True, gt_has_alpha=True)
-        self.fused_bwd = False              # True: MLP backward + scatter as one warp-specialised launch (csrc/fused.cu)
+        self.fused_bwd = True               # MLP backward + scatter as one warp-specialised launch (csrc/fused.cu: 201 us against 128 + 174 us
+                                            # for the two stand-alone kernels, profiles/r2_summary.md); False: two launches
         self.fused_fwd = False              # True: gather + MLP forward as one warp-specialised launch (whole batch: needs nparts == 1)
         self.use_cam_near_far = False       # clamp (near, far) with the per-ray values in the slot's cam_nf (--enable_cam_near_far)
         self._tv_overlap = True             # TV gradient as its own launch overlapped with the MLP kernels (tv mode 2)
@@ -207,12 +211,30 @@ class Stage0Trainer:
         self._ema = None
         self._ema_swapped = False
         self._color_master_provider = None  # PeerAdam: the fp32 colour masters live in per-rank slices (parallel.py)
-        self.gtables = [self.gtable]        # PeerAdam adds a second parity (parallel.py)
-        self.g_mlps = [self.g_mlp]
-        self.parity = 0
+        # single GPU: the gradient table of step i is zeroed on a side stream under step i+1 (which accumulates into the other parity)
+        # instead of by the optimizer kernel: 16 of its 112 bytes per row leave the critical path
+        self.defer_zero = True
+        self._zero_stream = None
         self.global_step = 0
         self._graphs = {}
         self.reset_parameters(seed)
+
+    # the gradient buffers of the CURRENT parity under their historical names
+    @property
+    def gtable(self):
+        return self.gtables[self.parity]
+
+    @gtable.setter
+    def gtable(self, t):
+        self.gtables[self.parity] = t
+
+    @property
+    def g_mlp(self):
+        return self.g_mlps[min(self.parity, len(self.g_mlps) - 1)]
+
+    @g_mlp.setter
+    def g_mlp(self, t):
+        self.g_mlps[min(self.parity, len(self.g_mlps) - 1)] = t
 
     @property
     def tv_overlap(self):
@@ -428,7 +450,7 @@ class Stage0Trainer:
 
     def mlp_bwd(self, part=0, nparts=1):
         call("n2m_s0_mlp_bwd_part", self._pp(), ptr(self.enc_tiles), ptr(self.dout), ptr(self.counters), self.Mcap, ptr(self.wpack),
-             ptr(self.denc_tiles), ptr(self.g_mlps[self.parity]), ptr(self.opt_state), part, nparts, stream())
+             ptr(self.denc_tiles), ptr(self.g_mlp), ptr(self.opt_state), part, nparts, stream())
 
     def fwd_fused(self):
         call("n2m_s0_fwd_fused", self._pp(), ptr(self.recs), ptr(self.counters), self.Mcap, ptr(self.rays_o), ptr(self.rays_d),
@@ -437,7 +459,7 @@ class Stage0Trainer:
     def bwd_fused(self, part=0, nparts=1):
         call("n2m_s0_bwd_fused_part", self._pp(), ptr(self.enc_tiles), ptr(self.dout), ptr(self.recs), ptr(self.counters), self.Mcap,
              ptr(self.rays_o), ptr(self.rays_d), ptr(self.wpack), ptr(self.offsets), ptr(self.gtables[self.parity]),
-             ptr(self.g_mlps[self.parity]), ptr(self.opt_state), part, nparts, stream())
+             ptr(self.g_mlp), ptr(self.opt_state), part, nparts, stream())
 
     def _backward(self, part=0, nparts=1):
         """per-sample backward of one part on the current stream"""
@@ -464,9 +486,10 @@ class Stage0Trainer:
             call("n2m_s0_tv_random", self._pp(), ptr(self.counters), ptr(self.table), ptr(self.offsets), ptr(self.gtables[self.parity]),
                  ptr(self.opt_state), int(self.tv_fallback_points), ptr(dump), stream())
 
-    def adam(self):
+    def adam(self, keep_grads=False):
         """Optimizer stage: head -> [table rows || MLP parameters + weight repack] -> GradScaler update.  The MLP branch
-        (three tiny launches) runs on a forked stream underneath the 0.7 GB table sweep."""
+        (three tiny launches) runs on a forked stream underneath the 0.7 GB table sweep.  `keep_grads`: do not zero the gradient
+        table (the caller zeroes it off the critical path, see `defer_zero`)."""
         main = torch.cuda.current_stream()
         call("n2m_s0_adam_head", ptr(self.g_mlp), ptr(self.opt_state), stream())
         if self._adam_stream is None:
@@ -476,8 +499,8 @@ class Stage0Trainer:
         with torch.cuda.stream(side):
             call("n2m_s0_adam_mlp", ptr(self.mlp), ptr(self.g_mlp), ptr(self.m_mlp), ptr(self.v_mlp), ptr(self.wpack),
                  ptr(self.opt_state), self.cfg.eps, stream())
-        call("n2m_s0_adam_tables", ptr(self.table), ptr(self.color_master), ptr(self.gtable), ptr(self.m_table), ptr(self.v_table),
-             self.rows, ptr(self.opt_state), self.cfg.eps, stream())
+        call("n2m_s0_adam_tables_keep" if keep_grads else "n2m_s0_adam_tables", ptr(self.table), ptr(self.color_master), ptr(self.gtable),
+             ptr(self.m_table), ptr(self.v_table), self.rows, ptr(self.opt_state), self.cfg.eps, stream())
         main.wait_stream(side)
         call("n2m_s0_adam_post", ptr(self.opt_state), stream())
 
@@ -546,10 +569,37 @@ class Stage0Trainer:
         elif has_tv:
             self.tv_random()          # TV itself ran inside the scatter kernels (tv mode 0), which also counted the groups
 
-    def _compute_then_adam(self):
-        """forward + backward + optimizer of one step"""
+    def _compute_dp(self):
+        """`_compute` for the fused data-parallel optimizers: the gradient buffers of the OTHER parity (consumed by every peer in the
+        previous step's reduce, which ended with a barrier) are zeroed on a side stream underneath this step's forward / backward."""
+        main = torch.cuda.current_stream()
+        if self._zero_stream is None:
+            self._zero_stream = torch.cuda.Stream(device=self.device)
+        side = self._zero_stream
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            self.gtables[self.parity ^ 1].zero_()
+            self.g_mlps[(self.parity ^ 1) % len(self.g_mlps)].zero_()
         self._compute()
-        self.adam()
+        main.wait_stream(side)
+
+    def _compute_then_adam(self):
+        """forward + backward + optimizer of one step (single GPU).  With `defer_zero` the gradient table the PREVIOUS step used is
+        zeroed on a side stream underneath this step, and this step's optimizer leaves its own table for the next step to clean."""
+        if not self.defer_zero:
+            self._compute()
+            self.adam()
+            return
+        main = torch.cuda.current_stream()
+        if self._zero_stream is None:
+            self._zero_stream = torch.cuda.Stream(device=self.device)
+        side = self._zero_stream
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            self.gtables[self.parity ^ 1].zero_()
+        self._compute()
+        self.adam(keep_grads=True)
+        main.wait_stream(side)
 
     def _step_body(self):
         self.march()
@@ -565,7 +615,7 @@ class Stage0Trainer:
             key = (name, self.parity)
         else:
             key = (name, self.cur, self.parity, int(self.params.shading_full), int(self.params.gt_has_alpha), int(self.nparts),
-                   bool(self.tv_overlap), bool(self.fused_bwd), bool(self.fused_fwd), int(self.tv_fallback_points))
+                   bool(self.tv_overlap), bool(self.fused_bwd), bool(self.fused_fwd), int(self.tv_fallback_points), bool(self.defer_zero))
         g = self._graphs.get(key)
         if g is None:
             g = torch.cuda.CUDAGraph()
@@ -619,9 +669,11 @@ class Stage0Trainer:
             self._run("march", self.march, use_graph)
         if grad_sync is None:
             self._run("compute+adam", self._compute_then_adam, use_graph)
+            if self.defer_zero:
+                self.parity ^= 1           # the next step accumulates into the other gradient table
         elif getattr(grad_sync, "fused", False):
-            # data parallel, sharded optimizer fused with its collective over NVLink peer memory (parallel.PeerAdam)
-            self._run("compute", self._compute, use_graph)
+            # data parallel, sharded optimizer fused with its collective over NVLink peer memory (parallel.PeerAdam / NvlsAdam)
+            self._run("compute", self._compute_dp, use_graph)
             p = self.parity
             self._run("peer_adam", lambda: grad_sync.run(p), use_graph)
             self.parity ^= 1
@@ -693,6 +745,45 @@ class Stage0Trainer:
             torch.cuda.current_stream().wait_stream(self._side)
         call("n2m_s0_packbits_dev", ptr(self.density_grid), self.density_bitfield.numel(), ptr(self.mean_density),
              float(density_thresh), ptr(self.density_bitfield), stream())
+
+    @torch.no_grad()
+    def density_volume(self, resolution=512, density_thresh=10.0):
+        """The marching-cubes input of NeRFRenderer.export_stage0 (renderer.py:480-513): sigma on the regular grid linspace(-1, 1, R)^3
+        (x-major), multiplied by the occupancy mask of cascade 0 (density_grid > min(mean_density, density_thresh), nearest-neighbour
+        up-sampled) so that empty / untrained regions stay empty; for R == grid_size the density grid itself, re-mapped from Morton order.
+        Returns a float32 [R, R, R] tensor on the device (the mesh extraction that follows in the reference is CPU library code)."""
+        self.drop_prefetch()
+        dev, c = self.device, self.cfg
+        R, H = int(resolution), c.grid_size
+        from . import raymarching as rm
+        coords = rm.morton3D_invert(torch.arange(H ** 3, dtype=torch.int32, device=dev)).long()
+        grid0 = torch.zeros(H, H, H, device=dev)
+        grid0[tuple(coords.T)] = self.density_grid[0]
+        if R == H:
+            return torch.nan_to_num(grid0, 0)
+        mean = getattr(self, "mean_density", None)
+        thresh = min(float(mean.item()), density_thresh) if mean is not None else density_thresh
+        if not hasattr(self, "_pcount"):
+            self._pcount = torch.zeros(4, dtype=torch.int32, device=dev)
+            self._pparams = S0Params()
+        ctypes.memmove(ctypes.byref(self._pparams), ctypes.byref(self.params), ctypes.sizeof(S0Params))
+        self._pparams.shading_full = 0
+        pp = ctypes.byref(self._pparams)
+        lin = torch.linspace(-1, 1, R, device=dev)
+        sig = torch.empty(R ** 3, device=dev)
+        per = max(1, self.Mcap // (R * R))                # x-slabs per chunk
+        for x0 in range(0, R, per):
+            x1 = min(R, x0 + per)
+            xx, yy, zz = torch.meshgrid(lin[x0:x1], lin, lin, indexing="ij")
+            pts = torch.stack([xx.reshape(-1), yy.reshape(-1), zz.reshape(-1)], -1).contiguous()
+            n = pts.shape[0]
+            self._pcount.fill_(n)
+            call("n2m_s0_encode_points", pp, ptr(pts), None, ptr(self._pcount), self.Mcap, ptr(self.table), ptr(self.offsets),
+                 ptr(self.enc_tiles), stream())
+            call("n2m_s0_mlp_fwd", pp, ptr(self.enc_tiles), ptr(self._pcount), self.Mcap, ptr(self.wpack), ptr(self.out), None, stream())
+            sig[x0 * R * R: x1 * R * R] = self.out[:n, 0]
+        mask = torch.nn.functional.interpolate(grid0[None, None], size=[R] * 3, mode="nearest")[0, 0] > thresh
+        return torch.nan_to_num(sig.view(R, R, R) * mask, 0)
 
     @torch.no_grad()
     def render(self, rays_o, rays_d, bg_color=1.0, shading="full"):

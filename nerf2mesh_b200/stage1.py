@@ -77,13 +77,13 @@ class Stage1Trainer:
              ptr(t0.opt_state), ptr(self.dout), ptr(self.image), ptr(self.weights_sum), ptr(self.loss_acc), stream())
         if t0.fused_bwd:
             call("n2m_s0_bwd_fused_part", self._pp(), ptr(self.enc_tiles), ptr(self.dout), ptr(self.recs), ptr(self.counters), self.cap,
-                 ptr(self.pts), ptr(self.pdirs), ptr(t0.wpack), ptr(t0.offsets), ptr(t0.gtables[t0.parity]), ptr(t0.g_mlps[t0.parity]),
+                 ptr(self.pts), ptr(self.pdirs), ptr(t0.wpack), ptr(t0.offsets), ptr(t0.gtables[t0.parity]), ptr(t0.g_mlp),
                  ptr(t0.opt_state), 0, 1, stream())
         else:
             if self.denc_tiles is None:
                 self.denc_tiles = torch.zeros(self.cap * 64, dtype=torch.float16, device=t0.device)
             call("n2m_s0_mlp_bwd", self._pp(), ptr(self.enc_tiles), ptr(self.dout), ptr(self.counters), self.cap, ptr(t0.wpack),
-                 ptr(self.denc_tiles), ptr(t0.g_mlps[t0.parity]), ptr(t0.opt_state), stream())
+                 ptr(self.denc_tiles), ptr(t0.g_mlp), ptr(t0.opt_state), stream())
             call("n2m_s0_encode_bwd", self._pp(), ptr(self.recs), ptr(self.counters), self.cap, ptr(self.pts), ptr(self.pdirs),
                  ptr(self.denc_tiles), ptr(t0.table), ptr(t0.offsets), ptr(t0.gtables[t0.parity]), ptr(t0.opt_state), stream())
 

@@ -31,15 +31,16 @@ def _worker(rank, world, port, q):
     g = torch.Generator().manual_seed(rank)
     bg = torch.rand(N, 3, generator=g); noises = torch.rand(N, generator=g)
     out = {}
-    for mode in ("nccl", "peer", "nvls"):
+    for mode in ("nccl", "peer", "nvls", "hybrid"):
         tr = Stage0Trainer(Stage0Config(bound=1.0, num_rays=N, max_samples=N * 256), seed=0)     # identical replicas
         tr.set_occupancy(bits, grid)
-        if mode == "nvls":
+        if mode in ("nvls", "hybrid"):
             ok = torch.ones(1, device="cuda")
             try:
-                sync = NvlsAdam(tr)
+                sync = NvlsAdam(tr, reduce="switch" if mode == "nvls" else "peer")
             except Exception as e:      # noqa: BLE001
                 out["nvls_unavailable"] = repr(e)[:200]
+                sync = None
                 ok.zero_()
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)
             if ok.item() == 0:
@@ -69,7 +70,7 @@ def test_peer_adam_matches_nccl_allreduce_world2():
     res = dict(q.get(timeout=600) for _ in range(2))
     [p.join(120) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
-    modes = ["peer"] + (["nvls"] if "nvls" in res[0] else [])
+    modes = ["peer"] + [m for m in ("nvls", "hybrid") if m in res[0]]
     for mode in modes:
         for name in res[0][mode]:
             a0, a1 = res[0][mode][name], res[1][mode][name]

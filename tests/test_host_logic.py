@@ -163,9 +163,9 @@ def test_step_orchestration_call_sequence(monkeypatch):
     slot = types.SimpleNamespace(**{k: T() for k in ("rays_o", "rays_d", "gt", "bg", "noises", "rays", "counters", "tbuf", "recs", "cam_nf")}, has_alpha=True)
     tr.slots, tr.cur = [slot, slot], 0
     for k in ("table", "offsets", "enc_tiles", "opt_state", "wpack", "out", "dout", "image", "weights_sum", "depth", "denc_tiles",
-              "color_master", "gtable", "m_table", "v_table", "mlp", "g_mlp", "m_mlp", "v_mlp", "loss_acc"):
+              "color_master", "m_table", "v_table", "mlp", "m_mlp", "v_mlp", "loss_acc"):
         setattr(tr, k, T())
-    tr.gtables, tr.g_mlps = [tr.gtable], [tr.g_mlp]
+    tr.gtables, tr.g_mlps, tr.defer_zero, tr._zero_stream = [T(), T()], [T()], False, None
     tr.params = S0.S0Params(); tr.Mcap, tr.N, tr.rows, tr.parity, tr.device = 128, 4, 160, 0, "cpu"
     tr._tv_overlap, tr._tv_stream, tr._part_streams = True, None, []
     tr._adam_stream = None
@@ -215,6 +215,11 @@ def test_step_orchestration_call_sequence(monkeypatch):
     import pytest
     with pytest.raises(RuntimeError):
         tr._compute()
+    # deferred zeroing of the gradient table: same launches, the optimizer variant that leaves the rows alone
+    calls.clear(); tr.defer_zero, tr.fused_bwd = True, False
+    tr._compute_then_adam()
+    assert names() == chain + ["n2m_s0_tv_random"] + adam[:2] + ["n2m_s0_adam_tables_keep", adam[3]]
+    tr.defer_zero = False
     # lambda_tv == 0: no TV work at all
     calls.clear(); tr.fused_bwd = False; tr.cfg.lambda_tv = 0.0
     tr._compute_then_adam()
