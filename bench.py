@@ -428,6 +428,7 @@ def run_ours(args):
     tr.fused_bwd = bool(args.fused_bwd)
     tr.fused_fwd = bool(args.fused_fwd)
     tr.defer_zero = bool(args.defer_zero)
+    tr.prefetch_at = args.prefetch_at
     if tr.fused_fwd:
         tr.nparts = 1
     sync, dp_used = None, args.dp
@@ -588,7 +589,7 @@ def run_ours(args):
                 "data": "synthetic",
                 "config": {"workload": workload, "rays_per_batch": NUM_RAYS, "global_rays": NUM_RAYS * world,
                            "samples_per_step": samples_total / K, "parallelism": f"dp{world}" + ("" if world == 1 else f"-{dp_used}"),
-                           "cuda_graph": not args.no_graph, "ray_range_parts": int(tr.nparts), "fused_bwd": bool(tr.fused_bwd), "fused_fwd": bool(tr.fused_fwd), "defer_zero": bool(tr.defer_zero),
+                           "cuda_graph": not args.no_graph, "ray_range_parts": int(tr.nparts), "fused_bwd": bool(tr.fused_bwd), "fused_fwd": bool(tr.fused_fwd), "defer_zero": bool(tr.defer_zero), "prefetch_at": tr.prefetch_at,
                            "march_prefetch": not args.no_prefetch, **{k: v for k, v in WORKLOADS[workload].items() if k != "cap"},
                            "sample_capacity": tr.Mcap, "capacity_overflow_steps": overflow_steps, "max_samples_seen": max_m,
                            "l2": "inputs cycle over 8 batches; tables+grads+Adam state (0.6 GB touched per step) exceed the 126 MB L2"},
@@ -685,12 +686,14 @@ def main():
     ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="--impl reference: wall-clock budget of the whole CPU run")
     ap.add_argument("--skip-reference", action="store_true", help="skip the same-box reference-CUDA leg")
     ap.add_argument("--psnr-iters", type=int, default=300, help="training steps of the PSNR-vs-reference pair (0 = skip)")
+    ap.add_argument("--prefetch-at", default="optimizer", choices=["optimizer", "start"],
+                    help="where the next batch's march is released on the side stream: under the optimizer stage or under the forward pass")
     ap.add_argument("--defer-zero", type=int, default=1, help="1: the gradient table is zeroed on a side stream under the next step instead of by the optimizer kernel")
     ap.add_argument("--fused-fwd", type=int, default=0, help="1: gather + MLP forward as one warp-specialised launch (implies --parts 1)")
     ap.add_argument("--fused-bwd", type=int, default=1, help="1: MLP backward + scatter as one warp-specialised launch (csrc/fused.cu)")
     ap.add_argument("--parts", type=int, default=2, choices=[1, 2, 4, 8],
                     help="ray-range parts run as concurrent gather->MLP->composite->MLP'->scatter chains on forked streams")
-    ap.add_argument("--dp", default="auto", choices=["auto", "hybrid", "nvls", "peer", "nccl"],
+    ap.add_argument("--dp", default="auto", choices=["auto", "nvls", "peer", "nccl"],
                     help="N > 1: 'nvls' = reduce-scatter inside the NVSwitch (multimem) + sharded Adam + multicast all-gather, 'peer' = the "
                          "same with P2P loads / stores over NVLink, 'nccl' = all-reduce + replicated Adam, 'auto' = first that sets up")
     args = ap.parse_args()

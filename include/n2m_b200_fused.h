@@ -277,10 +277,9 @@ int n2m_dp_adam(const void* ctx, uint32_t parity, uint32_t world, uint32_t rows,
 
 /* NVLS variant: the table gradients are reduced INSIDE the NVSwitch (multimem.ld_reduce on a multicast address that maps the gradient
  * table of every rank) and the refreshed 8-byte entries are broadcast with one multimem.st; mc_gtab / mc_table are the multicast addresses
- * (torch.distributed._symmetric_memory) of this parity's gradient table and of the working table.  mc_gtab == NULL: the gradients are
- * reduced with P2P loads as in n2m_dp_adam and only the all-gather uses the multicast store ("hybrid": the in-switch reduction saves
- * inbound traffic only -- every rank still sends its whole table -- while the multicast store saves (W-1)/W of the all-gather's outbound
- * bytes).  In both entry points gtab_next / gmlp_next may be NULL: the caller then zeroes the next-parity gradient buffers itself. */
+ * (torch.distributed._symmetric_memory) of this parity's gradient table and of the working table.  Per rank and step the links carry 16 B x rows out
+ * (the switch pulls every replica of a row once) against 16 B x rows x (W-1)/W each way with P2P loads, and the all-gather 8 B x rows / W
+ * out instead of 8 B x rows x (W-1)/W: slower than n2m_dp_adam at W = 2, faster at W = 8 (profiles/r2_scaling.md).  In both entry points gtab_next / gmlp_next may be NULL: the caller then zeroes the next-parity gradient buffers itself. */
 int n2m_dp_adam_nvls(const void* ctx, const void* mc_gtab, void* mc_table, uint32_t parity, uint32_t world, uint32_t rows, uint32_t n_mlp,
                      void* color_master_slice, float* m_slice, float* v_slice, float* mlp_params, float* m_mlp, float* v_mlp, void* wpack,
                      void* gtab_next, float* gmlp_next, float* opt_state, float eps, n2m_stream_t stream);

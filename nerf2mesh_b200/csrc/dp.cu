@@ -103,11 +103,9 @@ __device__ __forceinline__ void mc_st_entry(TableEntry* mc, TableEntry e) {
 
 
 // reduce-scatter + Adam + all-gather on this rank's row slice.  All 2 x W peer loads of a thread are issued before the first use (a
-// 128-bit load over NVLink has ~2-3 us of latency; the slice is streamed with 16 of them in flight per thread).  `mc_table` != NULL:
-// the refreshed entry goes to every rank with ONE multimem.st on the multicast address of the working table (NVSwitch replicates it)
-// instead of W peer stores -- the all-gather's outbound NVLink traffic drops from (W-1) x 8 B to 8 B per row.
+// 128-bit load over NVLink has ~2-3 us of latency; the slice is streamed with 16 of them in flight per thread).
 __global__ void __launch_bounds__(256)
-k_dp_adam_tables(const DpCtx* __restrict__ ctx, uint32_t parity, TableEntry* __restrict__ mc_table, float2* __restrict__ cmaster,
+k_dp_adam_tables(const DpCtx* __restrict__ ctx, uint32_t parity, float2* __restrict__ cmaster,
                  float* __restrict__ m, float* __restrict__ v, const float* __restrict__ st, float eps) {
     const uint32_t W = ctx->world, r = ctx->rank, rows = ctx->rows;
     const uint32_t per = slice_rows(rows, W);
@@ -151,12 +149,9 @@ k_dp_adam_tables(const DpCtx* __restrict__ ctx, uint32_t parity, TableEntry* __r
         e.c = __floats2half2_rn(pc.x, pc.y);
         cmaster[k] = pc;
         m[k] = md; v[k] = vd; mc_p[k] = mc; vc_p[k] = vc;
-        if (mc_table) mc_st_entry(mc_table + i, e);                                     // all-gather: one multicast store
-        else {
 #pragma unroll
-            for (int p = 0; p < kMaxWorld; ++p)
-                if (p < (int)W) ctx->table[p][i] = e;                                   // all-gather: P2P stores
-        }
+        for (int p = 0; p < kMaxWorld; ++p)
+            if (p < (int)W) ctx->table[p][i] = e;                                       // all-gather: P2P stores
     }
 }
 
@@ -341,7 +336,7 @@ int n2m_dp_adam(const void* ctx, uint32_t parity, uint32_t world, uint32_t rows,
 int n2m_dp_adam_nvls(const void* ctx, const void* mc_gtab, void* mc_table, uint32_t parity, uint32_t world, uint32_t rows, uint32_t n_mlp,
                      void* color_master_slice, float* m_slice, float* v_slice, float* mlp_params, float* m_mlp, float* v_mlp, void* wpack,
                      void* gtab_next, float* gmlp_next, float* opt_state, float eps, n2m_stream_t stream) {
-    N2M_REQUIRE(mc_table, "dp_adam_nvls", "null multicast pointer");      /* mc_gtab NULL: peer-load reduce + multicast all-gather */
+    N2M_REQUIRE(mc_gtab && mc_table, "dp_adam_nvls", "null multicast pointer");
     return dp_adam_impl(ctx, mc_gtab, mc_table, parity, world, rows, n_mlp, color_master_slice, m_slice, v_slice, mlp_params, m_mlp, v_mlp, wpack,
                         gtab_next, gmlp_next, opt_state, eps, stream);
 }
@@ -371,8 +366,8 @@ static int dp_adam_impl(const void* ctx, const void* mc_gtab, void* mc_table, ui
         k_dp_adam_tables_mc<<<div_up(per, 256u * kMcRowsPerThread), 256, 0, st>>>(c, static_cast<const float4*>(mc_gtab), static_cast<TableEntry*>(mc_table),
                                                                                   static_cast<float2*>(color_master_slice), m_slice, v_slice, opt_state, eps);
     else
-        k_dp_adam_tables<<<div_up(per, 256u * kRowsPerThread), 256, 0, st>>>(c, parity, static_cast<TableEntry*>(mc_table),
-                                                                           static_cast<float2*>(color_master_slice), m_slice, v_slice, opt_state, eps);
+        k_dp_adam_tables<<<div_up(per, 256u * kRowsPerThread), 256, 0, st>>>(c, parity, static_cast<float2*>(color_master_slice), m_slice, v_slice,
+                                                                           opt_state, eps);
     if (int e = check_launch("dp_adam(tables)")) return e;
     mark();
     k_dp_adam_mlp<<<div_up(n_mlp, 256u), 256, 0, st>>>(c, parity, mlp_params, m_mlp, v_mlp, opt_state, eps);

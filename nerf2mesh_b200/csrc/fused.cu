@@ -97,7 +97,7 @@ __device__ __forceinline__ void scatter_levels(const LevelConst* __restrict__ lc
         for (int k = 0; k < 8; ++k) {
             const int ix = k & 1, iy = (k >> 1) & 1, iz = (k >> 2) & 1;
             const uint32_t raw = hashed ? (xs[ix] ^ ys[iy] ^ zs[iz]) : (xs[ix] + ys[iy] + zs[iz]);
-            rowi[k] = pow2 ? (raw & (L.rows - 1)) : (raw % L.rows);
+            rowi[k] = wrap_row(raw, L.rows, pow2);
             const float w = wx[ix] * wy[iy] * wz[iz];
             vd[k] = w * gd; v0[k] = w * g0; v1[k] = w * g1;
         }
@@ -110,9 +110,11 @@ __device__ __forceinline__ void scatter_levels(const LevelConst* __restrict__ lc
         bool issue = active;
         if (merge) {
             const uint32_t run_start = 31u - __clz(heads & (0xffffffffu >> (31u - lane)));
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const bool take = lane >= run_start + (uint32_t)o;
+            // segmented inclusive scan; only as many doubling rounds as the longest run of this warp needs (the later ones add nothing)
+            const uint32_t longest = __reduce_max_sync(0xffffffffu, lane - run_start);
+#pragma unroll 1
+            for (uint32_t o = 1; o <= longest; o <<= 1) {
+                const bool take = lane >= run_start + o;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const float a = __shfl_up_sync(0xffffffffu, vd[k], o), b = __shfl_up_sync(0xffffffffu, v0[k], o),

@@ -107,7 +107,9 @@ __device__ __forceinline__ uint32_t lattice_row(const uint32_t (&p)[D], const Le
     if (gridtype == 0 && stride > g.rows) {
         idx = hash_xor<D>(p);
     }
-    return idx % g.rows;
+    // idx % rows without the integer division where it is an identity or a mask (dense levels, 2^k-row hashed levels)
+    if ((g.rows & (g.rows - 1)) == 0) return idx & (g.rows - 1);
+    return idx < g.rows ? idx : idx % g.rows;
 }
 
 __device__ __forceinline__ float smooth(float v) { return v * v * (3.0f - 2.0f * v); }

@@ -69,6 +69,14 @@ __device__ __forceinline__ LevelGeom level_geom(const int32_t* __restrict__ offs
     return g;
 }
 
+// index % rows of gridencoder.cu:84.  A dense level's index is already below its row count ((res + 1)^3 <= rows and every
+// coordinate <= res), a hashed level has 2^k rows: the integer division (~20 instructions per corner) is kept only as the guard
+__device__ __forceinline__ uint32_t wrap_row(uint32_t raw, uint32_t rows, bool pow2) {
+    if (pow2) return raw & (rows - 1);
+    if (raw >= rows) raw %= rows;
+    return raw;
+}
+
 // returns false when the sample is outside [0,1]^3 (the encoders output zeros there)
 __device__ __forceinline__ void corners_of(const LevelGeom& g, float u, float v, float w, Corners& c,
                                            uint32_t (&base)[3], bool& hashed, uint32_t* left = nullptr) {
@@ -101,7 +109,7 @@ __device__ __forceinline__ void corners_of(const LevelGeom& g, float u, float v,
     for (int k = 0; k < 8; ++k) {
         const int ix = k & 1, iy = (k >> 1) & 1, iz = (k >> 2) & 1;
         const uint32_t raw = hashed ? (xs[ix] ^ ys[iy] ^ zs[iz]) : (xs[ix] + ys[iy] + zs[iz]);
-        c.row[k] = pow2 ? (raw & (g.rows - 1)) : (raw % g.rows);
+        c.row[k] = wrap_row(raw, g.rows, pow2);
         c.w[k] = wx[ix] * wy[iy] * wz[iz];
     }
     if (left) {     // rows of the cells at base - 1 along each axis (TV neighbours); callers check base[d] > 0
@@ -115,9 +123,9 @@ __device__ __forceinline__ void corners_of(const LevelGeom& g, float u, float v,
             ly = xs[0] + ys[0] - my + zs[0];
             lz = xs[0] + ys[0] + zs[0] - mz;
         }
-        left[0] = pow2 ? (lx & (g.rows - 1)) : (lx % g.rows);
-        left[1] = pow2 ? (ly & (g.rows - 1)) : (ly % g.rows);
-        left[2] = pow2 ? (lz & (g.rows - 1)) : (lz % g.rows);
+        left[0] = wrap_row(lx, g.rows, pow2);
+        left[1] = wrap_row(ly, g.rows, pow2);
+        left[2] = wrap_row(lz, g.rows, pow2);
     }
 }
 

@@ -329,9 +329,11 @@ encode_bwd_tile(const n2m_s0_params& p, const float4* __restrict__ recs,
         bool issue = active;
         if (merge) {
             const uint32_t run_start = 31u - __clz(heads & (0xffffffffu >> (31u - lane)));
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const bool take = lane >= run_start + (uint32_t)o;
+            // segmented inclusive scan; only as many doubling rounds as the longest run of this warp needs (the later ones add nothing)
+            const uint32_t longest = __reduce_max_sync(0xffffffffu, lane - run_start);
+#pragma unroll 1
+            for (uint32_t o = 1; o <= longest; o <<= 1) {
+                const bool take = lane >= run_start + o;
                 if (SCATTER) {
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {

@@ -167,12 +167,8 @@ class NvlsAdam(PeerAdam):
     torch.distributed._symmetric_memory tensors -- PyTorch does the VMM / multicast-object plumbing, the data path is this repo's
     kernel.  Raises when the fabric / driver offers no multicast (callers fall back to PeerAdam, then to NCCL)."""
 
-    def __init__(self, trainer, group=None, reduce="switch"):
-        """reduce="switch": multimem.ld_reduce (in-switch); reduce="peer": P2P loads for the reduction, multicast store for the
-        all-gather only (the in-switch reduction saves inbound bytes, not outbound ones -- every rank still sends its whole table)."""
+    def __init__(self, trainer, group=None):
         import torch.distributed._symmetric_memory as symm_mem
-        assert reduce in ("switch", "peer")
-        self.reduce = reduce
         t = self.t = trainer
         self.group = group
         pg = group if group is not None else dist.group.WORLD
@@ -237,8 +233,7 @@ class NvlsAdam(PeerAdam):
         t = self.t
         nxt = parity ^ 1
         zi = self.zero_inside
-        mc_g = ctypes.c_void_p(self.mc_gtab[parity]) if self.reduce == "switch" else None
-        call("n2m_dp_adam_nvls", ptr(self.ctx), mc_g, ctypes.c_void_p(self.mc_table), parity, self.world,
+        call("n2m_dp_adam_nvls", ptr(self.ctx), ctypes.c_void_p(self.mc_gtab[parity]), ctypes.c_void_p(self.mc_table), parity, self.world,
              t.rows, t.n_mlp, ptr(self.cm), ptr(self.m), ptr(self.v), ptr(t.mlp), ptr(t.m_mlp), ptr(t.v_mlp), ptr(t.wpack),
              ptr(t.gtables[nxt]) if zi else None, ptr(t.g_mlps[nxt]) if zi else None, ptr(t.opt_state), t.cfg.eps, stream())
 
@@ -247,12 +242,14 @@ class NvlsAdam(PeerAdam):
 
 
 def make_grad_sync(trainer, mode="auto", group=None):
-    """Data-parallel optimizer for `trainer`: 'nvls' (in-switch reduce), 'peer' (P2P loads over NVLink), 'nccl' (all-reduce + replicated
-    Adam) or 'auto' = the first of those that every rank can set up.  Collective: all ranks must call it with the same mode.
-    Returns (sync, mode_used)."""
-    # measured (profiles/r2_scaling.md): the in-switch reduction is no faster than P2P loads for a reduce-SCATTER (it saves inbound, not
-    # outbound bytes), and the multicast all-gather does not beat direct P2P stores either -- so 'auto' is the plain peer kernel
-    order = {"auto": ["peer", "nccl"], "hybrid": ["hybrid", "peer", "nccl"], "nvls": ["nvls", "peer", "nccl"],
+    """Data-parallel optimizer for `trainer`: 'nvls' (in-switch reduce + multicast all-gather), 'peer' (P2P loads / stores over NVLink),
+    'nccl' (all-reduce + replicated Adam) or 'auto' = the fastest measured for this world size that every rank can set up.
+    Collective: all ranks must call it with the same mode.  Returns (sync, mode_used)."""
+    # measured (profiles/r2_scaling.md): per rank the in-switch reduce-scatter sends 16 B x rows whatever W is, P2P loads
+    # 16 B x rows x (W-1)/W each way, and the multicast all-gather 8 B x rows / W instead of 8 B x rows x (W-1)/W:
+    # peer wins at W = 2 (0.611 vs 0.708 ms/step), NVLS at W = 8 (0.680 vs 0.731); the byte counts cross at W = 4
+    W = dist.get_world_size(group)
+    order = {"auto": ["nvls", "peer", "nccl"] if W > 4 else ["peer", "nccl"], "nvls": ["nvls", "peer", "nccl"],
              "peer": ["peer", "nccl"], "nccl": ["nccl"]}[mode]
     for m in order:
         if m == "nccl":
@@ -260,7 +257,7 @@ def make_grad_sync(trainer, mode="auto", group=None):
         ok = torch.ones(1, device=trainer.device)
         sync = None
         try:
-            sync = NvlsAdam(trainer, group, "switch") if m == "nvls" else NvlsAdam(trainer, group, "peer") if m == "hybrid" else PeerAdam(trainer, group)
+            sync = NvlsAdam(trainer, group) if m == "nvls" else PeerAdam(trainer, group)
         except Exception as e:      # noqa: BLE001
             import sys
             print(f"[rank {dist.get_rank(group)}] {m} data-parallel optimizer unavailable ({str(e)[:200]})", file=sys.stderr)

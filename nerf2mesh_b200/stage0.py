@@ -215,6 +215,10 @@ class Stage0Trainer:
         # instead of by the optimizer kernel: 16 of its 112 bytes per row leave the critical path
         self.defer_zero = True
         self._zero_stream = None
+        # step(next_batch=...): where the next batch's march (issue-bound, a few MB of traffic) is released on the side stream --
+        # "optimizer": underneath the optimizer stage (HBM-bound table sweep, or the NVLink-bound data-parallel exchange), on a
+        # high-priority stream so that its blocks are dispatched ahead of the sweep's; "start": underneath the forward pass
+        self.prefetch_at = "optimizer"
         self.global_step = 0
         self._graphs = {}
         self.reset_parameters(seed)
@@ -601,6 +605,24 @@ class Stage0Trainer:
         self.adam(keep_grads=True)
         main.wait_stream(side)
 
+    def _compute_sg(self):
+        """`_compute` of a single-GPU step whose optimizer is launched separately (see `prefetch_at`)."""
+        if not self.defer_zero:
+            self._compute()
+            return
+        main = torch.cuda.current_stream()
+        if self._zero_stream is None:
+            self._zero_stream = torch.cuda.Stream(device=self.device)
+        side = self._zero_stream
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            self.gtables[self.parity ^ 1].zero_()
+        self._compute()
+        main.wait_stream(side)
+
+    def _adam_sg(self):
+        self.adam(keep_grads=self.defer_zero)
+
     def _step_body(self):
         self.march()
         self._compute_then_adam()
@@ -658,38 +680,51 @@ class Stage0Trainer:
         if key != (bool(self.params.shading_full), bool(self.params.gt_has_alpha)):
             self._fill_params(*key)
 
-        ev_start = None
+        ev_start = ev_mid = None
+        split = next_batch is not None and self.prefetch_at == "optimizer"
         if next_batch is not None:
             # the prefetch below must come after whatever is already queued on this stream (e.g. set_occupancy), but NOT after
             # this step's own compute: mark the spot now, enqueue the compute first (the GPU starts on it while the host is
             # still enqueueing the prefetch -- matters when the caller synchronises every step), the prefetch afterwards
             ev_start = torch.cuda.Event(); ev_start.record(main)
 
+        def mid():
+            nonlocal ev_mid
+            if split:
+                ev_mid = torch.cuda.Event(); ev_mid.record(main)
+
         if not marched:
             self._run("march", self.march, use_graph)
         if grad_sync is None:
-            self._run("compute+adam", self._compute_then_adam, use_graph)
+            if split:
+                self._run("compute_sg", self._compute_sg, use_graph)
+                mid()
+                self._run("adam_sg", self._adam_sg, use_graph)
+            else:
+                self._run("compute+adam", self._compute_then_adam, use_graph)
             if self.defer_zero:
                 self.parity ^= 1           # the next step accumulates into the other gradient table
         elif getattr(grad_sync, "fused", False):
             # data parallel, sharded optimizer fused with its collective over NVLink peer memory (parallel.PeerAdam / NvlsAdam)
             self._run("compute", self._compute_dp, use_graph)
+            mid()
             p = self.parity
             self._run("peer_adam", lambda: grad_sync.run(p), use_graph)
             self.parity ^= 1
         else:
             # data parallel: [forward+backward] -> gradient all-reduce (NCCL) -> [optimizer]
             self._run("compute", self._compute, use_graph)
+            mid()
             grad_sync()
             self._run("adam", self.adam, use_graph)
         ev = torch.cuda.Event(); ev.record(main)
         self._ev_done[self.cur] = ev
         self.global_step += 1
         if next_batch is not None:
-            # side stream: stage + march the next batch into the other slot
+            # side stream: stage the next batch into the other slot (at once) and march it (underneath the optimizer stage)
             nxt = 1 - self.cur
             if self._side is None:
-                self._side = torch.cuda.Stream(device=self.device)
+                self._side = torch.cuda.Stream(device=self.device, priority=-1 if self.prefetch_at == "optimizer" else 0)
             side = self._side
             if self._ev_done[nxt] is not None:
                 side.wait_event(self._ev_done[nxt])              # slot `nxt` was last read by the previous step
@@ -697,6 +732,8 @@ class Stage0Trainer:
             keep = self.cur
             with torch.cuda.stream(side):
                 self.slots[nxt].load(*next_batch)
+                if ev_mid is not None:
+                    side.wait_event(ev_mid)
                 self.cur = nxt
                 self._run("march", self.march, use_graph)
                 self.cur = keep
@@ -708,17 +745,30 @@ class Stage0Trainer:
     # -------------------------------------------------------------------------------------------
     # density grid / bitfield update and evaluation rendering
     # -------------------------------------------------------------------------------------------
-    def update_density_grid(self, decay=0.95, density_thresh=10.0):
+    def update_density_grid(self, decay=0.95, density_thresh=10.0, generator=None, shard_group=None):
         """NeRFRenderer.update_extra_state (renderer.py:1074-1149): evaluate the density field at one jittered
         point per grid cell and cascade (hash gather + sigma_net on tensor cores), grid = max(grid * decay, sigma),
         threshold = min(mean(clamp(grid, 0)), density_thresh), repack the bitfield.  Everything stays on the
         device (the reference syncs for `mean_density.item()`).
         With `step(next_batch=...)` a batch whose march is already staged on the side stream keeps the samples of the previous
         bitfield (the update then takes effect one step later than in the reference); call `drop_prefetch()` first for the
-        reference's exact order."""
+        reference's exact order.
+        `generator`: CUDA generator of the per-cell jitter (default: the global one, as the reference).
+        `shard_group` (data parallel, identical replicas): every rank evaluates 1/W of the cells of each cascade and the grid rows are
+        all-gathered (NCCL; 8 MB per cascade) -- the 2.1 M - 10.5 M density evaluations per call divide by W.  All ranks must pass
+        generators in the same state; the result is then bit-identical to the replicated update."""
         c = self.cfg
         H, cells = c.grid_size, c.grid_size ** 3
         dev = self.device
+        W, rank = 1, 0
+        if shard_group is not None:
+            import torch.distributed as dist
+            W, rank = dist.get_world_size(shard_group), dist.get_rank(shard_group)
+            if generator is None:
+                raise ValueError("a sharded density-grid update needs a generator that is in the same state on every rank")
+            if cells % W:
+                raise ValueError(f"grid cells ({cells}) not divisible by the world size ({W})")
+        lo, hi = rank * (cells // W), (rank + 1) * (cells // W)
         if not hasattr(self, "_pts"):
             self._pts = torch.zeros(self.Mcap, 3, device=dev)
             self._pcount = torch.zeros(4, dtype=torch.int32, device=dev)
@@ -729,9 +779,9 @@ class Stage0Trainer:
         for cas in range(c.cascade):
             bound = float(min(2 ** cas, c.bound))
             row = self.density_grid[cas]
-            noise = torch.rand(cells, 3, device=dev)          # == torch.rand_like(cas_xyzs) of the reference (renderer.py:1110)
-            for first in range(0, cells, self.Mcap):
-                cnt = min(self.Mcap, cells - first)
+            noise = torch.rand(cells, 3, device=dev, generator=generator)      # == torch.rand_like(cas_xyzs) of the reference (renderer.py:1110)
+            for first in range(lo, hi, self.Mcap):
+                cnt = min(self.Mcap, hi - first)
                 call("n2m_s0_grid_points", H, first, cnt, bound, ptr(noise), ptr(self._pts), stream())
                 self._pcount.fill_(cnt)
                 call("n2m_s0_encode_points", pp, ptr(self._pts), None, ptr(self._pcount), self.Mcap, ptr(self.table),
@@ -739,6 +789,8 @@ class Stage0Trainer:
                 call("n2m_s0_mlp_fwd", pp, ptr(self.enc_tiles), ptr(self._pcount), self.Mcap, ptr(self.wpack), ptr(self.out),
                      None, stream())
                 call("n2m_s0_grid_update", ptr(self.out), cnt, float(decay), row.data_ptr() + 4 * first, stream())
+            if W > 1:
+                dist.all_gather_into_tensor(row, row[lo:hi].clone(), group=shard_group)
         self.mean_density = self.density_grid.clamp(min=0).mean().reshape(1)
         if self._side is not None:
             # a prefetched march on the side stream may still be reading the bitfield

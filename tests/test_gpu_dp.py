@@ -31,13 +31,13 @@ def _worker(rank, world, port, q):
     g = torch.Generator().manual_seed(rank)
     bg = torch.rand(N, 3, generator=g); noises = torch.rand(N, generator=g)
     out = {}
-    for mode in ("nccl", "peer", "nvls", "hybrid"):
+    for mode in ("nccl", "peer", "nvls"):
         tr = Stage0Trainer(Stage0Config(bound=1.0, num_rays=N, max_samples=N * 256), seed=0)     # identical replicas
         tr.set_occupancy(bits, grid)
-        if mode in ("nvls", "hybrid"):
+        if mode == "nvls":
             ok = torch.ones(1, device="cuda")
             try:
-                sync = NvlsAdam(tr, reduce="switch" if mode == "nvls" else "peer")
+                sync = NvlsAdam(tr)
             except Exception as e:      # noqa: BLE001
                 out["nvls_unavailable"] = repr(e)[:200]
                 sync = None
@@ -54,6 +54,19 @@ def _worker(rank, world, port, q):
         st = tr.export_reference_state()         # under PeerAdam this gathers the sharded fp32 colour masters itself
         out[mode] = {k: v.cpu() for k, v in st.items() if "density" not in k and v.is_floating_point() and "aabb" not in k}
         out[mode + "_loss"] = tr.read_loss()
+        if mode == "nccl":
+            # density-grid update sharded over the ranks (1/W of the cells each + all-gather) == the replicated update, bit for bit
+            g0 = tr.density_grid.clone()
+            gen = torch.Generator(device="cuda"); gen.manual_seed(1234)
+            tr.update_density_grid(generator=gen)
+            full = (tr.density_grid.clone(), tr.density_bitfield.clone(), tr.mean_density.clone())
+            tr.density_grid.copy_(g0)
+            gen.manual_seed(1234)
+            tr.update_density_grid(generator=gen, shard_group=dist.group.WORLD)
+            torch.cuda.synchronize()
+            out["density_shard_equal"] = bool(torch.equal(full[0], tr.density_grid) and torch.equal(full[1], tr.density_bitfield)
+                                              and torch.equal(full[2], tr.mean_density))
+            out["density_occupied"] = int((tr.density_grid > 0).sum().item())
         dist.barrier()
     q.put((rank, out))
     dist.barrier()
@@ -70,7 +83,7 @@ def test_peer_adam_matches_nccl_allreduce_world2():
     res = dict(q.get(timeout=600) for _ in range(2))
     [p.join(120) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
-    modes = ["peer"] + [m for m in ("nvls", "hybrid") if m in res[0]]
+    modes = ["peer"] + [m for m in ("nvls",) if m in res[0]]
     for mode in modes:
         for name in res[0][mode]:
             a0, a1 = res[0][mode][name], res[1][mode][name]
@@ -80,5 +93,6 @@ def test_peer_adam_matches_nccl_allreduce_world2():
             moved = (b0 - b0.mean()).abs().max().item()
             assert d <= 2e-3 * max(moved, 1e-6) + 1e-7, f"{name}: {mode} vs nccl differ by {d}"
         assert abs(res[0][mode + "_loss"] - res[0]["nccl_loss"]) <= 1e-3 * abs(res[0]["nccl_loss"])
+    assert res[0]["density_shard_equal"] and res[1]["density_shard_equal"] and res[0]["density_occupied"] > 0
     if "nvls" not in res[0]:
         print("NVLS path not exercised:", res[0].get("nvls_unavailable"))
