@@ -429,6 +429,7 @@ def run_ours(args):
     tr.fused_fwd = bool(args.fused_fwd)
     tr.defer_zero = bool(args.defer_zero)
     tr.prefetch_at = args.prefetch_at
+    tr.tv_in_bwd = bool(args.tv_in_bwd)
     if tr.fused_fwd:
         tr.nparts = 1
     sync, dp_used = None, args.dp
@@ -530,7 +531,12 @@ def run_ours(args):
         for s in stages:
             flush.fill_(0.0)
             a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); getattr(tr, s)(); z.record()
+            a.record()
+            if s == "bwd_fused":
+                tr.bwd_fused(tv=bool(tr.tv_in_bwd))
+            elif not (s == "tv" and tr.tv_in_bwd and tr.fused_bwd):
+                getattr(tr, s)()
+            z.record()
             torch.cuda.synchronize()
             acc[s] += a.elapsed_time(z) / reps
     M_last = int(tr.counters[1].item())
@@ -589,7 +595,7 @@ def run_ours(args):
                 "data": "synthetic",
                 "config": {"workload": workload, "rays_per_batch": NUM_RAYS, "global_rays": NUM_RAYS * world,
                            "samples_per_step": samples_total / K, "parallelism": f"dp{world}" + ("" if world == 1 else f"-{dp_used}"),
-                           "cuda_graph": not args.no_graph, "ray_range_parts": int(tr.nparts), "fused_bwd": bool(tr.fused_bwd), "fused_fwd": bool(tr.fused_fwd), "defer_zero": bool(tr.defer_zero), "prefetch_at": tr.prefetch_at,
+                           "cuda_graph": not args.no_graph, "ray_range_parts": int(tr.nparts), "fused_bwd": bool(tr.fused_bwd), "fused_fwd": bool(tr.fused_fwd), "defer_zero": bool(tr.defer_zero), "prefetch_at": tr.prefetch_at, "tv_in_bwd": bool(tr.tv_in_bwd),
                            "march_prefetch": not args.no_prefetch, **{k: v for k, v in WORKLOADS[workload].items() if k != "cap"},
                            "sample_capacity": tr.Mcap, "capacity_overflow_steps": overflow_steps, "max_samples_seen": max_m,
                            "l2": "inputs cycle over 8 batches; tables+grads+Adam state (0.6 GB touched per step) exceed the 126 MB L2"},
@@ -686,6 +692,7 @@ def main():
     ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="--impl reference: wall-clock budget of the whole CPU run")
     ap.add_argument("--skip-reference", action="store_true", help="skip the same-box reference-CUDA leg")
     ap.add_argument("--psnr-iters", type=int, default=300, help="training steps of the PSNR-vs-reference pair (0 = skip)")
+    ap.add_argument("--tv-in-bwd", type=int, default=0, help="1: the TV gradient is evaluated inside the fused backward kernel instead of by its own launch")
     ap.add_argument("--prefetch-at", default="optimizer", choices=["optimizer", "start"],
                     help="where the next batch's march is released on the side stream: under the optimizer stage or under the forward pass")
     ap.add_argument("--defer-zero", type=int, default=1, help="1: the gradient table is zeroed on a side stream under the next step instead of by the optimizer kernel")

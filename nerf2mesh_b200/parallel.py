@@ -179,10 +179,13 @@ class NvlsAdam(PeerAdam):
         R = t.rows
         self.per = per = slice_rows(R, W)
         lo, hi = min(R, r * per), min(R, (r + 1) * per)
-        try:
-            symm_mem.enable_symm_mem_for_group(pg.group_name)
-        except Exception:      # noqa: BLE001  (newer torch enables it implicitly)
-            pass
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            try:
+                symm_mem.enable_symm_mem_for_group(pg.group_name)      # needed by older torch; a deprecated no-op in newer ones
+            except Exception:      # noqa: BLE001
+                pass
 
         def sym(src):
             buf = symm_mem.empty(tuple(src.shape), dtype=src.dtype, device=dev)

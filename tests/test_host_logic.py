@@ -170,6 +170,7 @@ def test_step_orchestration_call_sequence(monkeypatch):
     tr._tv_overlap, tr._tv_stream, tr._part_streams = True, None, []
     tr._adam_stream = None
     tr.fused_bwd, tr.fused_fwd, tr.tv_fallback_points, tr._graphs = False, False, 1000, {}
+    tr.tv_in_bwd = False
 
     tv = ["n2m_s0_tv", "n2m_s0_tv_random"]
     chain = ["n2m_s0_encode_fwd_part", "n2m_s0_mlp_fwd_part", "n2m_s0_composite_loss_part", "n2m_s0_mlp_bwd_part", "n2m_s0_encode_bwd_part"]
@@ -195,6 +196,11 @@ def test_step_orchestration_call_sequence(monkeypatch):
     calls.clear(); tr.nparts = 2
     tr._compute_then_adam()
     assert names() == tv + fchain * 2 + adam
+    # ... with the TV gradient inside that launch: no TV kernel, the fallback probe behind the chains
+    calls.clear(); tr.tv_in_bwd = True
+    tr._compute_then_adam()
+    assert names() == (chain[:3] + ["n2m_s0_bwd_fused_tv_part"]) * 2 + ["n2m_s0_tv_random"] + adam
+    tr.tv_in_bwd = False
     # gather + MLP forward as one launch (whole batch only)
     calls.clear(); tr.fused_fwd, tr.nparts = True, 1
     tr._compute_then_adam()
@@ -224,3 +230,85 @@ def test_step_orchestration_call_sequence(monkeypatch):
     calls.clear(); tr.fused_bwd = False; tr.cfg.lambda_tv = 0.0
     tr._compute_then_adam()
     assert names() == chain + adam
+
+
+def test_step_prefetch_ordering(monkeypatch):
+    """step(next_batch=...): with prefetch_at == "optimizer" the step is launched as compute | optimizer with an event between them and the
+    side stream marches the next batch only after that event (and after the slot's previous reader); with "start" the step is one launch and
+    the march waits for the start mark only.  CUDA layer mocked: streams / events record what was enqueued where."""
+    import types
+    import nerf2mesh_b200.stage0 as S0
+
+    log = []
+    cur = {"s": "main"}
+
+    class FakeStream:
+        def __init__(self, name): self.name = name
+        def wait_stream(self, o): log.append((self.name, "wait_stream", o.name))
+        def wait_event(self, e): log.append((self.name, "wait_event", e.tag))
+        def synchronize(self): pass
+
+    class FakeEvent:
+        n = 0
+        def __init__(self): FakeEvent.n += 1; self.tag = None
+        def record(self, s=None):
+            self.tag = f"ev{FakeEvent.n}@{(s.name if s is not None else cur['s'])}:{len(log)}"
+            log.append((s.name if s is not None else cur["s"], "record", self.tag))
+
+    class Ctx:
+        def __init__(self, s): self.s = s
+        def __enter__(self): self.prev = cur["s"]; cur["s"] = self.s.name
+        def __exit__(self, *a): cur["s"] = self.prev; return False
+
+    streams = {"main": FakeStream("main")}
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: streams.setdefault(cur["s"], FakeStream(cur["s"])))
+    made = []
+    def mk(*a, **k):
+        s = FakeStream(f"side{len(made)}"); s.priority = k.get("priority", 0); made.append(s); streams[s.name] = s; return s
+    monkeypatch.setattr(torch.cuda, "Stream", mk)
+    monkeypatch.setattr(torch.cuda, "Event", lambda *a, **k: FakeEvent())
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: Ctx(s))
+
+    def trainer(mode):
+        tr = object.__new__(S0.Stage0Trainer)
+        tr.prefetch_at, tr.defer_zero, tr.parity, tr.cur, tr.global_step, tr.device = mode, True, 0, 0, 0, "cpu"
+        tr._prefetched, tr._side, tr._ev_done, tr._ev_march = None, None, [None, None], [None, None]
+        tr.params = S0.S0Params(); tr.params.shading_full = 1; tr.params.gt_has_alpha = 1
+        slot = types.SimpleNamespace(has_alpha=True, load=lambda *a: log.append((cur["s"], "load", None)))
+        tr.slots = [slot, slot]
+        tr._run = lambda name, fn, g: log.append((cur["s"], "run", name))
+        return tr
+
+    batch = (None,) * 4
+    # ---- optimizer mode, two consecutive steps ----
+    tr = trainer("optimizer")
+    tr.step(*batch, next_batch=batch)
+    runs = [(s, n) for s, k, n in log if k == "run"]
+    assert runs == [("main", "march"), ("main", "compute_sg"), ("main", "adam_sg"), ("side0", "march")]
+    assert made[0].priority == -1
+    i_mid = next(i for i, e in enumerate(log) if e[1] == "record" and i > log.index(("main", "run", "compute_sg")))
+    assert i_mid < log.index(("main", "run", "adam_sg"))                       # the mark sits between the two launches
+    mid_tag = log[i_mid][2]
+    i_load = log.index(("side0", "load", None))
+    i_wait_mid = log.index(("side0", "wait_event", mid_tag))
+    assert i_load < i_wait_mid < log.index(("side0", "run", "march"))          # staged at once, marched after the mark
+    assert tr._prefetched == 1 and tr.parity == 1
+    log.clear()
+    tr.step(*batch, next_batch=batch)                                          # consumes the prefetched slot: no march on main
+    runs = [(s, n) for s, k, n in log if k == "run"]
+    assert runs == [("main", "compute_sg"), ("main", "adam_sg"), ("side0", "march")]
+    assert log[0][:2] == ("main", "wait_event")                                # main waits for the prefetched march first
+    assert sum(1 for e in log if e[0] == "side0" and e[1] == "wait_event") == 3   # previous reader of the slot, start mark, mid mark
+    # ---- start mode: one launch, normal-priority stream, no mid mark ----
+    log.clear(); made.clear()
+    tr = trainer("start")
+    tr.step(*batch, next_batch=batch)
+    runs = [(s, n) for s, k, n in log if k == "run"]
+    assert runs == [("main", "march"), ("main", "compute+adam"), ("side0", "march")]
+    assert made[0].priority == 0
+    assert sum(1 for e in log if e[0] == "side0" and e[1] == "wait_event") == 1
+    # ---- no prefetch: one launch whatever the mode ----
+    log.clear()
+    tr = trainer("optimizer")
+    tr.step(*batch)
+    assert [(s, n) for s, k, n in log if k == "run"] == [("main", "march"), ("main", "compute+adam")]
