@@ -14,6 +14,12 @@
  *   n2m_interpolate_backward  its gradient w.r.t. attr [V,A] (accumulated into the caller's zero-initialised buffer)
  *   n2m_compact_covered       xyzs[mask], dirs[mask] of renderer.py:865-880 without the boolean-mask host sync: covered pixel
  *                             indices + their positions / view directions, count in *counter (device)
+ *   n2m_antialias_*           dr.antialias(color, rast, pos, tri, pos_gradient_boost=b)   (renderer.py:886-887), csrc/antialias.cu:
+ *       topology: edge -> opposing-vertex hash of the mesh (the library's "topology hash"), `keys` [slots] u64 and `opp` [2*slots] i32
+ *       caller-allocated, slots = n2m_antialias_topology_slots(F) (a power of two >= 3 F); rebuilt only when `tri` changes;
+ *       forward: out [H*W,C] = color + silhouette blends, C = 1..4, out must not alias color;
+ *       backward: grad_color [H*W,C] (may be NULL) and grad_pos [V,4] (may be NULL; ACCUMULATED into the caller's zero-initialised
+ *       buffer: gradients w.r.t. clip-space x, y, w, multiplied by pos_gradient_boost), from grad_out [H*W,C] and the forward inputs.
  */
 #ifndef N2M_B200_RASTER_H
 #define N2M_B200_RASTER_H
@@ -33,6 +39,14 @@ int n2m_interpolate_backward(const float* grad_out, const float* rast, const int
 int n2m_compact_covered(const float* rast, const float* xyz, const float* dirs, uint32_t num_pixels, uint32_t cap, int32_t* counter,
                         int32_t* pix, float* pts, float* pdirs, n2m_stream_t stream);
 
+uint32_t n2m_antialias_topology_slots(uint32_t F);
+int n2m_antialias_topology(const int32_t* tri, uint32_t F, void* keys, int32_t* opp, uint32_t slots, n2m_stream_t stream);
+int n2m_antialias_forward(const float* color, const float* rast, const float* pos, const int32_t* tri, const void* keys, const int32_t* opp,
+                          uint32_t slots, uint32_t H, uint32_t W, uint32_t C, float* out, n2m_stream_t stream);
+int n2m_antialias_backward(const float* color, const float* rast, const float* pos, const int32_t* tri, const void* keys, const int32_t* opp,
+                           uint32_t slots, uint32_t H, uint32_t W, uint32_t C, const float* grad_out, float pos_gradient_boost,
+                           float* grad_color, float* grad_pos, n2m_stream_t stream);
+
 /* ---- stage-1 texture-MLP step (csrc/stage1.cu; host side nerf2mesh_b200/stage1.py) ----
  * n2m_s1_points: covered pixels of `rast` [h,w,4] -> compacted surface points for the stage-0 gather / MLP / backward kernels:
  *   pts [cap,3] = dr.interpolate(vertices, rast, tri) at the covered pixels, pdirs [cap,3] = rays_d [h/ssaa * w/ssaa, 3] up-sampled
@@ -45,6 +59,18 @@ int n2m_s1_points(const float* rast, const float* verts, const int32_t* tri, con
 int n2m_s1_loss(const void* out, const int32_t* inv, const float* gt, uint32_t gt_channels, const float* bg, uint32_t h0, uint32_t w0,
                 uint32_t ssaa, float lambda_mask, const float* loss_scale, void* dout, float* image, float* weights_sum, float* loss_out,
                 n2m_stream_t stream);
+
+
+/* antialiased variant of the step (renderer.py:881-907 with dr.antialias): n2m_s1_rgba scatters the per-point colours `out` [cap] float4
+ * (sigma, r, g, b) into rgba [h*w] float4 = (r, g, b, mask) (zero where uncovered); after n2m_antialias_forward (C = 4),
+ * n2m_s1_loss_aa evaluates clamp, alphas * rgbs, the ssaa average, the background mix and the loss of n2m_s1_loss on the antialiased
+ * image aa [h*w] float4 and writes d_aa = d loss / d aa * loss_scale; after n2m_antialias_backward, n2m_s1_dout gathers the colour
+ * part of the image gradient into dout [cap] float4 = (0, dr, dg, db) for the covered pixels. */
+int n2m_s1_rgba(const void* out, const int32_t* inv, uint32_t num_pixels, void* rgba, n2m_stream_t stream);
+int n2m_s1_loss_aa(const void* aa, const float* gt, uint32_t gt_channels, const float* bg, uint32_t h0, uint32_t w0, uint32_t ssaa,
+                   float lambda_mask, const float* loss_scale, void* d_aa, float* image, float* weights_sum, float* loss_out,
+                   n2m_stream_t stream);
+int n2m_s1_dout(const void* grad_rgba, const int32_t* inv, uint32_t num_pixels, void* dout, n2m_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -7,8 +7,10 @@ MLPs (`self.rgb`, network.py:170-189) on the covered pixels with the tensor-core
 super-samples, mix the background, MSE loss, backward into color_net / specular_net / encoder_color, Adam.  It shares
 the model state (hash tables, MLP weights, optimizer moments, GradScaler state) with a Stage0Trainer.
 
-Not built (DESIGN.md "stage 1"): dr.antialias (renderer.py:886-887) and therefore the gradient to the vertex offsets, the mesh
-regularisers (utils.py:750-790) and re-meshing (`refine_and_decimate`): vertices are fixed here.
+`antialias=True` inserts dr.antialias on (rgbs, alphas) as the reference does (renderer.py:886-887; csrc/antialias.cu) and leaves the
+image-loss gradient w.r.t. the vertices in `vertex_gradient()` -- the quantity the reference's vertex optimizer consumes.
+Not built (DESIGN.md "stage 1"): the vertex optimizer itself with its mesh regularisers (utils.py:750-790) and re-meshing
+(`refine_and_decimate`): vertices are fixed here.
 """
 import ctypes
 
@@ -22,11 +24,14 @@ from .stage0 import S0Params
 _lib.register({
     "n2m_s1_points": [P, P, P, P, U, U, U, U, P, P, P, P, P, P],
     "n2m_s1_loss": [P, P, P, U, P, U, U, U, F, P, P, P, P, P, P],
+    "n2m_s1_rgba": [P, P, U, P, P],
+    "n2m_s1_loss_aa": [P, P, U, P, U, U, U, F, P, P, P, P, P, P],
+    "n2m_s1_dout": [P, P, U, P, P],
 })
 
 
 class Stage1Trainer:
-    def __init__(self, t0, vertices, triangles, h0, w0, ssaa=2, max_points=None, lambda_mask=0.1):
+    def __init__(self, t0, vertices, triangles, h0, w0, ssaa=2, max_points=None, lambda_mask=0.1, antialias=False, pos_gradient_boost=1.0):
         assert ssaa in (1, 2), "the ssaa average equals the reference's bilinear down-scale only at factors 1 and 2"
         self.t0 = t0
         dev = t0.device
@@ -49,6 +54,15 @@ class Stage1Trainer:
         self.image = torch.zeros(Q, 3, device=dev); self.weights_sum = torch.zeros(Q, device=dev)
         self.loss_acc = torch.zeros(4, device=dev)
         self.rast = None
+        self.antialias = bool(antialias)
+        self.pos_gradient_boost = float(pos_gradient_boost)
+        if self.antialias:
+            self.topology = dr.TopologyHash(self.triangles)               # once per mesh
+            self.rgba = torch.zeros(n, 4, device=dev); self.aa = torch.zeros(n, 4, device=dev)
+            self.d_aa = torch.zeros(n, 4, device=dev); self.g_rgba = torch.zeros(n, 4, device=dev)
+            self.grad_vclip = torch.zeros(self.vertices.shape[0], 4, device=dev)
+        self.vclip = None
+        self.mvp = None
         self.params = S0Params()
         ctypes.memmove(ctypes.byref(self.params), ctypes.byref(t0.params), ctypes.sizeof(S0Params))
         self.params.lambda_specular = 0.0          # the specular regulariser is a stage-0 loss (utils.py:726,735-738)
@@ -62,19 +76,36 @@ class Stage1Trainer:
         t0 = self.t0
         self.params.shading_full = int(shading == "full")
         mvp = mvp.to(t0.device, torch.float32)
-        vclip = torch.nn.functional.pad(self.vertices, (0, 1), value=1.0) @ mvp.T           # renderer.py:858
+        vclip = (torch.nn.functional.pad(self.vertices, (0, 1), value=1.0) @ mvp.T).contiguous()           # renderer.py:858
+        self.vclip, self.mvp = vclip, mvp
         self.rast, _ = dr.rasterize(self.glctx, vclip[None], self.triangles, (self.h, self.w))
         call("n2m_s1_points", ptr(self.rast), ptr(self.vertices), ptr(self.triangles), ptr(rays_d), self.h, self.w, self.ssaa, self.cap,
              ptr(self.counters), ptr(self.inv), ptr(self.pts), ptr(self.pdirs), ptr(self.recs), stream())
         call("n2m_s0_encode_points", self._pp(), ptr(self.pts), ptr(self.pdirs), ptr(self.counters), self.cap, ptr(t0.table),
              ptr(t0.offsets), ptr(self.enc_tiles), stream())
         call("n2m_s0_mlp_fwd", self._pp(), ptr(self.enc_tiles), ptr(self.counters), self.cap, ptr(t0.wpack), ptr(self.out), None, stream())
+        if self.antialias:
+            n = self.h * self.w
+            th = self.topology
+            call("n2m_s1_rgba", ptr(self.out), ptr(self.inv), n, ptr(self.rgba), stream())
+            call("n2m_antialias_forward", ptr(self.rgba), ptr(self.rast), ptr(self.vclip), ptr(self.triangles), ptr(th.keys), ptr(th.opp),
+                 th.slots, self.h, self.w, 4, ptr(self.aa), stream())
 
     def loss_backward(self, gt, bg):
         t0 = self.t0
         self.loss_acc.zero_()
-        call("n2m_s1_loss", ptr(self.out), ptr(self.inv), ptr(gt), gt.shape[-1], ptr(bg), self.h0, self.w0, self.ssaa, self.lambda_mask,
-             ptr(t0.opt_state), ptr(self.dout), ptr(self.image), ptr(self.weights_sum), ptr(self.loss_acc), stream())
+        if self.antialias:
+            n = self.h * self.w
+            th = self.topology
+            call("n2m_s1_loss_aa", ptr(self.aa), ptr(gt), gt.shape[-1], ptr(bg), self.h0, self.w0, self.ssaa, self.lambda_mask,
+                 ptr(t0.opt_state), ptr(self.d_aa), ptr(self.image), ptr(self.weights_sum), ptr(self.loss_acc), stream())
+            self.grad_vclip.zero_()
+            call("n2m_antialias_backward", ptr(self.rgba), ptr(self.rast), ptr(self.vclip), ptr(self.triangles), ptr(th.keys), ptr(th.opp),
+                 th.slots, self.h, self.w, 4, ptr(self.d_aa), self.pos_gradient_boost, ptr(self.g_rgba), ptr(self.grad_vclip), stream())
+            call("n2m_s1_dout", ptr(self.g_rgba), ptr(self.inv), n, ptr(self.dout), stream())
+        else:
+            call("n2m_s1_loss", ptr(self.out), ptr(self.inv), ptr(gt), gt.shape[-1], ptr(bg), self.h0, self.w0, self.ssaa, self.lambda_mask,
+                 ptr(t0.opt_state), ptr(self.dout), ptr(self.image), ptr(self.weights_sum), ptr(self.loss_acc), stream())
         if t0.fused_bwd:
             call("n2m_s0_bwd_fused_part", self._pp(), ptr(self.enc_tiles), ptr(self.dout), ptr(self.recs), ptr(self.counters), self.cap,
                  ptr(self.pts), ptr(self.pdirs), ptr(t0.wpack), ptr(t0.offsets), ptr(t0.gtables[t0.parity]), ptr(t0.g_mlp),
@@ -96,6 +127,13 @@ class Stage1Trainer:
         self.loss_backward(gt.contiguous(), bg.contiguous())
         t0.adam()
         t0.global_step += 1
+
+    def vertex_gradient(self):
+        """d loss / d vertices [V,3] of the last `loss_backward` (through dr.antialias and the projection of renderer.py:858; the
+        gradient the reference accumulates on `vertices_offsets`), unscaled.  Valid when the step's found_inf flag is clear."""
+        if not self.antialias:
+            raise RuntimeError("vertex gradients flow through dr.antialias only: construct Stage1Trainer(antialias=True)")
+        return (self.grad_vclip @ self.mvp[:, :3]) / self.t0.opt_state[0]
 
     def read_loss(self):
         return float(self.loss_acc[0].item())

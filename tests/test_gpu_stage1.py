@@ -2,7 +2,8 @@
 kernels) against the reference's render_stage1 arithmetic composed from the UNMODIFIED reference model (`NeRFNetwork.rgb`,
 network.py:170-189, over the reference's grid-encoder kernels) and torch ops, following nerf/renderer.py:824-907 and
 nerf/utils.py:703-712 line by line -- with this repo's rasterize / interpolate standing in for nvdiffrast (itself checked against the
-CPU oracle in test_gpu_raster.py) and without dr.antialias (not built)."""
+CPU oracle in test_gpu_raster.py), without dr.antialias and with this repo's antialias (csrc/antialias.cu, checked against its CPU oracle
+in test_gpu_antialias.py) in the place of the library's, including the image-loss gradient it sends to the vertices."""
 import numpy as np
 import pytest
 import torch
@@ -18,7 +19,7 @@ from oracle import raster_oracle as R
 pytestmark = pytest.mark.gpu
 
 
-def _setup(h0=96, w0=96, ssaa=2, steps=30):
+def _setup(h0=96, w0=96, ssaa=2, steps=30, antialias=False):
     N = 1024
     cfg = Stage0Config(bound=1.0, num_rays=N, max_samples=N * 256)
     t0 = Stage0Trainer(cfg, seed=5)
@@ -38,13 +39,13 @@ def _setup(h0=96, w0=96, ssaa=2, steps=30):
     # flip y in the projection (as the reference's provider does in its mvp)
     mvp = R.perspective_mvp(cam, fovy=2 * np.arctan(0.5 * h0 / intr[1]), aspect=w0 / h0)
     mvp[1] *= -1
-    s1 = Stage1Trainer(t0, torch.from_numpy(v), torch.from_numpy(f), h0, w0, ssaa=ssaa)
+    s1 = Stage1Trainer(t0, torch.from_numpy(v), torch.from_numpy(f), h0, w0, ssaa=ssaa, antialias=antialias)
     gt = torch.rand(h0 * w0, 4, generator=g); gt[:, 3] = (gt[:, 3] > 0.5).float()
     bg = torch.rand(h0 * w0, 3, generator=g)
     return t0, s1, torch.from_numpy(mvp), rays_d.cuda(), gt.cuda(), bg.cuda()
 
 
-def _reference_stage1(ns, ref_stage, t0, s1, mvp, rays_d, gt, bg, lambda_mask=0.1):
+def _reference_stage1(ns, ref_stage, t0, s1, mvp, rays_d, gt, bg, lambda_mask=0.1, antialias=False):
     """render_stage1 (renderer.py:824-907) + the stage-1 loss (utils.py:703-712) with the unmodified reference model"""
     opt = ref_stage.default_opt(bound=1.0, dt_gamma=0.0, adaptive_num_rays=False)
     model = ns.make_model(opt)
@@ -55,7 +56,7 @@ def _reference_stage1(ns, ref_stage, t0, s1, mvp, rays_d, gt, bg, lambda_mask=0.
     dirs = rays_d.view(h0, w0, 3)
     dirs = F.interpolate(dirs.permute(2, 0, 1)[None], (h, w), mode="nearest")[0].permute(1, 2, 0).reshape(-1, 3).contiguous()   # scale_img_hwc(mag='nearest')
     dirs = dirs / torch.sqrt(torch.clamp((dirs * dirs).sum(-1, keepdim=True), min=1e-20))
-    vertices = s1.vertices
+    vertices = s1.vertices.clone().requires_grad_(antialias)        # the leaf standing in for self.vertices + self.vertices_offsets
     vclip = torch.matmul(F.pad(vertices, pad=(0, 1), mode="constant", value=1.0), torch.transpose(mvp.cuda(), 0, 1)).float().unsqueeze(0)
     glctx = dr.RasterizeCudaContext()
     rast, _ = dr.rasterize(glctx, vclip, s1.triangles, (h, w))
@@ -69,7 +70,11 @@ def _reference_stage1(ns, ref_stage, t0, s1, mvp, rays_d, gt, bg, lambda_mask=0.
     rgbs[mask_flatten] = mask_rgbs.float()
     rgbs = rgbs.view(1, h, w, 3)
     alphas = mask.float()
-    alphas = alphas.squeeze(0).clamp(0, 1); rgbs = rgbs.squeeze(0).clamp(0, 1)         # dr.antialias omitted on both sides
+    if antialias:          # renderer.py:886-887
+        alphas = dr.antialias(alphas, rast, vclip, s1.triangles, pos_gradient_boost=1.0).squeeze(0).clamp(0, 1)
+        rgbs = dr.antialias(rgbs, rast, vclip, s1.triangles, pos_gradient_boost=1.0).squeeze(0).clamp(0, 1)
+    else:
+        alphas = alphas.squeeze(0).clamp(0, 1); rgbs = rgbs.squeeze(0).clamp(0, 1)         # dr.antialias omitted on both sides
     image = alphas * rgbs
     T = 1 - alphas
 
@@ -88,18 +93,19 @@ def _reference_stage1(ns, ref_stage, t0, s1, mvp, rays_d, gt, bg, lambda_mask=0.
     scaler.scale(loss).backward()
     inv = 1.0 / float(t0.opt_state[0].item())
     grads = {n: p.grad * inv for n, p in model.named_parameters() if p.grad is not None}
-    return dict(image=image.view(-1, 3).detach(), ws=ws.detach(), loss=float(loss), grads=grads, covered=int(mask_flatten.sum()), rast=rast)
+    return dict(image=image.view(-1, 3).detach(), ws=ws.detach(), loss=float(loss), grads=grads, covered=int(mask_flatten.sum()), rast=rast,
+                grad_vertices=None if vertices.grad is None else vertices.grad * inv)
 
 
-@pytest.mark.parametrize("ssaa", [2, 1])
-def test_stage1_step_matches_reference_composition(ssaa):
+@pytest.mark.parametrize("ssaa,antialias", [(2, False), (1, False), (2, True), (1, True)])
+def test_stage1_step_matches_reference_composition(ssaa, antialias):
     from oracle import ref_stage
     if not ref_stage.staged():
         pytest.skip("reference Python files not staged")
     ns = ref_stage.load("ref")
-    t0, s1, mvp, rays_d, gt, bg = _setup(ssaa=ssaa)
+    t0, s1, mvp, rays_d, gt, bg = _setup(ssaa=ssaa, antialias=antialias)
     t0.opt_state[0] = 4096.0
-    ref = _reference_stage1(ns, ref_stage, t0, s1, mvp, rays_d, gt, bg)
+    ref = _reference_stage1(ns, ref_stage, t0, s1, mvp, rays_d, gt, bg, antialias=antialias)
     t0.gtable.zero_(); t0.g_mlp.zero_()
     s1.forward(mvp, rays_d)
     s1.loss_backward(gt, bg)
@@ -107,7 +113,14 @@ def test_stage1_step_matches_reference_composition(ssaa):
     assert s1.counters[2].item() == 0 and s1.counters[1].item() == ref["covered"] and ref["covered"] > 0.1 * s1.h * s1.w
     assert torch.equal(s1.rast, ref["rast"])
     assert (s1.image - ref["image"]).abs().max().item() <= 2e-3
-    assert (s1.weights_sum - ref["ws"]).abs().max().item() <= 1e-6
+    assert (s1.weights_sum - ref["ws"]).abs().max().item() <= (1e-5 if antialias else 1e-6)
+    if antialias:
+        # the silhouette pixels changed, and the loss reaches the vertices through them (the reference's only path to vertices_offsets)
+        assert ((s1.aa[:, 3] - s1.rgba[:, 3]).abs() > 1e-3).sum().item() > 30
+        gv, rv = s1.vertex_gradient().double().flatten(), ref["grad_vertices"].double().flatten()
+        assert rv.abs().max().item() > 0
+        cos = (torch.dot(gv, rv) / (gv.norm() * rv.norm() + 1e-300)).item()
+        assert cos > 0.999 and ((gv - rv).norm() / rv.norm()).item() <= 3e-2, (cos, ((gv - rv).norm() / rv.norm()).item())
     assert abs(s1.read_loss() - ref["loss"]) <= 1e-3 * abs(ref["loss"])
     g = t0.export_reference_grads()
     assert t0.opt_state[3].item() == 0
