@@ -429,7 +429,6 @@ def run_ours(args):
     tr.fused_fwd = bool(args.fused_fwd)
     tr.defer_zero = bool(args.defer_zero)
     tr.prefetch_at = args.prefetch_at
-    tr.tv_in_bwd = bool(args.tv_in_bwd)
     if tr.fused_fwd:
         tr.nparts = 1
     sync, dp_used = None, args.dp
@@ -531,12 +530,7 @@ def run_ours(args):
         for s in stages:
             flush.fill_(0.0)
             a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            if s == "bwd_fused":
-                tr.bwd_fused(tv=bool(tr.tv_in_bwd))
-            elif not (s == "tv" and tr.tv_in_bwd and tr.fused_bwd):
-                getattr(tr, s)()
-            z.record()
+            a.record(); getattr(tr, s)(); z.record()
             torch.cuda.synchronize()
             acc[s] += a.elapsed_time(z) / reps
     M_last = int(tr.counters[1].item())
@@ -595,7 +589,7 @@ def run_ours(args):
                 "data": "synthetic",
                 "config": {"workload": workload, "rays_per_batch": NUM_RAYS, "global_rays": NUM_RAYS * world,
                            "samples_per_step": samples_total / K, "parallelism": f"dp{world}" + ("" if world == 1 else f"-{dp_used}"),
-                           "cuda_graph": not args.no_graph, "ray_range_parts": int(tr.nparts), "fused_bwd": bool(tr.fused_bwd), "fused_fwd": bool(tr.fused_fwd), "defer_zero": bool(tr.defer_zero), "prefetch_at": tr.prefetch_at, "tv_in_bwd": bool(tr.tv_in_bwd),
+                           "cuda_graph": not args.no_graph, "ray_range_parts": int(tr.nparts), "fused_bwd": bool(tr.fused_bwd), "fused_fwd": bool(tr.fused_fwd), "defer_zero": bool(tr.defer_zero), "prefetch_at": tr.prefetch_at,
                            "march_prefetch": not args.no_prefetch, **{k: v for k, v in WORKLOADS[workload].items() if k != "cap"},
                            "sample_capacity": tr.Mcap, "capacity_overflow_steps": overflow_steps, "max_samples_seen": max_m,
                            "l2": "inputs cycle over 8 batches; tables+grads+Adam state (0.6 GB touched per step) exceed the 126 MB L2"},
@@ -627,7 +621,7 @@ def run_stage1(args):
     h0 = w0 = 800
     t0 = Stage0Trainer(Stage0Config(bound=1.0, num_rays=1024, max_samples=1024 * 128), seed=0)
     v, f = R.icosphere(7)                                         # 327 680 faces ~ the reference's decimate target 3e5 (main.py:101)
-    s1 = Stage1Trainer(t0, torch.from_numpy(v), torch.from_numpy(f), h0, w0, ssaa=2)
+    s1 = Stage1Trainer(t0, torch.from_numpy(v), torch.from_numpy(f), h0, w0, ssaa=2, antialias=bool(args.antialias))
     g = torch.Generator().manual_seed(0)
     views = []
     for k in range(8):
@@ -668,12 +662,30 @@ def run_stage1(args):
         dr.rasterize(glctx, vclip[None], s1.triangles, (s1.h, s1.w))
     q1.record()
     torch.cuda.synchronize()
+    aa_ms = None
+    if s1.antialias:          # the antialias operator alone (4 channels): forward, backward (colour + vertex gradients)
+        th = s1.topology
+        from nerf2mesh_b200._lib import call, ptr, stream
+        a0, a1, a2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        a0.record()
+        for it in range(10):
+            call("n2m_antialias_forward", ptr(s1.rgba), ptr(s1.rast), ptr(s1.vclip), ptr(s1.triangles), ptr(th.keys), ptr(th.opp), th.slots, s1.h, s1.w, 4,
+                 ptr(s1.aa), stream())
+        a1.record()
+        for it in range(10):
+            call("n2m_antialias_backward", ptr(s1.rgba), ptr(s1.rast), ptr(s1.vclip), ptr(s1.triangles), ptr(th.keys), ptr(th.opp), th.slots, s1.h, s1.w, 4,
+                 ptr(s1.d_aa), 1.0, ptr(s1.g_rgba), ptr(s1.grad_vclip), stream())
+        a2.record()
+        torch.cuda.synchronize()
+        aa_ms = {"forward": a0.elapsed_time(a1) / 10, "backward": a1.elapsed_time(a2) / 10,
+                 "blended_pixels": int(((s1.aa - s1.rgba).abs().amax(1) > 0).sum().item())}
     hi = s1.h * s1.w
     line = {"metric": "pixels/sec (stage-1 texture step: rasterize + interpolate + colour MLPs fwd/bwd + Adam)",
             "value": hi / (ms * 1e-3), "unit": "super-sampled pixels/s", "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
             "config": {"workload": "lego_stage1", "mesh_faces": int(f.shape[0]), "image": [h0, w0], "ssaa": 2, "raster": [s1.h, s1.w],
-                       "covered_pixels_per_step": cov.item() / K, "antialias": False},
+                       "covered_pixels_per_step": cov.item() / K, "antialias": bool(s1.antialias)},
+            "antialias_ms": aa_ms,
             "rasterize_ms": q0.elapsed_time(q1) / 10, "rasterize_pixels_per_s": hi / (q0.elapsed_time(q1) / 10 * 1e-3),
             "forward_ms": r0.elapsed_time(r1) / 10}
     print(json.dumps(line))
@@ -692,7 +704,7 @@ def main():
     ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="--impl reference: wall-clock budget of the whole CPU run")
     ap.add_argument("--skip-reference", action="store_true", help="skip the same-box reference-CUDA leg")
     ap.add_argument("--psnr-iters", type=int, default=300, help="training steps of the PSNR-vs-reference pair (0 = skip)")
-    ap.add_argument("--tv-in-bwd", type=int, default=0, help="1: the TV gradient is evaluated inside the fused backward kernel instead of by its own launch")
+    ap.add_argument("--antialias", type=int, default=1, help="lego_stage1: 1 = dr.antialias on (rgbs, alphas) as the reference does (renderer.py:886-887)")
     ap.add_argument("--prefetch-at", default="optimizer", choices=["optimizer", "start"],
                     help="where the next batch's march is released on the side stream: under the optimizer stage or under the forward pass")
     ap.add_argument("--defer-zero", type=int, default=1, help="1: the gradient table is zeroed on a side stream under the next step instead of by the optimizer kernel")

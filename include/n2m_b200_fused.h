@@ -211,14 +211,6 @@ int n2m_s0_set_fused_debug(int mode);
 int n2m_s0_bwd_fused_part(const n2m_s0_params* p, const void* enc_tiles, const void* dout, const void* recs, const int32_t* counters,
                           uint32_t Mcap, const float* rays_o, const float* rays_d, const void* wpack, const int32_t* offsets,
                           void* gtable, float* g_mlp, float* loss_scale, uint32_t part, uint32_t nparts, n2m_stream_t stream);
-/* the same + the total-variation gradient of the density table at this part's samples (GridEncoder.grad_total_variation over
- * Trainer.post_train_step's tmp_xyzs, grid.py:170-192, utils.py:801-823; replaces n2m_s0_tv as well): the scatter warps read the seven
- * neighbouring density features of every sample's base cell from `table` and fold lambda/6 * sum(delta) * rsqrt(sum(delta^2) + 1e-9)
- * into the RED of corner 0.  counters[3] / counters[15] receive the inner / outer sample counts n2m_s0_tv_random looks at. */
-int n2m_s0_bwd_fused_tv_part(const n2m_s0_params* p, const void* enc_tiles, const void* dout, const void* recs, int32_t* counters,
-                             uint32_t Mcap, const float* rays_o, const float* rays_d, const void* wpack, const int32_t* offsets,
-                             const void* table, void* gtable, float* g_mlp, float* loss_scale, uint32_t part, uint32_t nparts,
-                             n2m_stream_t stream);
 
 /* optimizer state block (device, float[8]): [0] loss_scale, [1] growth_tracker, [2] adam step t,
  * [3] found_inf, [4] lr (host-written each step), [5] 1-beta1^t, [6] sqrt(1-beta2^t), [7] 1/loss_scale.

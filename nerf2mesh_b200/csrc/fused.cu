@@ -63,13 +63,8 @@ __device__ __forceinline__ LevelConst make_level_const(const int32_t* __restrict
 }
 
 // ---- scatter of one tile by one warp: rows [32 * sg, 32 * sg + 32) of the tile, levels lq, lq + 4, lq + 8, lq + 12 ----
-// TV: the total-variation gradient of the density table (gridencoder.cu:506-609 over the step's samples, utils.py:801-823) is evaluated
-// here as well: every lane adds tvw * sum(delta) * rsqrt(sum(delta^2) + 1e-9) of its base cell to corner 0's density gradient (the same
-// row the stand-alone TV kernel adds to) before the runs are merged -- seven table loads per lane and level, no extra RED.
-template <bool TV>
 __device__ __forceinline__ void scatter_levels(const LevelConst* __restrict__ lc, uint32_t lq, const Sample& s, bool active,
-                                               const uint8_t* __restrict__ row, float4* __restrict__ gtable, uint32_t lane, bool no_red,
-                                               const TableEntry* __restrict__ table, float tvw) {
+                                               const uint8_t* __restrict__ row, float4* __restrict__ gtable, uint32_t lane, bool no_red) {
 #pragma unroll 1
     for (uint32_t i = 0; i < 4; ++i) {
         const uint32_t l = lq + 4 * i;
@@ -97,49 +92,15 @@ __device__ __forceinline__ void scatter_levels(const LevelConst* __restrict__ lc
         }
         const float wx[2] = {1 - fx, fx}, wy[2] = {1 - fy, fy}, wz[2] = {1 - fz, fz};
         uint32_t rowi[8];
+        float vd[8], v0[8], v1[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const int ix = k & 1, iy = (k >> 1) & 1, iz = (k >> 2) & 1;
             const uint32_t raw = hashed ? (xs[ix] ^ ys[iy] ^ zs[iz]) : (xs[ix] + ys[iy] + zs[iz]);
             rowi[k] = wrap_row(raw, L.rows, pow2);
-        }
-        float tvg = 0.f;
-        if (TV && tvw != 0.f) {
-            // neighbours of the base cell: +1 along an axis = corners 1, 2, 4; -1 = one stride / hash step back
-            uint32_t lx, ly, lz;
-            if (hashed) {
-                lx = (x0 - 1u) ^ ys[0] ^ zs[0];
-                ly = xs[0] ^ (ys[0] - 2654435761u) ^ zs[0];
-                lz = xs[0] ^ ys[0] ^ (zs[0] - 805459861u);
-            } else {
-                lx = xs[0] - L.mx + ys[0] + zs[0];
-                ly = xs[0] + ys[0] - L.my + zs[0];
-                lz = xs[0] + ys[0] + zs[0] - L.mz;
-            }
-            const TableEntry* tab = table + L.row0;
-            const float centre = __ldg(&tab[rowi[0]].d);
-            const float rv[3] = {__ldg(&tab[rowi[1]].d), __ldg(&tab[rowi[2]].d), __ldg(&tab[rowi[4]].d)};
-            const uint32_t base[3] = {x0, y0, z0};
-            const uint32_t lrow[3] = {wrap_row(lx, L.rows, pow2), wrap_row(ly, L.rows, pow2), wrap_row(lz, L.rows, pow2)};
-            float lv[3];
-#pragma unroll
-            for (int d = 0; d < 3; ++d) lv[d] = base[d] > 0 ? __ldg(&tab[lrow[d]].d) : 0.f;
-            float sum = 0.f, sq = 0.f;
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                if (base[d] < L.res) { const float dv = centre - rv[d]; sum += dv; sq += dv * dv; }
-                if (base[d] > 0) { const float dv = centre - lv[d]; sum += dv; sq += dv * dv; }
-            }
-            tvg = tvw * sum * rsqrtf(sq + 1e-9f);
-        }
-        float vd[8], v0[8], v1[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int ix = k & 1, iy = (k >> 1) & 1, iz = (k >> 2) & 1;
             const float w = wx[ix] * wy[iy] * wz[iz];
             vd[k] = w * gd; v0[k] = w * g0; v1[k] = w * g1;
         }
-        vd[0] += tvg;
         float4* gt = gtable + L.row0;
         // runs of consecutive lanes in the same cell: sum them first, the last lane of a run issues the REDs
         const uint32_t key = active ? (x0 | (y0 << 10) | (z0 << 20)) : 0xffffffffu;
@@ -171,13 +132,12 @@ __device__ __forceinline__ void scatter_levels(const LevelConst* __restrict__ lc
     }
 }
 
-template <bool TV>
 __global__ void __launch_bounds__(kFusedThreads, 1)
 k_s0_bwd_fused(n2m_s0_params p, const uint8_t* __restrict__ enc_tiles, const float4* __restrict__ dout,
                const float4* __restrict__ recs, const int32_t* __restrict__ counters, const float* __restrict__ rays_o,
                const float* __restrict__ rays_d, const uint8_t* __restrict__ wpack, const int32_t* __restrict__ offsets,
                float4* __restrict__ gtable, float* __restrict__ g_mlp, float* __restrict__ loss_scale, uint32_t part, uint32_t nparts,
-               uint32_t dbg, const TableEntry* __restrict__ table) {
+               uint32_t dbg) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar_mma, bar_tma, bar_full[2], bar_empty[2];
     __shared__ uint32_t tmem_s;
@@ -232,30 +192,12 @@ k_s0_bwd_fused(n2m_s0_params p, const uint8_t* __restrict__ enc_tiles, const flo
             const uint32_t r = sg * 32 + lane;
             const uint32_t j = tile * kTile + r;
             Sample s;
-            const bool mine = j >= pr.lo && j < pr.hi;
-            bool active = mine;
+            bool active = j >= pr.lo && j < pr.hi;
             if (active) {
                 s = sample_of(recs[j], rays_o, rays_d, p);
                 active = !((s.u < 0 || s.u > 1) || (s.v < 0 || s.v > 1) || (s.w < 0 || s.w > 1));
             } else {
                 s.x = s.y = s.z = s.u = s.v = s.w = 0.5f; s.dx = s.dy = s.dz = 0.f;
-            }
-            float tvw = 0.f;
-            if (TV) {
-                // TV weight: lambda inside the unit cube, 10 lambda outside when bound > 1 (utils.py:815-821), loss-scaled domain;
-                // + how many samples each of the reference's TV calls would receive (the random-point fallback looks at these)
-                const float mag = fmaxf(fabsf(s.x), fmaxf(fabsf(s.y), fabsf(s.z)));
-                const bool outer = p.grid_bound > 1 && mag > 1;
-                const float lam = outer ? p.lambda_tv * 10 : p.lambda_tv;
-                tvw = active ? lam / 6 * loss_scale[0] : 0.f;
-                if (lq == 0) {
-                    const uint32_t m_out = __ballot_sync(0xffffffffu, mine && outer), m_in = __ballot_sync(0xffffffffu, mine && !outer);
-                    if (lane == 0) {
-                        int32_t* tv_counts = const_cast<int32_t*>(counters);
-                        if (m_in) atomicAdd(tv_counts + 3, (int)__popc(m_in));
-                        if (m_out) atomicAdd(tv_counts + 15, (int)__popc(m_out));
-                    }
-                }
             }
             tc::mbar_wait(&bar_full[buf], use & 1);
             const uint8_t* row = sD + buf * D_BYTES + r * 16;
@@ -275,7 +217,7 @@ k_s0_bwd_fused(n2m_s0_params p, const uint8_t* __restrict__ enc_tiles, const flo
                 }
                 if (bad) loss_scale[3] = 1.f;
             }
-            scatter_levels<TV>(s_lc, lq, s, active, row, gtable, lane, (dbg & 1u) != 0, table, tvw);
+            scatter_levels(s_lc, lq, s, active, row, gtable, lane, (dbg & 1u) != 0);
             __syncwarp();
             if (lane == 0) mbar_arrive1(&bar_empty[buf]);          // the image of this tile is no longer needed by this warp
         }
@@ -740,29 +682,11 @@ extern "C" {
 int n2m_s0_set_fused_debug(int mode) { g_fused_dbg = (uint32_t)mode; return 0; }
 
 int n2m_s0_fused_init(void) {
-    cudaError_t e = cudaFuncSetAttribute(k_s0_bwd_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FB_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_s0_bwd_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FB_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(k_s0_bwd_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FB_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_s0_fwd_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FF_BYTES);
     if (e != cudaSuccess) return fail("s0_fused_init", cudaGetErrorString(e));
     fused_num_sms();
     return 0;
-}
-
-static int bwd_fused_launch(const n2m_s0_params* p, const void* enc_tiles, const void* dout, const void* recs, const int32_t* counters,
-                            uint32_t Mcap, const float* rays_o, const float* rays_d, const void* wpack, const int32_t* offsets,
-                            void* gtable, float* g_mlp, float* loss_scale, uint32_t part, uint32_t nparts, const void* table, n2m_stream_t stream) {
-    N2M_REQUIRE(p && enc_tiles && dout && recs && counters && rays_o && rays_d && wpack && offsets && gtable && g_mlp && loss_scale,
-                "s0_bwd_fused", "null pointer");
-    N2M_REQUIRE(p->num_levels == kLevels, "s0_bwd_fused", "fused path supports num_levels == 16");
-    N2M_REQUIRE(Mcap % kTile == 0 && Mcap > 0, "s0_bwd_fused", "Mcap must be a positive multiple of 128");
-    N2M_REQUIRE(valid_parts(part, nparts), "s0_bwd_fused", "nparts must be 1, 2, 4 or 8 and part < nparts");
-    const uint32_t grid = min(Mcap / kTile, (uint32_t)fused_num_sms());
-    auto kern = (table && p->lambda_tv > 0) ? k_s0_bwd_fused<true> : k_s0_bwd_fused<false>;
-    kern<<<grid, kFusedThreads, FB_BYTES, as_stream(stream)>>>(
-        *p, static_cast<const uint8_t*>(enc_tiles), static_cast<const float4*>(dout), static_cast<const float4*>(recs), counters,
-        rays_o, rays_d, static_cast<const uint8_t*>(wpack), offsets, static_cast<float4*>(gtable), g_mlp, loss_scale, part, nparts, g_fused_dbg,
-        static_cast<const TableEntry*>(table));
-    return check_launch("s0_bwd_fused");
 }
 
 /* MLP backward + hash-grid scatter of one part of the batch in one persistent launch (replaces n2m_s0_mlp_bwd_part followed by
@@ -770,20 +694,16 @@ static int bwd_fused_launch(const n2m_s0_params* p, const void* enc_tiles, const
 int n2m_s0_bwd_fused_part(const n2m_s0_params* p, const void* enc_tiles, const void* dout, const void* recs, const int32_t* counters,
                           uint32_t Mcap, const float* rays_o, const float* rays_d, const void* wpack, const int32_t* offsets,
                           void* gtable, float* g_mlp, float* loss_scale, uint32_t part, uint32_t nparts, n2m_stream_t stream) {
-    return bwd_fused_launch(p, enc_tiles, dout, recs, counters, Mcap, rays_o, rays_d, wpack, offsets, gtable, g_mlp, loss_scale, part, nparts,
-                            nullptr, stream);
-}
-
-/* the same + the total-variation gradient of the density table at this part's samples (replaces n2m_s0_tv as well: the scatter warps
- * read the seven neighbouring density features of every sample's base cell from `table` and fold the TV term into the RED of corner 0;
- * counters[3] / counters[15] receive the inner / outer sample counts the random-point fallback n2m_s0_tv_random looks at) */
-int n2m_s0_bwd_fused_tv_part(const n2m_s0_params* p, const void* enc_tiles, const void* dout, const void* recs, int32_t* counters,
-                             uint32_t Mcap, const float* rays_o, const float* rays_d, const void* wpack, const int32_t* offsets,
-                             const void* table, void* gtable, float* g_mlp, float* loss_scale, uint32_t part, uint32_t nparts,
-                             n2m_stream_t stream) {
-    N2M_REQUIRE(table, "s0_bwd_fused_tv", "null pointer");
-    return bwd_fused_launch(p, enc_tiles, dout, recs, counters, Mcap, rays_o, rays_d, wpack, offsets, gtable, g_mlp, loss_scale, part, nparts,
-                            table, stream);
+    N2M_REQUIRE(p && enc_tiles && dout && recs && counters && rays_o && rays_d && wpack && offsets && gtable && g_mlp && loss_scale,
+                "s0_bwd_fused", "null pointer");
+    N2M_REQUIRE(p->num_levels == kLevels, "s0_bwd_fused", "fused path supports num_levels == 16");
+    N2M_REQUIRE(Mcap % kTile == 0 && Mcap > 0, "s0_bwd_fused", "Mcap must be a positive multiple of 128");
+    N2M_REQUIRE(valid_parts(part, nparts), "s0_bwd_fused", "nparts must be 1, 2, 4 or 8 and part < nparts");
+    const uint32_t grid = min(Mcap / kTile, (uint32_t)fused_num_sms());
+    k_s0_bwd_fused<<<grid, kFusedThreads, FB_BYTES, as_stream(stream)>>>(
+        *p, static_cast<const uint8_t*>(enc_tiles), static_cast<const float4*>(dout), static_cast<const float4*>(recs), counters,
+        rays_o, rays_d, static_cast<const uint8_t*>(wpack), offsets, static_cast<float4*>(gtable), g_mlp, loss_scale, part, nparts, g_fused_dbg);
+    return check_launch("s0_bwd_fused");
 }
 
 /* hash-grid gather + MLP forward of the WHOLE batch in one persistent launch (replaces n2m_s0_encode_fwd followed by n2m_s0_mlp_fwd):

@@ -68,7 +68,6 @@ _lib.register({
     "n2m_s0_fused_init": [],
     "n2m_s0_set_fused_debug": [I],
     "n2m_s0_bwd_fused_part": [PP, P, P, P, P, U, P, P, P, P, P, P, P, U, U, P],
-    "n2m_s0_bwd_fused_tv_part": [PP, P, P, P, P, U, P, P, P, P, P, P, P, P, U, U, P],
     "n2m_s0_fwd_fused": [PP, P, P, U, P, P, P, P, P, P, P, P, P],
     "n2m_s0_ema_update": [P, P, P, P, P, P, U, F, P],
     "n2m_s0_ema_swap": [P, P, P, P, P, P, U, P, P],
@@ -220,9 +219,6 @@ class Stage0Trainer:
         # "optimizer": underneath the optimizer stage (HBM-bound table sweep, or the NVLink-bound data-parallel exchange), on a
         # high-priority stream so that its blocks are dispatched ahead of the sweep's; "start": underneath the forward pass
         self.prefetch_at = "optimizer"
-        # fused_bwd: evaluate the TV gradient inside the fused backward kernel (its scatter warps already hold every sample's base
-        # cell; seven table loads per sample and level, folded into the RED of corner 0) instead of as a launch of its own
-        self.tv_in_bwd = False
         self.global_step = 0
         self._graphs = {}
         self.reset_parameters(seed)
@@ -464,13 +460,7 @@ class Stage0Trainer:
         call("n2m_s0_fwd_fused", self._pp(), ptr(self.recs), ptr(self.counters), self.Mcap, ptr(self.rays_o), ptr(self.rays_d),
              ptr(self.table), ptr(self.offsets), ptr(self.wpack), ptr(self.enc_tiles), ptr(self.out), self.loss_acc.data_ptr() + 4, stream())
 
-    def bwd_fused(self, part=0, nparts=1, tv=False):
-        """MLP backward + scatter of one part in one launch; `tv`: + the TV gradient at the part's samples (see `tv_in_bwd`)"""
-        if tv:
-            call("n2m_s0_bwd_fused_tv_part", self._pp(), ptr(self.enc_tiles), ptr(self.dout), ptr(self.recs), ptr(self.counters), self.Mcap,
-                 ptr(self.rays_o), ptr(self.rays_d), ptr(self.wpack), ptr(self.offsets), ptr(self.table), ptr(self.gtables[self.parity]),
-                 ptr(self.g_mlp), ptr(self.opt_state), part, nparts, stream())
-            return
+    def bwd_fused(self, part=0, nparts=1):
         call("n2m_s0_bwd_fused_part", self._pp(), ptr(self.enc_tiles), ptr(self.dout), ptr(self.recs), ptr(self.counters), self.Mcap,
              ptr(self.rays_o), ptr(self.rays_d), ptr(self.wpack), ptr(self.offsets), ptr(self.gtables[self.parity]),
              ptr(self.g_mlp), ptr(self.opt_state), part, nparts, stream())
@@ -478,7 +468,7 @@ class Stage0Trainer:
     def _backward(self, part=0, nparts=1):
         """per-sample backward of one part on the current stream"""
         if self.fused_bwd:
-            self.bwd_fused(part, nparts, tv=self.tv_in_bwd and self.cfg.lambda_tv > 0)
+            self.bwd_fused(part, nparts)
         else:
             self.mlp_bwd(part, nparts)
             self.encode_bwd(part, nparts)
@@ -538,10 +528,9 @@ class Stage0Trainer:
         main = torch.cuda.current_stream()
         P_ = int(self.nparts)
         has_tv = self.cfg.lambda_tv > 0
-        tv_fused = self.fused_bwd and self.tv_in_bwd and has_tv          # TV inside the fused backward kernel: no TV launch
-        fork_tv = self.tv_overlap and has_tv and not tv_fused
-        if self.fused_bwd and has_tv and not (fork_tv or tv_fused):
-            raise RuntimeError("fused_bwd without tv_in_bwd evaluates no TV gradient: keep tv_overlap=True (TV as its own launch)")
+        fork_tv = self.tv_overlap and has_tv
+        if self.fused_bwd and has_tv and not fork_tv:
+            raise RuntimeError("fused_bwd evaluates no TV gradient: keep tv_overlap=True (TV as its own launch)")
 
         def launch_tv():
             if fork_tv:
@@ -582,7 +571,7 @@ class Stage0Trainer:
         if fork_tv:
             main.wait_stream(self._tv_stream)
         elif has_tv:
-            self.tv_random()          # TV itself ran inside the scatter / fused backward kernels, which also counted the groups
+            self.tv_random()          # TV itself ran inside the scatter kernels (tv mode 0), which also counted the groups
 
     def _compute_dp(self):
         """`_compute` for the fused data-parallel optimizers: the gradient buffers of the OTHER parity (consumed by every peer in the
@@ -648,8 +637,7 @@ class Stage0Trainer:
             key = (name, self.parity)
         else:
             key = (name, self.cur, self.parity, int(self.params.shading_full), int(self.params.gt_has_alpha), int(self.nparts),
-                   bool(self.tv_overlap), bool(self.fused_bwd), bool(self.fused_fwd), int(self.tv_fallback_points), bool(self.defer_zero),
-                   bool(self.tv_in_bwd))
+                   bool(self.tv_overlap), bool(self.fused_bwd), bool(self.fused_fwd), int(self.tv_fallback_points), bool(self.defer_zero))
         g = self._graphs.get(key)
         if g is None:
             g = torch.cuda.CUDAGraph()

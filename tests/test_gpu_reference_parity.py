@@ -37,9 +37,6 @@ CASES = {
     "lego": dict(bound=1.0, dt_gamma=0.0, lambda_entropy=0.0, radius=S.LEGO_RADIUS, alpha=True, cam_nf=False, cap=160),
     "garden": dict(bound=16.0, dt_gamma=1.0 / 256, lambda_entropy=1e-3, radius=1.2, alpha=False, cam_nf=True, cap=256),
     "garden_notv": dict(bound=16.0, dt_gamma=1.0 / 256, lambda_entropy=1e-3, radius=1.2, alpha=False, cam_nf=True, cap=256, lambda_tv=0.0),
-    # TV gradient evaluated inside the fused backward kernel instead of by its own launch
-    "lego_tvfused": dict(bound=1.0, dt_gamma=0.0, lambda_entropy=0.0, radius=S.LEGO_RADIUS, alpha=True, cam_nf=False, cap=160, tv_in_bwd=True),
-    "garden_tvfused": dict(bound=16.0, dt_gamma=1.0 / 256, lambda_entropy=1e-3, radius=1.2, alpha=False, cam_nf=True, cap=256, tv_in_bwd=True),
 }
 
 
@@ -83,7 +80,6 @@ def _make_ours(c, bits, grid):
     tr = Stage0Trainer(cfg, seed=3)
     tr.set_occupancy(bits, grid)
     tr.use_cam_near_far = c["cam_nf"]
-    tr.tv_in_bwd = bool(c.get("tv_in_bwd", False))
     return tr
 
 
@@ -169,7 +165,7 @@ def _cmp(a, r):
                 cos=(torch.dot(a, r) / (a.norm() * r.norm() + 1e-300)).item(), scale=scale)
 
 
-@pytest.mark.parametrize("name", ["lego", "garden", "garden_notv", "lego_tvfused", "garden_tvfused"])
+@pytest.mark.parametrize("name", ["lego", "garden", "garden_notv"])
 def test_fused_step_matches_reference_cuda_path(name):
     c = CASES[name]
     ref_stage, ns = _ref_stack()
@@ -649,24 +645,6 @@ def test_tv_gradient_alone_matches_reference_post_train_step(name):
         # (|ours| / |ref| = 1.001 measured at level 1 of the garden batch); ours adds merged runs
         tol = 3e-3 if l < 4 else 1e-3
         assert rel <= tol, (l, rel, (a - r).abs().max().item(), sc, (a.norm() / r.norm()).item())
-    # the same TV term evaluated INSIDE the fused backward kernel (tv_in_bwd): forward pass, per-sample gradients zeroed, one launch
-    tr._fill_params(True, tr.slots[tr.cur].has_alpha)
-    tr.loss_acc.zero_()
-    tr.encode_fwd(); tr.mlp_fwd(); tr.composite_loss()
-    tr.dout.zero_()
-    cnt_tv = (int(tr.counters[3].item()), int(tr.counters[15].item()))
-    tr.counters[3] = 0; tr.counters[15] = 0
-    tr.gtable.zero_(); tr.g_mlp.zero_()
-    tr.bwd_fused(tv=True)
-    torch.cuda.synchronize()
-    assert (int(tr.counters[3].item()), int(tr.counters[15].item())) == cnt_tv
-    gt_f = tr.export_reference_grads()
-    g_fused = gt_f["encoder.embeddings"].reshape(-1)
-    assert gt_f["encoder_color.embeddings"].abs().max().item() == 0          # TV touches the density table only
-    for l in range(16):
-        a, o, r = g_fused[offs[l]:offs[l + 1]].double(), g_ours[offs[l]:offs[l + 1]].double(), g_ref[offs[l]:offs[l + 1]].double()
-        assert ((a - o).norm() / o.norm()).item() <= 2e-5, (l, ((a - o).norm() / o.norm()).item())       # vs the stand-alone TV launch
-        assert ((a - r).norm() / r.norm()).item() <= (3e-3 if l < 4 else 1e-3), l                        # vs the reference
 
 
 def test_density_volume_matches_reference_export_stage0_input():

@@ -170,7 +170,6 @@ def test_step_orchestration_call_sequence(monkeypatch):
     tr._tv_overlap, tr._tv_stream, tr._part_streams = True, None, []
     tr._adam_stream = None
     tr.fused_bwd, tr.fused_fwd, tr.tv_fallback_points, tr._graphs = False, False, 1000, {}
-    tr.tv_in_bwd = False
 
     tv = ["n2m_s0_tv", "n2m_s0_tv_random"]
     chain = ["n2m_s0_encode_fwd_part", "n2m_s0_mlp_fwd_part", "n2m_s0_composite_loss_part", "n2m_s0_mlp_bwd_part", "n2m_s0_encode_bwd_part"]
@@ -196,11 +195,6 @@ def test_step_orchestration_call_sequence(monkeypatch):
     calls.clear(); tr.nparts = 2
     tr._compute_then_adam()
     assert names() == tv + fchain * 2 + adam
-    # ... with the TV gradient inside that launch: no TV kernel, the fallback probe behind the chains
-    calls.clear(); tr.tv_in_bwd = True
-    tr._compute_then_adam()
-    assert names() == (chain[:3] + ["n2m_s0_bwd_fused_tv_part"]) * 2 + ["n2m_s0_tv_random"] + adam
-    tr.tv_in_bwd = False
     # gather + MLP forward as one launch (whole batch only)
     calls.clear(); tr.fused_fwd, tr.nparts = True, 1
     tr._compute_then_adam()
