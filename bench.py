@@ -351,6 +351,22 @@ def psnr_leg(iters, eval_res=100, eval_views=2, seed=0):
             if which == "ours":
                 over, max_m = tr.check_capacity(grow=False)
                 res[which]["overflowed_steps"] = over
+                # evaluation renderer on a full 800 x 800 view of this model: device-side alive-ray rounds (csrc/render.cu) against
+                # the all-samples path (every marched sample through the training kernels), CUDA events, second call of each
+                ro, rd = full_image_rays(test_poses[0], intr, 800, 800)
+                ro, rd = ro.to(dev), rd.to(dev)
+                ev = {"rays": int(ro.shape[0])}
+                for name, kw in (("alive_rounds", {}), ("all_samples", {"early_stop": False})):
+                    a_img, _, _ = tr.render(ro, rd, bg_color=1.0, **kw)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(); a_img, _, _ = tr.render(ro, rd, bg_color=1.0, **kw); e1.record()
+                    torch.cuda.synchronize()
+                    ev[name + "_ms"] = e0.elapsed_time(e1)
+                    if name == "alive_rounds":
+                        ev["sample_rows_evaluated"] = int(tr.render_rows); first = a_img
+                    else:
+                        ev["max_abs_diff"] = float((a_img - first).abs().max().item())
+                res["eval_render"] = ev
             del tr
             torch.cuda.empty_cache()
         res["iters"] = iters

@@ -245,6 +245,25 @@ int n2m_s0_fwd_fused(const n2m_s0_params* p, const void* recs, const int32_t* co
                      const float* rays_d, const void* table, const int32_t* offsets, const void* wpack, void* enc_tiles, void* out,
                      float* spec_sq_sum, n2m_stream_t stream);
 
+/* Evaluation renderer with the alive-ray bookkeeping on the device (csrc/render.cu) = NeRFRenderer.render, inference branch
+ * (nerf/renderer.py:749-802: per round march_rays -> model -> composite_rays -> mask compaction, one host read-back per round).
+ *   render_begin : near / far (+ per-ray camera clamp, nullable), zeroed weights_sum / depth / image [N], rays_t, the first alive list;
+ *                  alive [2 N] i32, ctl [16] i32 (control block: [1] sample rows of the round -- the counters the forward kernels read --,
+ *                  [8] alive rays, [9] slab width, [10] survivors appended so far, [11] list parity, [12] rounds run, [13] sample rows evaluated)
+ *   render_rounds: `num_rounds` rounds of plan -> march (records {t, dt, t + dt, ray} in slab order) -> n2m_s0_encode_fwd -> n2m_s0_mlp_fwd
+ *                  -> slab compositor (raymarching.cu:842-924) + survivor compaction, all sizes read on the device; `schedule` (HOST
+ *                  array) = slab widths, clipped on the device to Mcap / alive; recs [Mcap] float4, enc_tiles [Mcap*64] half,
+ *                  out [Mcap] float4; Mcap a multiple of 128 and >= N.  Afterwards ctl[10] = rays still alive.
+ *   render_finish: image += (1 - weights_sum) * bg (renderer.py:804), bg [N,3] or NULL (then bg_scalar). */
+int n2m_s0_render_begin(const n2m_s0_params* p, const float* rays_o, const float* rays_d, const float* aabb, const float* cam_near_far,
+                        uint32_t N, float* rays_t, float* rays_far, int32_t* alive, int32_t* ctl, float* weights_sum, float* depth,
+                        float* image, n2m_stream_t stream);
+int n2m_s0_render_rounds(const n2m_s0_params* p, const float* rays_o, const float* rays_d, const uint8_t* bitfield, uint32_t N,
+                         const uint32_t* schedule, uint32_t num_rounds, float* rays_t, float* rays_far, int32_t* alive, int32_t* ctl,
+                         void* recs, void* enc_tiles, void* out, uint32_t Mcap, const void* table, const int32_t* offsets, const void* wpack,
+                         float* weights_sum, float* depth, float* image, n2m_stream_t stream);
+int n2m_s0_render_finish(float* image, const float* weights_sum, const float* bg, float bg_scalar, uint32_t N, n2m_stream_t stream);
+
 /* EMA of the parameters = torch_ema.ExponentialMovingAverage as the reference's Trainer holds it (nerf/utils.py:544-545, decay 0.95
  * from main.py:241): `update` once per EPOCH (utils.py:1213-1214), parameters swapped with the shadow for evaluation
  * (utils.py:1250-1252,1340-1341) and for the 'best' checkpoint (utils.py:1389-1401).  shadow_density [rows] f32, shadow_color [rows] float2,

@@ -289,24 +289,43 @@ def test_update_density_grid_matches_reference_composition():
 
 
 def test_render_equals_training_forward():
-    """chunked render() == the training forward on the same rays (host chunking / padding logic; the parity of render() against the
-    reference's inference loop is test_evaluation_render_matches_reference_inference_loop in test_gpu_reference_parity.py)"""
+    """chunked render(early_stop=False) == the training forward on the same rays (host chunking / padding logic), and the renderer with
+    the device-side alive-ray bookkeeping (csrc/render.cu) == that image up to the order in which the transmittance is accumulated; the
+    parity of render() against the reference's inference loop is test_evaluation_render_matches_reference_inference_loop in
+    test_gpu_reference_parity.py"""
     tr, b = make()
     stage(tr, b)
     tr.noises.zero_()
     tr.forward_backward()
-    img0 = tr.image.clone(); ws0 = tr.weights_sum.clone()
-    img, ws, dep = tr.render(b["ro"].cuda(), b["rd"].cuda(), bg_color=b["bg"].cuda())
+    img0 = tr.image.clone(); ws0 = tr.weights_sum.clone(); dep0 = tr.depth.clone()
+    img, ws, dep = tr.render(b["ro"].cuda(), b["rd"].cuda(), bg_color=b["bg"].cuda(), early_stop=False)
     assert torch.equal(img, img0) and torch.equal(ws, ws0)
     # ragged call: more rays than one chunk, white background
     ro2 = torch.cat([b["ro"], b["ro"][:10]]).cuda(); rd2 = torch.cat([b["rd"], b["rd"][:10]]).cuda()
-    img2, ws2, _ = tr.render(ro2, rd2, bg_color=1.0)
+    img2, ws2, _ = tr.render(ro2, rd2, bg_color=1.0, early_stop=False)
     assert img2.shape == (N + 10, 3) and torch.equal(img2[:10], img2[N:])
     assert torch.isfinite(img2).all()
     # per-ray background tensor with a ragged last chunk
     bgt = torch.rand(N + 10, 3, device="cuda")
-    img3, _, _ = tr.render(ro2, rd2, bg_color=bgt)
+    img3, _, _ = tr.render(ro2, rd2, bg_color=bgt, early_stop=False)
     assert torch.allclose(img3 - (1 - ws2)[:, None] * bgt, img2 - (1 - ws2)[:, None], atol=1e-6)
+    # ---- device-side alive-ray renderer: one chunk, several ragged chunks, and a schedule too short to finish (extra rounds) ----
+    assert (ws0 > 0.5).float().mean().item() > 0.05
+    for kw in (dict(), dict(chunk=40), dict(chunk=32)):
+        e_img, e_ws, e_dep = tr.render(b["ro"].cuda(), b["rd"].cuda(), bg_color=b["bg"].cuda(), **kw)
+        assert (e_img - img0).abs().max().item() <= 2e-4, (kw, (e_img - img0).abs().max().item())
+        assert (e_ws - ws0).abs().max().item() <= 2e-4 and (e_dep - dep0).abs().max().item() <= 2e-4 * max(1.0, dep0.abs().max().item())
+    rounds_default = tr.render_rounds
+    assert rounds_default == len(tr.RENDER_SCHEDULE)
+    tr.RENDER_SCHEDULE = (2, 2)
+    try:
+        e_img, e_ws, _ = tr.render(ro2, rd2, bg_color=bgt)
+        assert tr.render_rounds > 2                                  # rays were left alive: the read-back triggered further rounds
+    finally:
+        del tr.RENDER_SCHEDULE                                       # back to the class default
+    assert (e_img - img3).abs().max().item() <= 2e-4 and (e_ws - ws2).abs().max().item() <= 2e-4
+    # early termination is real: the rounds evaluate fewer sample rows than the march emitted for the whole batch
+    assert torch.isfinite(e_img).all()
 
 
 @pytest.mark.parametrize("nparts", [2, 4, 8])
