@@ -648,15 +648,16 @@ def run_stage1(args):
         mvp = R.perspective_mvp(cam, fovy=2 * np.arctan(0.5 * h0 / intr[1]), aspect=w0 / h0); mvp[1] *= -1
         gt = torch.rand(h0 * w0, 4, generator=g); gt[:, 3] = 1.0
         views.append((torch.from_numpy(mvp).cuda(), rd.cuda(), gt.cuda(), torch.rand(h0 * w0, 3, generator=g).cuda()))
-    K, W = args.steps, args.warmup
+    K, W = args.steps, max(args.warmup, 17)            # every view's graph is captured during warm-up
+    ug = not args.no_graph
     for it in range(W):
-        s1.step(*views[it % 8])
+        s1.step(*views[it % 8], use_graph=ug)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     cov = torch.zeros(1, dtype=torch.int64, device="cuda")
     e0.record()
     for it in range(K):
-        s1.step(*views[(W + it) % 8])
+        s1.step(*views[(W + it) % 8], use_graph=ug)
         cov.add_(s1.counters[1])
     e1.record()
     torch.cuda.synchronize()
@@ -700,7 +701,7 @@ def run_stage1(args):
             "value": hi / (ms * 1e-3), "unit": "super-sampled pixels/s", "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
             "config": {"workload": "lego_stage1", "mesh_faces": int(f.shape[0]), "image": [h0, w0], "ssaa": 2, "raster": [s1.h, s1.w],
-                       "covered_pixels_per_step": cov.item() / K, "antialias": bool(s1.antialias)},
+                       "covered_pixels_per_step": cov.item() / K, "antialias": bool(s1.antialias), "cuda_graph": ug},
             "antialias_ms": aa_ms,
             "rasterize_ms": q0.elapsed_time(q1) / 10, "rasterize_pixels_per_s": hi / (q0.elapsed_time(q1) / 10 * 1e-3),
             "forward_ms": r0.elapsed_time(r1) / 10}

@@ -63,6 +63,7 @@ class Stage1Trainer:
             self.grad_vclip = torch.zeros(self.vertices.shape[0], 4, device=dev)
         self.vclip = None
         self.mvp = None
+        self._graphs, self._warm = {}, False
         self.params = S0Params()
         ctypes.memmove(ctypes.byref(self.params), ctypes.byref(t0.params), ctypes.sizeof(S0Params))
         self.params.lambda_specular = 0.0          # the specular regulariser is a stage-0 loss (utils.py:726,735-738)
@@ -118,14 +119,33 @@ class Stage1Trainer:
             call("n2m_s0_encode_bwd", self._pp(), ptr(self.recs), ptr(self.counters), self.cap, ptr(self.pts), ptr(self.pdirs),
                  ptr(self.denc_tiles), ptr(t0.table), ptr(t0.offsets), ptr(t0.gtables[t0.parity]), ptr(t0.opt_state), stream())
 
-    def step(self, mvp, rays_d, gt, bg, shading="full", lr=None):
-        """One optimizer step on one view: mvp [4,4], rays_d [h0*w0,3] (unnormalised), gt [h0*w0, 3 or 4], bg [h0*w0,3]."""
+    def step(self, mvp, rays_d, gt, bg, shading="full", lr=None, use_graph=False):
+        """One optimizer step on one view: mvp [4,4], rays_d [h0*w0,3] (unnormalised), gt [h0*w0, 3 or 4], bg [h0*w0,3].
+        `use_graph`: the step is captured once per view (keyed by the addresses of its device-resident tensors, which must then stay
+        valid and in place -- the dataset of a stage-1 run is a fixed set of views) and replayed as one CUDA graph: ~17 launches and a
+        handful of torch ops leave the host's critical path (the eager step is host-bound at this size, profiles/r2_summary.md)."""
         t0 = self.t0
         if lr is not None:
             t0.opt_state[4:5].fill_(float(lr))
-        self.forward(mvp, rays_d.contiguous(), shading)
-        self.loss_backward(gt.contiguous(), bg.contiguous())
-        t0.adam()
+        rays_d, gt, bg = rays_d.contiguous(), gt.contiguous(), bg.contiguous()
+        if not use_graph or not self._warm:
+            self.forward(mvp, rays_d, shading)
+            self.loss_backward(gt, bg)
+            t0.adam()
+            self._warm = True                         # lazily created buffers / streams exist now: later steps may be captured
+        else:
+            mvp = mvp.to(t0.device, torch.float32)
+            key = (mvp.data_ptr(), rays_d.data_ptr(), gt.data_ptr(), bg.data_ptr(), int(gt.shape[-1]), shading, int(t0.parity), bool(t0.fused_bwd))
+            g = self._graphs.get(key)
+            if g is None:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self.forward(mvp, rays_d, shading)
+                    self.loss_backward(gt, bg)
+                    t0.adam()
+                self._graphs[key] = (g, mvp, rays_d, gt, bg)          # keeps the captured addresses alive
+                g = self._graphs[key]
+            g[0].replay()
         t0.global_step += 1
 
     def vertex_gradient(self):

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def declared_symbols():
     names = []
-    for h in ("n2m_b200.h", "n2m_b200_fused.h", "n2m_b200_raster.h"):
+    for h in sorted(f for f in os.listdir(os.path.join(ROOT, "include")) if f.endswith(".h")):
         src = open(os.path.join(ROOT, "include", h)).read()
         src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
         names += re.findall(r"\b(n2m_[a-zA-Z0-9_]+)\s*\(", src)
@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_bindings_cover_the_headers():
-    from nerf2mesh_b200 import _lib, parallel, raster, sampler, stage0, stage1  # noqa: F401  (register the fused / data-parallel signatures)
+    from nerf2mesh_b200 import _lib, mesh, parallel, raster, sampler, stage0, stage1  # noqa: F401  (register the fused / data-parallel signatures)
     bound = set(_lib.SIGNATURES) | {"n2m_last_error", "n2m_version", "n2m_launch_count", "n2m_s0_wpack_bytes",
                                    "n2m_s0_mlp_param_count", "n2m_s0_init", "n2m_dp_ctx_bytes", "n2m_antialias_topology_slots"}
     assert set(declared_symbols()) <= bound, set(declared_symbols()) - bound
