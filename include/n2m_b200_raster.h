@@ -72,6 +72,19 @@ int n2m_s1_loss_aa(const void* aa, const float* gt, uint32_t gt_channels, const 
                    n2m_stream_t stream);
 int n2m_s1_dout(const void* grad_rgba, const int32_t* inv, uint32_t num_pixels, void* dout, n2m_stream_t stream);
 
+/* vertex-offset optimizer of stage 1 (`vertices_offsets`: nn.Parameter at renderer.py:160, Adam group with lr_vert at :180; regularisers
+ * utils.py:750-779).  n2m_s1_vert_check: non-finite scan of the loss-scaled clip-space gradient grad_vclip [V,4] into found_inf
+ * (opt_state[3]) -- call it BEFORE the optimizer head.  n2m_s1_vert_step (between the optimizer head and its post kernel):
+ *   grad = (grad_vclip . mvp[:, :3]) / loss_scale + lambda_lap * d/dv mean_i |(L v)_i| + lambda_offsets * d/doff mean_i sum_c off_ic^2
+ * with the uniform Laplacian L = D - A over the unique edges of the mesh (the edge hash of n2m_antialias_topology), Adam(0.9, 0.999, eps)
+ * with its own step count vert_state[0] on offsets [V,3], vertices = base + offsets; skipped when found_inf is set.  scratch [6 V] f32;
+ * grad_out [V,3] (nullable) receives the total gradient; loss_out (nullable) += lambda_lap * mean |L v| (the offsets term is left to
+ * the caller: it needs no kernel).  mvp [4,4] row-major on the device; lr_vert < 0: the learning rate is read from vert_state[1]. */
+int n2m_s1_vert_check(const float* grad_vclip, uint32_t V, float* opt_state, n2m_stream_t stream);
+int n2m_s1_vert_step(const float* grad_vclip, const float* mvp, const void* topo_keys, uint32_t topo_slots, const float* base, float* offsets,
+                     float* m, float* v, float* vertices, float* scratch, float* grad_out, uint32_t V, float lambda_lap, float lambda_offsets,
+                     float lr_vert, float eps, const float* opt_state, float* vert_state, float* loss_out, n2m_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -218,6 +218,84 @@ k_s1_loss_aa(const float4* __restrict__ aa, const float* __restrict__ gt, uint32
     }
 }
 
+// ---- vertex-offset optimizer (NeRFRenderer.vertices_offsets: renderer.py:160,180 -- Adam group with lr_vert; regularisers
+// utils.py:750-779: lambda_lap * laplacian_smooth_loss (uniform Laplacian, utils.py:176-221) + lambda_offsets * mean(sum(offsets^2))) ----
+// y += L x for the uniform Laplacian L = D - A, one thread per slot of the edge hash of csrc/antialias.cu (one slot = one undirected edge)
+__global__ void __launch_bounds__(256)
+k_s1_laplacian(const unsigned long long* __restrict__ keys, uint32_t slots, const float* __restrict__ x, float* __restrict__ y) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= slots) return;
+    const unsigned long long k = keys[i];
+    if (k == ~0ull) return;
+    const uint32_t a = (uint32_t)(k >> 32), b = (uint32_t)(k & 0xffffffffull);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float d = x[3 * (size_t)a + c] - x[3 * (size_t)b + c];
+        atomicAdd(y + 3 * (size_t)a + c, d);
+        atomicAdd(y + 3 * (size_t)b + c, -d);
+    }
+}
+
+// u [V,3] = L v  ->  u_i / |u_i| in place (0 where |u_i| = 0: the subgradient torch.norm uses), loss_out[0] += lambda_lap * mean |u_i|
+__global__ void __launch_bounds__(256)
+k_s1_lap_normalize(float* __restrict__ u, uint32_t V, float lambda_lap, float* __restrict__ loss_out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    float n = 0.f;
+    if (i < V) {
+        const float a = u[3 * (size_t)i], b = u[3 * (size_t)i + 1], c = u[3 * (size_t)i + 2];
+        n = sqrtf(a * a + b * b + c * c);
+        const float r = n > 0.f ? __fdiv_rn(1.f, n) : 0.f;
+        u[3 * (size_t)i] = a * r; u[3 * (size_t)i + 1] = b * r; u[3 * (size_t)i + 2] = c * r;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    if (loss_out && (threadIdx.x & 31) == 0 && n != 0.f) atomicAdd(loss_out, lambda_lap * n / (float)V);
+}
+
+// non-finite scan of the loss-scaled clip-space gradient -> found_inf (GradScaler.unscale_ over the vertices_offsets group)
+__global__ void __launch_bounds__(256)
+k_s1_vert_check(const float* __restrict__ g, uint32_t n, float* __restrict__ st) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool bad = i < n && !isfinite(g[i]);
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) st[3] = 1.f;
+}
+
+// grad = (grad_vclip . mvp[:, :3]) / loss_scale + (lambda_lap / V) * (L w) + (2 lambda_offsets / V) * offsets; Adam(eps) on the offsets with
+// its own step count vst[0]; vertices = base + offsets.  Skipped as a whole when found_inf is set (st[3]).
+__global__ void __launch_bounds__(256)
+k_s1_vert_adam(const float4* __restrict__ grad_vclip, const float* __restrict__ mvp, const float* __restrict__ lap_grad, const float* __restrict__ base,
+               float* __restrict__ offsets, float* __restrict__ m, float* __restrict__ v, float* __restrict__ vertices, float* __restrict__ grad_out,
+               uint32_t V, float lambda_lap, float lambda_offsets, float lr, float eps, const float* __restrict__ st, const float* __restrict__ vst) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V) return;
+    if (lr < 0.f) lr = vst[1];                                          // learning rate kept on the device (graph-replayed steps)
+    const bool skip = st[3] != 0.f;
+    const float inv_scale = st[7];
+    const float t = vst[0] + (skip ? 0.f : 1.f);                       // this step's count (k_s1_vert_tick advances it afterwards)
+    const float bc1 = 1.f - powf(0.9f, fmaxf(t, 1.f)), bc2s = sqrtf(1.f - powf(0.999f, fmaxf(t, 1.f)));
+    const float4 gc = grad_vclip[i];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const size_t j = 3 * (size_t)i + c;
+        const float gi = (gc.x * mvp[c] + gc.y * mvp[4 + c] + gc.z * mvp[8 + c] + gc.w * mvp[12 + c]) * inv_scale;
+        const float off = offsets[j];
+        const float g = gi + (lambda_lap > 0.f ? lambda_lap / (float)V * lap_grad[j] : 0.f) + 2.f * lambda_offsets / (float)V * off;
+        if (grad_out) grad_out[j] = g;
+        if (skip) continue;
+        const float mi = 0.9f * m[j] + 0.1f * g;
+        const float vi = 0.999f * v[j] + 0.001f * g * g;
+        m[j] = mi; v[j] = vi;
+        const float denom = __fdiv_rn(__fsqrt_rn(vi), bc2s) + eps;
+        const float o2 = off - __fdiv_rn(lr, bc1) * __fdiv_rn(mi, denom);
+        offsets[j] = o2;
+        vertices[j] = base[j] + o2;
+    }
+}
+
+__global__ void k_s1_vert_tick(const float* __restrict__ st, float* __restrict__ vst) {
+    if (threadIdx.x == 0 && blockIdx.x == 0 && st[3] == 0.f) vst[0] += 1.f;
+}
+
 }  // namespace
 }  // namespace n2m
 
@@ -271,6 +349,40 @@ int n2m_s1_loss_aa(const void* aa, const float* gt, uint32_t gt_channels, const 
     k_s1_loss_aa<<<div_up(h0 * w0, 256u), 256, 0, as_stream(stream)>>>(static_cast<const float4*>(aa), gt, gt_channels, bg, h0, w0, ssaa, lambda_mask,
                                                                       loss_scale, static_cast<float4*>(d_aa), image, weights_sum, loss_out);
     return check_launch("s1_loss_aa");
+}
+
+int n2m_s1_vert_check(const float* grad_vclip, uint32_t V, float* opt_state, n2m_stream_t stream) {
+    N2M_REQUIRE(grad_vclip && opt_state, "s1_vert_check", "null pointer");
+    if (V == 0) return 0;
+    k_s1_vert_check<<<div_up(4 * V, 256u), 256, 0, as_stream(stream)>>>(grad_vclip, 4 * V, opt_state);
+    return check_launch("s1_vert_check");
+}
+
+int n2m_s1_vert_step(const float* grad_vclip, const float* mvp, const void* topo_keys, uint32_t topo_slots, const float* base, float* offsets,
+                     float* m, float* v, float* vertices, float* scratch, float* grad_out, uint32_t V, float lambda_lap, float lambda_offsets,
+                     float lr_vert, float eps, const float* opt_state, float* vert_state, float* loss_out, n2m_stream_t stream) {
+    N2M_REQUIRE(grad_vclip && mvp && base && offsets && m && v && vertices && scratch && opt_state && vert_state, "s1_vert_step", "null pointer");
+    N2M_REQUIRE(lambda_lap <= 0.f || (topo_keys && topo_slots > 0), "s1_vert_step", "the Laplacian term needs the mesh's edge hash");
+    if (V == 0) return 0;
+    cudaStream_t st = as_stream(stream);
+    float* u = scratch;                       // [V,3]: L v, then its row-normalised form
+    float* lg = scratch + 3 * (size_t)V;      // [V,3]: L (u / |u|)
+    if (lambda_lap > 0.f) {
+        const unsigned long long* keys = static_cast<const unsigned long long*>(topo_keys);
+        cudaError_t e = cudaMemsetAsync(scratch, 0, 6 * (size_t)V * sizeof(float), st);
+        if (e != cudaSuccess) return fail("s1_vert_step(memset)", cudaGetErrorString(e));
+        k_s1_laplacian<<<div_up(topo_slots, 256u), 256, 0, st>>>(keys, topo_slots, vertices, u);
+        if (int err = check_launch("s1_vert_step(L v)")) return err;
+        k_s1_lap_normalize<<<div_up(V, 256u), 256, 0, st>>>(u, V, lambda_lap, loss_out);
+        if (int err = check_launch("s1_vert_step(normalize)")) return err;
+        k_s1_laplacian<<<div_up(topo_slots, 256u), 256, 0, st>>>(keys, topo_slots, u, lg);
+        if (int err = check_launch("s1_vert_step(L w)")) return err;
+    }
+    k_s1_vert_adam<<<div_up(V, 256u), 256, 0, st>>>(reinterpret_cast<const float4*>(grad_vclip), mvp, lg, base, offsets, m, v, vertices, grad_out, V,
+                                                   lambda_lap, lambda_offsets, lr_vert, eps, opt_state, vert_state);
+    if (int err = check_launch("s1_vert_step(adam)")) return err;
+    k_s1_vert_tick<<<1, 32, 0, st>>>(opt_state, vert_state);
+    return check_launch("s1_vert_step(tick)");
 }
 
 }  // extern "C"

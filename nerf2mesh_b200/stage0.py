@@ -493,10 +493,11 @@ class Stage0Trainer:
             call("n2m_s0_tv_random", self._pp(), ptr(self.counters), ptr(self.table), ptr(self.offsets), ptr(self.gtables[self.parity]),
                  ptr(self.opt_state), int(self.tv_fallback_points), ptr(dump), stream())
 
-    def adam(self, keep_grads=False):
+    def adam(self, keep_grads=False, between=None):
         """Optimizer stage: head -> [table rows || MLP parameters + weight repack] -> GradScaler update.  The MLP branch
         (three tiny launches) runs on a forked stream underneath the 0.7 GB table sweep.  `keep_grads`: do not zero the gradient
-        table (the caller zeroes it off the critical path, see `defer_zero`)."""
+        table (the caller zeroes it off the critical path, see `defer_zero`).  `between`: callable run after the parameter updates and
+        before the GradScaler update -- further parameter groups of the same optimizer step (stage 1: the vertex offsets)."""
         main = torch.cuda.current_stream()
         call("n2m_s0_adam_head", ptr(self.g_mlp), ptr(self.opt_state), stream())
         if self._adam_stream is None:
@@ -508,6 +509,8 @@ class Stage0Trainer:
                  ptr(self.opt_state), self.cfg.eps, stream())
         call("n2m_s0_adam_tables_keep" if keep_grads else "n2m_s0_adam_tables", ptr(self.table), ptr(self.color_master), ptr(self.gtable),
              ptr(self.m_table), ptr(self.v_table), self.rows, ptr(self.opt_state), self.cfg.eps, stream())
+        if between is not None:
+            between()
         main.wait_stream(side)
         call("n2m_s0_adam_post", ptr(self.opt_state), stream())
 

@@ -9,8 +9,10 @@ the model state (hash tables, MLP weights, optimizer moments, GradScaler state) 
 
 `antialias=True` inserts dr.antialias on (rgbs, alphas) as the reference does (renderer.py:886-887; csrc/antialias.cu) and leaves the
 image-loss gradient w.r.t. the vertices in `vertex_gradient()` -- the quantity the reference's vertex optimizer consumes.
-Not built (DESIGN.md "stage 1"): the vertex optimizer itself with its mesh regularisers (utils.py:750-790) and re-meshing
-(`refine_and_decimate`): vertices are fixed here.
+`lr_vert > 0` also trains the vertex offsets as the reference's default stage 1 does (`vertices_offsets`, renderer.py:160,180: an Adam
+group with lr_vert; regularisers lambda_lap * laplacian_smooth_loss (uniform) + lambda_offsets * mean(sum(offsets^2)), utils.py:750-779).
+Not built (DESIGN.md "stage 1"): re-meshing (`refine_and_decimate`, CPU mesh libraries) and the pytorch3d regularisers that are off by
+default (lambda_normal, lambda_edgelen).
 """
 import ctypes
 
@@ -27,11 +29,14 @@ _lib.register({
     "n2m_s1_rgba": [P, P, U, P, P],
     "n2m_s1_loss_aa": [P, P, U, P, U, U, U, F, P, P, P, P, P, P],
     "n2m_s1_dout": [P, P, U, P, P],
+    "n2m_s1_vert_check": [P, U, P, P],
+    "n2m_s1_vert_step": [P, P, P, U, P, P, P, P, P, P, P, U, F, F, F, F, P, P, P, P],
 })
 
 
 class Stage1Trainer:
-    def __init__(self, t0, vertices, triangles, h0, w0, ssaa=2, max_points=None, lambda_mask=0.1, antialias=False, pos_gradient_boost=1.0):
+    def __init__(self, t0, vertices, triangles, h0, w0, ssaa=2, max_points=None, lambda_mask=0.1, antialias=False, pos_gradient_boost=1.0,
+                 lr_vert=0.0, lambda_lap=0.001, lambda_offsets=0.1):
         assert ssaa in (1, 2), "the ssaa average equals the reference's bilinear down-scale only at factors 1 and 2"
         self.t0 = t0
         dev = t0.device
@@ -64,6 +69,18 @@ class Stage1Trainer:
         self.vclip = None
         self.mvp = None
         self._graphs, self._warm = {}, False
+        # vertex offsets (main.py:49,84-85 defaults: lr_vert 1e-4, lambda_lap 1e-3, lambda_offsets 0.1); 0 = vertices fixed
+        self.lr_vert, self.lambda_lap, self.lambda_offsets = float(lr_vert), float(lambda_lap), float(lambda_offsets)
+        if self.lr_vert > 0:
+            if not self.antialias:
+                raise ValueError("the image loss reaches the vertices through dr.antialias only: lr_vert > 0 needs antialias=True")
+            V = self.vertices.shape[0]
+            self.base_vertices = self.vertices.clone()
+            self.offsets = torch.zeros(V, 3, device=dev)
+            self.m_vert = torch.zeros(V, 3, device=dev); self.v_vert = torch.zeros(V, 3, device=dev)
+            self.vert_state = torch.zeros(4, device=dev)                  # [0] Adam step count of this group, [1] current lr_vert
+            self.vert_scratch = torch.zeros(6 * V, device=dev)
+            self.grad_offsets = torch.zeros(V, 3, device=dev)             # total gradient of the last step (diagnostic / tests)
         self.params = S0Params()
         ctypes.memmove(ctypes.byref(self.params), ctypes.byref(t0.params), ctypes.sizeof(S0Params))
         self.params.lambda_specular = 0.0          # the specular regulariser is a stage-0 loss (utils.py:726,735-738)
@@ -76,7 +93,7 @@ class Stage1Trainer:
         """rasterize -> surface points -> colour MLPs; leaves per-point colours in `out`, the pixel -> point map in `inv`."""
         t0 = self.t0
         self.params.shading_full = int(shading == "full")
-        mvp = mvp.to(t0.device, torch.float32)
+        mvp = mvp.to(t0.device, torch.float32).contiguous()
         vclip = (torch.nn.functional.pad(self.vertices, (0, 1), value=1.0) @ mvp.T).contiguous()           # renderer.py:858
         self.vclip, self.mvp = vclip, mvp
         self.rast, _ = dr.rasterize(self.glctx, vclip[None], self.triangles, (self.h, self.w))
@@ -128,25 +145,44 @@ class Stage1Trainer:
         if lr is not None:
             t0.opt_state[4:5].fill_(float(lr))
         rays_d, gt, bg = rays_d.contiguous(), gt.contiguous(), bg.contiguous()
+        if self.lr_vert > 0:
+            self.vert_state[1:2].fill_(self.lr_vert)
         if not use_graph or not self._warm:
-            self.forward(mvp, rays_d, shading)
-            self.loss_backward(gt, bg)
-            t0.adam()
+            self._step_body(mvp, rays_d, gt, bg, shading)
             self._warm = True                         # lazily created buffers / streams exist now: later steps may be captured
         else:
-            mvp = mvp.to(t0.device, torch.float32)
+            if not (mvp.is_cuda and mvp.dtype == torch.float32 and mvp.is_contiguous()):
+                raise RuntimeError("use_graph: mvp must be a contiguous float32 CUDA tensor that stays in place (the graph is keyed by its address)")
             key = (mvp.data_ptr(), rays_d.data_ptr(), gt.data_ptr(), bg.data_ptr(), int(gt.shape[-1]), shading, int(t0.parity), bool(t0.fused_bwd))
             g = self._graphs.get(key)
             if g is None:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    self.forward(mvp, rays_d, shading)
-                    self.loss_backward(gt, bg)
-                    t0.adam()
+                    self._step_body(mvp, rays_d, gt, bg, shading)
                 self._graphs[key] = (g, mvp, rays_d, gt, bg)          # keeps the captured addresses alive
                 g = self._graphs[key]
             g[0].replay()
         t0.global_step += 1
+
+    def _step_body(self, mvp, rays_d, gt, bg, shading):
+        self.forward(mvp, rays_d, shading)
+        self.loss_backward(gt, bg)
+        if self.lr_vert > 0:
+            call("n2m_s1_vert_check", ptr(self.grad_vclip), self.vertices.shape[0], ptr(self.t0.opt_state), stream())
+            self.t0.adam(between=self._vertex_step)
+        else:
+            self.t0.adam()
+
+    def _vertex_step(self):
+        """the `vertices_offsets` group of the optimizer step: regularisers (evaluated on the offsets before the update, as autograd does),
+        Adam, vertices = base + offsets"""
+        V = self.vertices.shape[0]
+        th = self.topology
+        if self.lambda_offsets > 0:
+            self.loss_acc[0:1].add_(self.lambda_offsets * (self.offsets * self.offsets).sum(1).mean())          # utils.py:764-776
+        call("n2m_s1_vert_step", ptr(self.grad_vclip), ptr(self.mvp), ptr(th.keys), th.slots, ptr(self.base_vertices), ptr(self.offsets),
+             ptr(self.m_vert), ptr(self.v_vert), ptr(self.vertices), ptr(self.vert_scratch), ptr(self.grad_offsets), V, self.lambda_lap,
+             self.lambda_offsets, -1.0, self.t0.cfg.eps, ptr(self.t0.opt_state), ptr(self.vert_state), ptr(self.loss_acc), stream())
 
     def vertex_gradient(self):
         """d loss / d vertices [V,3] of the last `loss_backward` (through dr.antialias and the projection of renderer.py:858; the

@@ -19,7 +19,7 @@ from oracle import raster_oracle as R
 pytestmark = pytest.mark.gpu
 
 
-def _setup(h0=96, w0=96, ssaa=2, steps=30, antialias=False, subdiv=4):
+def _setup(h0=96, w0=96, ssaa=2, steps=30, antialias=False, subdiv=4, **s1_kw):
     N = 1024
     cfg = Stage0Config(bound=1.0, num_rays=N, max_samples=N * 256)
     t0 = Stage0Trainer(cfg, seed=5)
@@ -39,7 +39,7 @@ def _setup(h0=96, w0=96, ssaa=2, steps=30, antialias=False, subdiv=4):
     # flip y in the projection (as the reference's provider does in its mvp)
     mvp = R.perspective_mvp(cam, fovy=2 * np.arctan(0.5 * h0 / intr[1]), aspect=w0 / h0)
     mvp[1] *= -1
-    s1 = Stage1Trainer(t0, torch.from_numpy(v), torch.from_numpy(f), h0, w0, ssaa=ssaa, antialias=antialias)
+    s1 = Stage1Trainer(t0, torch.from_numpy(v), torch.from_numpy(f), h0, w0, ssaa=ssaa, antialias=antialias, **s1_kw)
     gt = torch.rand(h0 * w0, 4, generator=g); gt[:, 3] = (gt[:, 3] > 0.5).float()
     bg = torch.rand(h0 * w0, 3, generator=g)
     return t0, s1, torch.from_numpy(mvp), rays_d.cuda(), gt.cuda(), bg.cuda()
@@ -179,3 +179,57 @@ def test_graph_replayed_step_equals_eager_step():
     s1.step(mvp, rays_d, gt, bg, use_graph=True)                   # pure replay
     torch.cuda.synchronize()
     assert len(s1._graphs) == 1 and abs(s1.read_loss() - loss_e) <= 1e-6 * abs(loss_e)
+
+
+def test_vertex_offset_optimizer_matches_autograd_and_torch_adam():
+    """lr_vert > 0: the `vertices_offsets` group of the reference's stage 1 (renderer.py:160,180; regularisers utils.py:750-779).  The total
+    gradient = image loss through dr.antialias (reference composition) + lambda_lap * laplacian_smooth_loss (the reference's own function)
+    + lambda_offsets * mean(sum(offsets^2)) by autograd; the update = torch.optim.Adam(lr_vert, eps=1e-15) on that gradient."""
+    from oracle import ref_stage
+    if not ref_stage.staged():
+        pytest.skip("reference Python files not staged")
+    ns = ref_stage.load("ref")
+    lam_lap, lam_off, lr_v = 0.01, 0.1, 1e-3
+    t0, s1, mvp, rays_d, gt, bg = _setup(ssaa=2, antialias=True, subdiv=2, steps=8, lr_vert=lr_v, lambda_lap=lam_lap, lambda_offsets=lam_off)
+    t0.opt_state[0] = 4096.0
+    g = torch.Generator(device="cuda").manual_seed(3)
+    s1.offsets.copy_(torch.randn(s1.offsets.shape, device="cuda", generator=g) * 2e-3)
+    s1.vertices.copy_(s1.base_vertices + s1.offsets)
+    off_old = s1.offsets.clone()
+    ref = _reference_stage1(ns, ref_stage, t0, s1, mvp, rays_d, gt, bg, antialias=True)            # image loss + its gradient w.r.t. the vertices
+    off = off_old.clone().requires_grad_(True)
+    reg = lam_lap * ns.utils.laplacian_smooth_loss(s1.base_vertices + off, s1.triangles) + lam_off * (off ** 2).sum(-1).mean()
+    reg.backward()
+    t0.gtable.zero_(); t0.g_mlp.zero_()
+    s1.step(mvp, rays_d, gt, bg)
+    torch.cuda.synchronize()
+    assert t0.opt_state[3].item() == 0
+    assert abs(s1.read_loss() - (ref["loss"] + float(reg))) <= 1e-3 * abs(ref["loss"] + float(reg))
+    img_part = s1.vertex_gradient()
+    reg_part = s1.grad_offsets - img_part
+    assert ((reg_part - off.grad).norm() / off.grad.norm()).item() <= 1e-4, ((reg_part - off.grad).norm() / off.grad.norm()).item()
+    tot_ref = ref["grad_vertices"] + off.grad
+    rel = ((s1.grad_offsets - tot_ref).norm() / tot_ref.norm()).item()
+    assert rel <= 3e-2, rel
+    assert img_part.abs().max().item() > 0 and (ref["grad_vertices"].norm() / off.grad.norm()).item() > 1e-3      # both parts matter in the sum
+    # Adam: torch's optimizer fed with OUR gradients, two steps (fresh state, as the reference's stage-1 trainer starts)
+    p = torch.nn.Parameter(off_old.clone())
+    opt = torch.optim.Adam([p], lr=lr_v, eps=1e-15)
+    p.grad = s1.grad_offsets.clone(); opt.step()
+    assert (s1.offsets - p.data).abs().max().item() <= 1e-3 * lr_v, (s1.offsets - p.data).abs().max().item()
+    assert torch.equal(s1.vertices, s1.base_vertices + s1.offsets) and s1.vert_state[0].item() == 1
+    s1.step(mvp, rays_d, gt, bg)
+    torch.cuda.synchronize()
+    p.grad = s1.grad_offsets.clone(); opt.step()
+    assert (s1.offsets - p.data).abs().max().item() <= 2e-3 * lr_v
+    assert s1.vert_state[0].item() == 2
+    # a skipped step (found_inf) leaves the group untouched
+    before = s1.offsets.clone()
+    s1.forward(mvp, rays_d); s1.loss_backward(gt, bg)
+    s1.grad_vclip[0, 0] = float("inf")
+    from nerf2mesh_b200._lib import call, ptr, stream
+    call("n2m_s1_vert_check", ptr(s1.grad_vclip), s1.vertices.shape[0], ptr(t0.opt_state), stream())
+    scale = t0.opt_state[0].item()
+    t0.adam(between=s1._vertex_step)
+    torch.cuda.synchronize()
+    assert torch.equal(s1.offsets, before) and s1.vert_state[0].item() == 2 and t0.opt_state[0].item() == 0.5 * scale
