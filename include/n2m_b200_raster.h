@@ -8,8 +8,8 @@
  *   n2m_rasterize             dr.rasterize(glctx, pos, tri, (H, W))   (renderer.py:860; also :338, :968)
  *       pos  [V,4] f32 clip-space vertices, tri [F,3] i32, rast [H,W,4] f32 = (u, v, z/w, triangle_id + 1), zeros where empty;
  *       pixel (x, y) samples NDC ((x+0.5)/W*2-1, (y+0.5)/H*2-1); (u, v) perspective-correct barycentrics of vertices 0 / 1;
- *       vis [H*W] u64 and queue [F+1] u32 are caller-allocated scratch.  Triangles with a vertex at w <= 0 are skipped
- *       (no near-plane clipping).
+ *       vis [H*W] u64 and queue [F+1] u32 are caller-allocated scratch.  Fragments outside -1 <= z/w <= 1 are clipped; triangles that
+ *       cross the camera plane (some w <= 0) are rasterised in homogeneous coordinates (the part in front of the near plane).
  *   n2m_interpolate_forward   dr.interpolate(attr, rast, tri)         (renderer.py:862-863): out [H*W,A] = u a0 + v a1 + (1-u-v) a2
  *   n2m_interpolate_backward  its gradient w.r.t. attr [V,A] (accumulated into the caller's zero-initialised buffer)
  *   n2m_compact_covered       xyzs[mask], dirs[mask] of renderer.py:865-880 without the boolean-mask host sync: covered pixel

@@ -15,8 +15,12 @@
 //   k_rast_resolve   : one thread per pixel: decode the winner, recompute its screen-space barycentrics with the SAME fp32 expressions,
 //                      make them perspective-correct with the clip-space w, write (u, v, z/w, id + 1) as one float4
 //   k_interp_fwd/bwd : attr = u a0 + v a1 + (1-u-v) a2 per pixel; backward scatters to the three vertices with red.global.add
-// Not reproduced (documented in oracle/raster_oracle.py): near-plane clipping (triangles with a vertex at w <= 0 are skipped) and the
-// exact OpenGL top-left fill rule for pixel centres that lie exactly on an edge.
+// Near / far clipping: triangles in front of the camera plane (all w > 0) are tested per pixel against -1 <= z/w <= 1.  Triangles that
+// CROSS the camera plane (some w <= 0: ground or shell triangles around a camera inside the scene) are rasterised in 2-D homogeneous
+// coordinates (Olano & Greer 1997): for pixel NDC (X, Y) the solution of sum_i b'_i (x_i, y_i, w_i) = (X, Y, 1) is non-negative exactly
+// on the part of the triangle in front of the camera, z/w = sum_i b'_i z_i gets the same [-1, 1] test, (u, v) = (b'_0, b'_1) / sum b'
+// -- the result of clipping against the near plane without building clipped polygons; only the bounding box comes from the clipped
+// outline.  Not reproduced (oracle/raster_oracle.py): the exact OpenGL top-left fill rule for pixel centres exactly on an edge.
 #include "n2m_common.cuh"
 #include "../../include/n2m_b200_raster.h"
 
@@ -26,19 +30,66 @@ namespace {
 constexpr uint32_t kInlinePixels = 64;
 
 struct TriSetup {
-    float x0, y0, x1, y1, x2, y2;     // pixel coordinates (pixel centre x + 0.5)
-    float z0, z1, z2;                 // NDC depth
-    float w0, w1, w2;                 // clip w
-    float inv_area;
+    float x0, y0, x1, y1, x2, y2;     // pixel coordinates (pixel centre x + 0.5);  homogeneous path: rows 0 / 1 of adj(M) (A, B) pairs
+    float z0, z1, z2;                 // NDC depth;  homogeneous path: clip-space z
+    float w0, w1, w2;                 // clip w;  homogeneous path: the constant terms C_k of the three solutions
+    float inv_area;                   // homogeneous path: 1 / det(M)
+    float a2, b2;                     // homogeneous path: (A_2, B_2)
     int xa, xb, ya, yb;               // inclusive pixel bounding box, clamped to the target
     bool valid;
+    bool homog;                       // the triangle crosses the camera plane (one or two vertices at w <= 0)
 };
+
+// pixel bounding box of the triangle clipped against the near plane z >= -w (Sutherland-Hodgman, at most four points)
+__device__ __forceinline__ bool near_clip_bbox(const float4 p0, const float4 p1, const float4 p2, uint32_t H, uint32_t W, int& xa, int& xb, int& ya, int& yb) {
+    const float4 poly[3] = {p0, p1, p2};
+    float xmin = 3.4e38f, xmax = -3.4e38f, ymin = 3.4e38f, ymax = -3.4e38f;
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float4 a = poly[k], b = poly[(k + 1) % 3];
+        const float da = a.z + a.w, db = b.z + b.w;
+        float4 q[2]; int n = 0;
+        if (da >= 0.f) q[n++] = a;
+        if ((da >= 0.f) != (db >= 0.f)) {
+            const float t = __fdiv_rn(da, da - db);
+            q[n++] = make_float4(a.x + t * (b.x - a.x), a.y + t * (b.y - a.y), a.z + t * (b.z - a.z), a.w + t * (b.w - a.w));
+        }
+        for (int j = 0; j < n; ++j) {
+            const float rw = __fdiv_rn(1.f, fmaxf(q[j].w, 1e-30f));
+            const float sx = (q[j].x * rw * 0.5f + 0.5f) * (float)W, sy = (q[j].y * rw * 0.5f + 0.5f) * (float)H;
+            xmin = fminf(xmin, sx); xmax = fmaxf(xmax, sx); ymin = fminf(ymin, sy); ymax = fmaxf(ymax, sy);
+            any = true;
+        }
+    }
+    if (!any) return false;
+    xa = max((int)floorf(fminf(xmin, (float)W + 1.f) - 0.5f), 0); xb = min((int)ceilf(fmaxf(xmax, -1.f) - 0.5f), (int)W - 1);
+    ya = max((int)floorf(fminf(ymin, (float)H + 1.f) - 0.5f), 0); yb = min((int)ceilf(fmaxf(ymax, -1.f) - 0.5f), (int)H - 1);
+    return xa <= xb && ya <= yb;
+}
 
 __device__ __forceinline__ TriSetup setup_tri(const float4* __restrict__ pos, const int32_t* __restrict__ tri, uint32_t f, uint32_t H, uint32_t W) {
     TriSetup t;
     const int i0 = tri[3 * f], i1 = tri[3 * f + 1], i2 = tri[3 * f + 2];
     const float4 p0 = __ldg(pos + i0), p1 = __ldg(pos + i1), p2 = __ldg(pos + i2);
+    t.homog = false;
+    t.a2 = t.b2 = 0.f;
     t.valid = p0.w > 0.f && p1.w > 0.f && p2.w > 0.f;
+    if (!t.valid && (p0.w > 0.f || p1.w > 0.f || p2.w > 0.f)) {
+        // crosses the camera plane: b'_k = (A_k X + B_k Y + C_k) / det, (A_k, B_k, C_k) = row k of adj(M), M = [x; y; w] of the vertices
+        t.homog = true;
+        t.x0 = p1.y * p2.w - p2.y * p1.w; t.y0 = p2.x * p1.w - p1.x * p2.w; t.w0 = p1.x * p2.y - p2.x * p1.y;
+        t.x1 = p2.y * p0.w - p0.y * p2.w; t.y1 = p0.x * p2.w - p2.x * p0.w; t.w1 = p2.x * p0.y - p0.x * p2.y;
+        t.a2 = p0.y * p1.w - p1.y * p0.w; t.b2 = p1.x * p0.w - p0.x * p1.w; t.w2 = p0.x * p1.y - p1.x * p0.y;
+        t.x2 = t.y2 = 0.f;
+        const float det = p0.x * t.x0 + p1.x * t.x1 + p2.x * t.a2;
+        t.z0 = p0.z; t.z1 = p1.z; t.z2 = p2.z;
+        t.valid = det != 0.f && isfinite(det);
+        t.inv_area = t.valid ? __fdiv_rn(1.f, det) : 0.f;
+        t.xa = t.ya = 0; t.xb = t.yb = -1;
+        if (t.valid) t.valid = near_clip_bbox(p0, p1, p2, H, W, t.xa, t.xb, t.ya, t.yb);
+        return t;
+    }
     t.w0 = p0.w; t.w1 = p1.w; t.w2 = p2.w;
     const float r0 = __fdiv_rn(1.f, p0.w), r1 = __fdiv_rn(1.f, p1.w), r2 = __fdiv_rn(1.f, p2.w);
     const float hw = 0.5f * (float)W, hh = 0.5f * (float)H;
@@ -68,14 +119,24 @@ __device__ __forceinline__ bool bary(const TriSetup& t, float px, float py, floa
     return b0 >= 0.f && b1 >= 0.f && b2 >= 0.f;
 }
 
+// homogeneous path: the three solutions b'_k at pixel (x, y); false when the pixel is not covered in front of the camera
+__device__ __forceinline__ bool bary_homog(const TriSetup& t, int x, int y, uint32_t H, uint32_t W, float& b0, float& b1, float& b2) {
+    const float X = ((float)x + 0.5f) * __fdiv_rn(2.f, (float)W) - 1.f, Y = ((float)y + 0.5f) * __fdiv_rn(2.f, (float)H) - 1.f;
+    b0 = (t.x0 * X + t.y0 * Y + t.w0) * t.inv_area;
+    b1 = (t.x1 * X + t.y1 * Y + t.w1) * t.inv_area;
+    b2 = (t.a2 * X + t.b2 * Y + t.w2) * t.inv_area;
+    return b0 >= 0.f && b1 >= 0.f && b2 >= 0.f;
+}
+
 __device__ __forceinline__ uint32_t depth_key(float z) {          // order-preserving map float -> uint32
     const uint32_t u = __float_as_uint(z);
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
-__device__ __forceinline__ void shade_pixel(const TriSetup& t, uint32_t f, int x, int y, uint32_t W, unsigned long long* __restrict__ vis) {
+__device__ __forceinline__ void shade_pixel(const TriSetup& t, uint32_t f, int x, int y, uint32_t H, uint32_t W, unsigned long long* __restrict__ vis) {
     float b0, b1, b2;
-    if (!bary(t, (float)x + 0.5f, (float)y + 0.5f, b0, b1, b2)) return;
+    if (t.homog) { if (!bary_homog(t, x, y, H, W, b0, b1, b2)) return; }
+    else if (!bary(t, (float)x + 0.5f, (float)y + 0.5f, b0, b1, b2)) return;
     const float z = b0 * t.z0 + b1 * t.z1 + b2 * t.z2;
     if (!(z >= -1.f && z <= 1.f)) return;
     const unsigned long long key = ((unsigned long long)depth_key(z) << 32) | (unsigned long long)(f + 1u);
@@ -99,7 +160,7 @@ k_rast_small(const float4* __restrict__ pos, const int32_t* __restrict__ tri, ui
     const uint32_t bw = (uint32_t)(t.xb - t.xa + 1), bh = (uint32_t)(t.yb - t.ya + 1);
     if (bw * bh > kInlinePixels) { queue[1 + atomicAdd(queue, 1u)] = f; return; }
     for (int y = t.ya; y <= t.yb; ++y)
-        for (int x = t.xa; x <= t.xb; ++x) shade_pixel(t, f, x, y, W, vis);
+        for (int x = t.xa; x <= t.xb; ++x) shade_pixel(t, f, x, y, H, W, vis);
 }
 
 __global__ void __launch_bounds__(256)
@@ -110,7 +171,7 @@ k_rast_large(const float4* __restrict__ pos, const int32_t* __restrict__ tri, ui
         const uint32_t f = queue[1 + q];
         const TriSetup t = setup_tri(pos, tri, f, H, W);
         const uint32_t bw = (uint32_t)(t.xb - t.xa + 1), n = bw * (uint32_t)(t.yb - t.ya + 1);
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) shade_pixel(t, f, t.xa + (int)(i % bw), t.ya + (int)(i / bw), W, vis);
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) shade_pixel(t, f, t.xa + (int)(i % bw), t.ya + (int)(i / bw), H, W, vis);
     }
 }
 
@@ -124,6 +185,13 @@ k_rast_resolve(const float4* __restrict__ pos, const int32_t* __restrict__ tri, 
     const uint32_t f = (uint32_t)(key & 0xffffffffull) - 1u;
     const TriSetup t = setup_tri(pos, tri, f, H, W);
     float b0, b1, b2;
+    if (t.homog) {
+        bary_homog(t, (int)(i % W), (int)(i / W), H, W, b0, b1, b2);
+        const float zh = b0 * t.z0 + b1 * t.z1 + b2 * t.z2;
+        const float invs = __fdiv_rn(1.f, b0 + b1 + b2);
+        rast[i] = make_float4(b0 * invs, b1 * invs, zh, (float)(f + 1u));
+        return;
+    }
     bary(t, (float)(i % W) + 0.5f, (float)(i / W) + 0.5f, b0, b1, b2);
     const float z = b0 * t.z0 + b1 * t.z1 + b2 * t.z2;
     const float p0 = __fdiv_rn(b0, t.w0), p1 = __fdiv_rn(b1, t.w1), p2 = __fdiv_rn(b2, t.w2);

@@ -14,9 +14,11 @@ output convention (nvdiffrast documentation, "rasterize" / "interpolate"):
 
 "Parity unpinned": the reference's tests hold no golden vectors at this boundary (it has no tests at all) and the library cannot be
 run here, so this oracle is anchored on the documented convention and on the reference's call sites only; exact fill-rule ties
-(a pixel centre exactly on an edge) and near-plane clipping follow OpenGL rules in the library and are NOT reproduced: triangles with
-any w <= 0 are skipped, and an edge hit counts as covered.  The tests avoid both and allow id mismatches only on pixels whose
-smallest screen-space barycentric is within 1e-5 of zero.
+(a pixel centre exactly on an edge) follow OpenGL rules in the library and are NOT reproduced: an edge hit counts as covered.  The
+tests avoid them and allow id mismatches only on pixels whose smallest screen-space barycentric is within 1e-5 of zero.
+Near / far clipping: triangles in front of the camera plane (all w > 0) are tested per pixel against -1 <= z/w <= 1; triangles that
+cross the camera plane (some w <= 0) are rasterised in homogeneous coordinates (`_rasterize_homogeneous`), which yields exactly the part
+in front of the near plane without constructing clipped polygons -- the result the library's clipper produces.
 """
 import numpy as np
 
@@ -34,6 +36,8 @@ def rasterize(pos, tri, H, W):
     for f in range(tri.shape[0]):
         i0, i1, i2 = tri[f]
         if w[i0] <= 0 or w[i1] <= 0 or w[i2] <= 0:
+            if not (w[i0] <= 0 and w[i1] <= 0 and w[i2] <= 0):
+                _rasterize_homogeneous(pos, f, i0, i1, i2, H, W, rast, zbuf, idbuf)
             continue
         x0, y0, x1, y1, x2, y2 = sx[i0], sy[i0], sx[i1], sy[i1], sx[i2], sy[i2]
         area = (x1 - x0) * (y2 - y0) - (x2 - x0) * (y1 - y0)
@@ -66,6 +70,65 @@ def rasterize(pos, tri, H, W):
         sub[win, 0] = (p0 / ps)[win]; sub[win, 1] = (p1 / ps)[win]; sub[win, 2] = z[win]; sub[win, 3] = f + 1
         sub_z[win] = z[win]; sub_id[win] = f + 1
     return rast
+
+
+def near_clip_bbox(p0, p1, p2, H, W):
+    """pixel bounding box (xa, xb, ya, yb, inclusive, clamped; None if empty) of a triangle clipped against the near plane z >= -w"""
+    poly = [np.asarray(p, np.float64) for p in (p0, p1, p2)]
+    out = []
+    for k in range(3):
+        a, b = poly[k], poly[(k + 1) % 3]
+        da, db = a[2] + a[3], b[2] + b[3]
+        if da >= 0:
+            out.append(a)
+        if (da >= 0) != (db >= 0):
+            t = da / (da - db)
+            out.append(a + t * (b - a))
+    if not out:
+        return None
+    xs, ys = [], []
+    for q in out:
+        ww = max(q[3], 1e-30)
+        xs.append((q[0] / ww * 0.5 + 0.5) * W); ys.append((q[1] / ww * 0.5 + 0.5) * H)
+    xa = int(max(np.floor(min(min(xs), W + 1.0) - 0.5), 0)); xb = int(min(np.ceil(max(max(xs), -1.0) - 0.5), W - 1))
+    ya = int(max(np.floor(min(min(ys), H + 1.0) - 0.5), 0)); yb = int(min(np.ceil(max(max(ys), -1.0) - 0.5), H - 1))
+    if xa > xb or ya > yb:
+        return None
+    return xa, xb, ya, yb
+
+
+def _rasterize_homogeneous(pos, f, i0, i1, i2, H, W, rast, zbuf, idbuf):
+    """a triangle with one or two vertices at w <= 0 (it crosses the camera plane): 2-D homogeneous rasterization (Olano & Greer 1997).
+    For pixel NDC (X, Y) solve  sum_i b'_i (x_i, y_i, w_i) = (X, Y, 1): the pixel is covered iff all b'_i >= 0 (the point then lies in
+    the triangle and in front of the camera), z/w = sum_i b'_i z_i (tested against [-1, 1]: the near / far clip, per pixel),
+    (u, v) = (b'_0, b'_1) / sum b'."""
+    p = [pos[i0], pos[i1], pos[i2]]
+    box = near_clip_bbox(p[0], p[1], p[2], H, W)
+    if box is None:
+        return
+    xa, xb, ya, yb = box
+    M = np.array([[p[0][0], p[1][0], p[2][0]], [p[0][1], p[1][1], p[2][1]], [p[0][3], p[1][3], p[2][3]]], np.float64)
+    det = np.linalg.det(M)
+    if det == 0 or not np.isfinite(det):
+        return
+    Mi = np.linalg.inv(M)
+    px = (np.arange(xa, xb + 1) + 0.5) / W * 2 - 1
+    py = (np.arange(ya, yb + 1) + 0.5) / H * 2 - 1
+    PX, PY = np.meshgrid(px, py)
+    b = [Mi[k, 0] * PX + Mi[k, 1] * PY + Mi[k, 2] for k in range(3)]
+    inside = (b[0] >= 0) & (b[1] >= 0) & (b[2] >= 0)
+    if not inside.any():
+        return
+    z = b[0] * p[0][2] + b[1] * p[1][2] + b[2] * p[2][2]
+    ok = inside & (z >= -1) & (z <= 1)
+    sub_z = zbuf[ya:yb + 1, xa:xb + 1]; sub_id = idbuf[ya:yb + 1, xa:xb + 1]
+    win = ok & ((z < sub_z) | ((z == sub_z) & (f + 1 < sub_id)))
+    if not win.any():
+        return
+    bs = b[0] + b[1] + b[2]
+    sub = rast[ya:yb + 1, xa:xb + 1]
+    sub[win, 0] = (b[0] / bs)[win]; sub[win, 1] = (b[1] / bs)[win]; sub[win, 2] = z[win]; sub[win, 3] = f + 1
+    sub_z[win] = z[win]; sub_id[win] = f + 1
 
 
 def edge_distance(pos, tri, rast):

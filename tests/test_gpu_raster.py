@@ -109,3 +109,49 @@ def test_compact_covered_matches_boolean_mask():
     order = torch.argsort(pix[:n])
     assert torch.equal(pix[:n][order].long(), torch.nonzero(mask).view(-1))
     assert torch.equal(pts[:n][order], xyz.view(-1, 3)[mask]) and torch.equal(pd[:n][order], dirs[mask])
+
+
+@pytest.mark.parametrize("H,W", [(64, 64), (200, 320)])
+def test_triangles_crossing_the_camera_plane_match_oracle(H, W):
+    """a camera INSIDE the mesh (the outer shells of a bound-16 scene, a ground plane under the camera): triangles with one or two
+    vertices behind the camera plane are rasterised in homogeneous coordinates -- the part in front of the near plane, with the same
+    depth and perspective-correct barycentrics the oracle (tests/test_raster_oracle.py: analytic ground-plane check) produces"""
+    rng = np.random.default_rng(0)
+    near, far, f = 0.1, 100.0, 1.0 / np.tan(0.3)
+    P = np.array([[f * H / W, 0, 0, 0], [0, f, 0, 0], [0, 0, (far + near) / (near - far), 2 * far * near / (near - far)], [0, 0, -1, 0]])
+    # ground grid 12 x 12 from z = +6 (behind) to z = -40, a big icosphere around the camera (radius 8, seen from inside), a small one in front
+    gx, gz = np.meshgrid(np.linspace(-20, 20, 13), np.linspace(6, -40, 13), indexing="ij")
+    gv = np.stack([gx.reshape(-1), np.full(gx.size, -0.2), gz.reshape(-1)], 1)          # 0.2 below the eye: the cells that cross z = 0 are in view
+    gf = []
+    for i in range(12):
+        for j in range(12):
+            a = i * 13 + j
+            gf += [[a, a + 13, a + 14], [a, a + 14, a + 1]]
+    sv, sf = R.icosphere(2, radius=8.0)
+    sv = sv + np.array([0.3, -0.2, 0.5], np.float32)
+    tv, tf = R.icosphere(2, radius=0.7)
+    tv = tv + np.array([0.5, 0.2, -4.0], np.float32)
+    v = np.concatenate([gv, sv, tv]).astype(np.float32)
+    fcs = np.concatenate([np.array(gf), sf + len(gv), tf + len(gv) + len(sv)]).astype(np.int32)
+    pos = (np.concatenate([v, np.ones((len(v), 1), np.float32)], 1) @ P.T).astype(np.float32)
+    w = pos[:, 3]
+    crossing = ((w[fcs] <= 0).any(1) & (w[fcs] > 0).any(1)).sum()
+    assert crossing > 30 and ((w[fcs] <= 0).all(1)).sum() > 30                       # both kinds are present
+    ref = R.rasterize(pos, fcs, H, W)
+    rast, _ = dr.rasterize(dr.RasterizeCudaContext(), torch.from_numpy(pos).cuda()[None], torch.from_numpy(fcs).cuda(), (H, W))
+    out = rast[0].cpu().numpy().astype(np.float64)
+    assert (ref[..., 3] > 0).mean() > 0.95                                           # the shell around the camera fills the view
+    crossing_ids = np.nonzero((w[fcs] <= 0).any(1))[0] + 1
+    assert np.isin(ref[..., 3], crossing_ids).mean() > 0.05                          # and crossing triangles are really visible
+    mism = out[..., 3] != ref[..., 3]
+    # ids may differ only where a pixel centre is within fp32 rounding of an edge (smallest barycentric ~ 0) or two depths tie
+    near_edge = np.minimum(np.minimum(ref[..., 0], ref[..., 1]), 1 - ref[..., 0] - ref[..., 1]) < 2e-4
+    near_edge_o = np.minimum(np.minimum(out[..., 0], out[..., 1]), 1 - out[..., 0] - out[..., 1]) < 2e-4
+    assert (mism & ~(near_edge | near_edge_o)).sum() == 0, int((mism & ~(near_edge | near_edge_o)).sum())
+    assert mism.mean() < 5e-3
+    ok = ~mism & (ref[..., 3] > 0)
+    assert np.abs(out[ok, :2] - ref[ok, :2]).max() <= 5e-4 and np.abs(out[ok, 2] - ref[ok, 2]).max() <= 2e-5
+    # world positions through interpolate: the ground pixels lie on y = -0.2
+    xyz, _ = dr.interpolate(torch.from_numpy(v).cuda()[None], rast, torch.from_numpy(fcs).cuda())
+    ground = torch.from_numpy((out[..., 3] > 0) & (out[..., 3] <= len(gf))).cuda()
+    assert ground.any() and (xyz[0][ground][:, 1] + 0.2).abs().max().item() <= 1e-3

@@ -57,3 +57,56 @@ def test_perspective_correct_barycentrics_and_interpolation_roundtrip():
     ga = R.interpolate_backward(g, v.shape, r, f)
     a2 = rng.standard_normal(v.shape)
     assert np.isclose((R.interpolate(a2, r, f) * g).sum(), (ga * a2).sum())
+
+
+def _ground_scene():
+    """camera at the origin looking down -z (OpenGL), a ground quad y = -1 reaching from BEHIND the camera (z = +5) to z = -50, plus a
+    wall behind the camera that must not appear"""
+    near, far, f = 0.1, 100.0, 1.0 / np.tan(0.3)
+    proj = np.array([[f, 0, 0, 0], [0, f, 0, 0], [0, 0, (far + near) / (near - far), 2 * far * near / (near - far)], [0, 0, -1, 0]])
+    v = np.array([[-30, -1, 5], [30, -1, 5], [30, -1, -50], [-30, -1, -50],            # ground: two vertices behind the camera
+                  [-5, -5, 3], [5, -5, 3], [0, 5, 3]], np.float64)                     # wall entirely behind the camera (all w < 0)
+    pos = np.concatenate([v, np.ones((len(v), 1))], 1) @ proj.T
+    tri = np.array([[0, 1, 2], [0, 2, 3], [4, 5, 6]], np.int32)
+    return pos, tri, v, (near, far, f)
+
+
+def test_triangles_crossing_the_camera_plane_are_clipped_not_dropped():
+    pos, tri, v, (near, far, f) = _ground_scene()
+    assert (pos[:2, 3] < 0).all() and (pos[2:4, 3] > 0).all() and (pos[4:, 3] < 0).all()
+    H = W = 48
+    r = R.rasterize(pos, tri, H, W)
+    cov = r[..., 3] > 0
+    ys = (np.arange(H) + 0.5) / H * 2 - 1
+    xs = (np.arange(W) + 0.5) / W * 2 - 1
+    A, B = (far + near) / (near - far), 2 * far * near / (near - far)
+    for row in range(H):
+        for col in range(0, W, 7):
+            Y, X = ys[row], xs[col]
+            # the pixel's ray (X / f, Y / f, -1) t meets y = -1 at t = -f / Y (Y < 0), eye depth -t
+            hit = Y < 0 and (f / -Y) <= 50 and abs(X / f * (f / -Y)) <= 30
+            assert cov[row, col] == hit, (row, col)
+            if hit:
+                t = f / -Y
+                assert abs(r[row, col, 2] - (A * -t + B) / t) < 1e-9
+                # perspective-correct interpolation of the world position through (u, v) lands on the ray / plane intersection
+                i0, i1, i2 = tri[int(r[row, col, 3]) - 1]
+                p = r[row, col, 0] * v[i0] + r[row, col, 1] * v[i1] + (1 - r[row, col, 0] - r[row, col, 1]) * v[i2]
+                assert np.allclose(p, [X / f * t, -1.0, -t], atol=1e-8)
+    assert not (r[..., 3] == 3).any()                                  # the wall behind the camera is never visible
+    assert cov.sum() > 0.3 * H * W
+
+
+def test_near_and_far_planes_clip_per_pixel():
+    pos, tri, v, (near, far, f) = _ground_scene()
+    # same ground, camera lifted so that the ground passes through the near plane below the view: nothing closer than `near` survives
+    v2 = v.copy(); v2[:4, 1] = -0.05                                    # 0.05 below the eye: crosses z_eye = -near at steep rays
+    P = np.array([[f, 0, 0, 0], [0, f, 0, 0], [0, 0, (far + near) / (near - far), 2 * far * near / (near - far)], [0, 0, -1, 0]])
+    pos2 = np.concatenate([v2, np.ones((len(v2), 1))], 1) @ P.T
+    r = R.rasterize(pos2, tri, 64, 64)
+    cov = r[..., 3] > 0
+    assert cov.any() and (r[cov, 2] >= -1).all() and (r[cov, 2] <= 1).all()
+    ys = (np.arange(64) + 0.5) / 64 * 2 - 1
+    # rows whose ray reaches the plane before the near distance are empty: t = 0.05 f / -Y < near  <=>  -Y > 0.05 f / near
+    steep = -ys > 0.05 * f / near
+    assert not cov[steep].any() and cov[(~steep) & (ys < 0)].any()
