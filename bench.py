@@ -637,7 +637,8 @@ def run_stage1(args):
     h0 = w0 = 800
     t0 = Stage0Trainer(Stage0Config(bound=1.0, num_rays=1024, max_samples=1024 * 128), seed=0)
     v, f = R.icosphere(7)                                         # 327 680 faces ~ the reference's decimate target 3e5 (main.py:101)
-    s1 = Stage1Trainer(t0, torch.from_numpy(v), torch.from_numpy(f), h0, w0, ssaa=2, antialias=bool(args.antialias))
+    lr_vert = float(args.lr_vert) if args.antialias else 0.0           # the vertex offsets are trained through dr.antialias only
+    s1 = Stage1Trainer(t0, torch.from_numpy(v), torch.from_numpy(f), h0, w0, ssaa=2, antialias=bool(args.antialias), lr_vert=lr_vert)
     g = torch.Generator().manual_seed(0)
     views = []
     for k in range(8):
@@ -701,7 +702,8 @@ def run_stage1(args):
             "value": hi / (ms * 1e-3), "unit": "super-sampled pixels/s", "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
             "config": {"workload": "lego_stage1", "mesh_faces": int(f.shape[0]), "image": [h0, w0], "ssaa": 2, "raster": [s1.h, s1.w],
-                       "covered_pixels_per_step": cov.item() / K, "antialias": bool(s1.antialias), "cuda_graph": ug},
+                       "covered_pixels_per_step": cov.item() / K, "antialias": bool(s1.antialias), "cuda_graph": ug,
+                       "lr_vert": lr_vert, "lambda_lap": s1.lambda_lap, "lambda_offsets": s1.lambda_offsets},
             "antialias_ms": aa_ms,
             "rasterize_ms": q0.elapsed_time(q1) / 10, "rasterize_pixels_per_s": hi / (q0.elapsed_time(q1) / 10 * 1e-3),
             "forward_ms": r0.elapsed_time(r1) / 10}
@@ -721,6 +723,7 @@ def main():
     ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="--impl reference: wall-clock budget of the whole CPU run")
     ap.add_argument("--skip-reference", action="store_true", help="skip the same-box reference-CUDA leg")
     ap.add_argument("--psnr-iters", type=int, default=300, help="training steps of the PSNR-vs-reference pair (0 = skip)")
+    ap.add_argument("--lr-vert", type=float, default=1e-4, help="lego_stage1 with --antialias 1: learning rate of the vertex-offset group (main.py:49; 0 = vertices fixed)")
     ap.add_argument("--antialias", type=int, default=1, help="lego_stage1: 1 = dr.antialias on (rgbs, alphas) as the reference does (renderer.py:886-887)")
     ap.add_argument("--prefetch-at", default="optimizer", choices=["optimizer", "start"],
                     help="where the next batch's march is released on the side stream: under the optimizer stage or under the forward pass")
