@@ -306,3 +306,130 @@ def test_step_prefetch_ordering(monkeypatch):
     tr = trainer("optimizer")
     tr.step(*batch)
     assert [(s, n) for s, k, n in log if k == "run"] == [("main", "march"), ("main", "compute+adam")]
+
+
+def test_stage1_step_call_sequences(monkeypatch):
+    """Stage1Trainer._step_body with the CUDA layer mocked: plain, antialiased, and antialiased with the vertex-offset group (the check
+    before the optimizer head, the group's update between the table sweep and the GradScaler update)"""
+    import types
+    import nerf2mesh_b200.stage0 as S0
+    import nerf2mesh_b200.stage1 as S1
+    import nerf2mesh_b200.raster as RA
+
+    calls = []
+    rec = lambda name, *a: calls.append(name)
+    for mod in (S0, S1, RA):
+        monkeypatch.setattr(mod, "call", rec)
+    for mod in (S0, S1, RA):
+        monkeypatch.setattr(mod, "stream", lambda: 0)
+
+    def fake_rasterize(glctx, pos, tri, resolution, **kw):          # the wrapper itself refuses host tensors: there is no CPU path
+        calls.append("n2m_rasterize")
+        return torch.zeros(1, resolution[0], resolution[1], 4), None
+    monkeypatch.setattr(RA, "rasterize", fake_rasterize)
+
+    class FakeStream:
+        def wait_stream(self, o): pass
+    class Ctx:
+        def __init__(self, s): pass
+        def __enter__(self): return self
+        def __exit__(self, *a): return False
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: FakeStream())
+    monkeypatch.setattr(torch.cuda, "Stream", lambda *a, **k: FakeStream())
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: Ctx(s))
+
+    t0 = object.__new__(S0.Stage0Trainer)
+    t0.device = "cpu"
+    t0.cfg = types.SimpleNamespace(eps=1e-15)
+    for k in ("table", "offsets", "opt_state", "wpack", "color_master", "m_table", "v_table", "mlp", "m_mlp", "v_mlp"):
+        setattr(t0, k, torch.zeros(8))
+    t0.gtables, t0.g_mlps, t0.parity, t0.rows, t0._adam_stream, t0.fused_bwd, t0.global_step = [torch.zeros(8)] * 2, [torch.zeros(8)], 0, 8, None, True, 0
+    t0.params = S0.S0Params()
+
+    def make(**kw):
+        monkeypatch.setattr(RA, "TopologyHash", lambda tri: types.SimpleNamespace(keys=torch.zeros(4, dtype=torch.int64), opp=torch.zeros(4, 2, dtype=torch.int32), slots=4, tri=tri))
+        return S1.Stage1Trainer(t0, torch.rand(5, 3), torch.tensor([[0, 1, 2], [2, 3, 4]]), 4, 4, ssaa=2, **kw)
+
+    mvp, rd, gt, bg = torch.eye(4), torch.rand(16, 3), torch.rand(16, 4), torch.rand(16, 3)
+    fwd = ["n2m_rasterize", "n2m_s1_points", "n2m_s0_encode_points", "n2m_s0_mlp_fwd"]
+    adam = ["n2m_s0_adam_head", "n2m_s0_adam_mlp", "n2m_s0_adam_tables", "n2m_s0_adam_post"]
+    s1 = make()
+    s1.step(mvp, rd, gt, bg)
+    assert calls == fwd + ["n2m_s1_loss", "n2m_s0_bwd_fused_part"] + adam and t0.global_step == 1
+    calls.clear()
+    s1 = make(antialias=True)
+    s1.step(mvp, rd, gt, bg)
+    aa_f, aa_b = ["n2m_s1_rgba", "n2m_antialias_forward"], ["n2m_s1_loss_aa", "n2m_antialias_backward", "n2m_s1_dout"]
+    assert calls == fwd + aa_f + aa_b + ["n2m_s0_bwd_fused_part"] + adam
+    calls.clear()
+    s1 = make(antialias=True, lr_vert=1e-4)
+    s1.step(mvp, rd, gt, bg)
+    assert calls == fwd + aa_f + aa_b + ["n2m_s0_bwd_fused_part", "n2m_s1_vert_check"] + adam[:3] + ["n2m_s1_vert_step", adam[3]]
+    assert s1.vert_state[1].item() == pytest_approx(1e-4)
+    # the image loss reaches the vertices through antialias only
+    try:
+        make(lr_vert=1e-4)
+        assert False
+    except ValueError:
+        pass
+    # graph mode insists on a device-resident mvp (the graph is keyed by its address)
+    s1._warm = True
+    try:
+        s1.step(mvp, rd, gt, bg, use_graph=True)
+        assert False
+    except RuntimeError as e:
+        assert "use_graph" in str(e)
+
+
+def pytest_approx(x):
+    import pytest
+    return pytest.approx(x, rel=1e-6)
+
+
+def test_render_chunking_and_round_continuation(monkeypatch):
+    """Stage0Trainer.render (device-side alive-ray rounds) with the CUDA layer mocked: one begin / rounds / finish per chunk, further rounds
+    while the control block reports rays alive, row and round diagnostics summed over the chunks"""
+    import types
+    import nerf2mesh_b200.stage0 as S0
+
+    log = []
+    alive_script = []          # values ctl[10] takes after successive `rounds` calls
+
+    tr = object.__new__(S0.Stage0Trainer)
+    tr.device = "cpu"
+    tr.params = S0.S0Params()
+    tr.aabb = torch.zeros(6); tr.density_bitfield = torch.zeros(8, dtype=torch.uint8)
+    tr.table = tr.offsets = tr.wpack = torch.zeros(8)
+    tr._prefetched = None
+    tr.drop_prefetch = lambda: None
+
+    def fake_call(name, *a):
+        log.append((name, a))
+        if name == "n2m_s0_render_begin":
+            tr._render_buf["ctl"].zero_()
+        if name == "n2m_s0_render_rounds":
+            ctl = tr._render_buf["ctl"]
+            ctl[10] = alive_script.pop(0) if alive_script else 0
+            ctl[12] += int(a[6]); ctl[13] += 100
+    monkeypatch.setattr(S0, "call", fake_call)
+    monkeypatch.setattr(S0, "stream", lambda: 0)
+
+    ro, rd = torch.rand(100, 3), torch.rand(100, 3)
+    img, ws, dep = tr.render(ro, rd, bg_color=1.0, chunk=40)                      # 3 ragged chunks: 40, 40, 20
+    names = [n for n, _ in log]
+    assert names == ["n2m_s0_render_begin", "n2m_s0_render_rounds", "n2m_s0_render_finish"] * 3
+    assert [a[5] for n, a in log if n == "n2m_s0_render_begin"] == [40, 40, 20]
+    assert img.shape == (100, 3) and ws.shape == (100,) and dep.shape == (100,)
+    assert tr.render_rounds == len(tr.RENDER_SCHEDULE) and tr.render_rows == 300
+    rb = tr._render_buf
+    assert rb["cap"] % 128 == 0 and rb["cap"] >= 40 * 16
+    # a schedule that leaves rays alive: the read-back triggers further rounds before the background mix
+    log.clear(); alive_script[:] = [7, 3, 0]
+    tr.render(ro[:30], rd[:30], bg_color=torch.rand(30, 3), chunk=40)
+    assert [n for n, _ in log] == ["n2m_s0_render_begin"] + ["n2m_s0_render_rounds"] * 3 + ["n2m_s0_render_finish"]
+    assert tr.render_rounds == len(tr.RENDER_SCHEDULE) + 2 + 2 and tr.render_rows == 300
+    fin = log[-1][1]
+    assert fin[2] is not None and fin[4] == 30                                    # per-ray background pointer, ray count
+    # shading flag reaches the kernels' parameter block
+    tr.render(ro[:10], rd[:10], shading="diffuse")
+    assert rb["params"].shading_full == 0
