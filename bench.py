@@ -633,7 +633,7 @@ def run_stage1(args):
     from nerf2mesh_b200.stage0 import Stage0Config, Stage0Trainer
     from nerf2mesh_b200.stage1 import Stage1Trainer
     from nerf2mesh_b200.train_synthetic import full_image_rays
-    from oracle import raster_oracle as R           # mesh / projection builders only (host-side input synthesis)
+    R = S                                            # mesh / projection builders (host-side input synthesis)
     h0 = w0 = 800
     t0 = Stage0Trainer(Stage0Config(bound=1.0, num_rays=1024, max_samples=1024 * 128), seed=0)
     v, f = R.icosphere(7)                                         # 327 680 faces ~ the reference's decimate target 3e5 (main.py:101)

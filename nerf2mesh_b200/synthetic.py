@@ -181,3 +181,46 @@ def occupancy_regime(regime, H=128, cascades=1, bound=1.0, seed=1):
     else:
         raise ValueError(regime)
     return grid, packbits_host(grid), bricks
+
+
+# ---- synthetic closed meshes and projections for stage 1 (icosphere-like, F up to 3e5) ----
+def icosphere(subdiv=3, radius=0.6):
+    t = (1.0 + 5 ** 0.5) / 2
+    v = np.array([[-1, t, 0], [1, t, 0], [-1, -t, 0], [1, -t, 0], [0, -1, t], [0, 1, t], [0, -1, -t], [0, 1, -t],
+                  [t, 0, -1], [t, 0, 1], [-t, 0, -1], [-t, 0, 1]], np.float64)
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    f = np.array([[0, 11, 5], [0, 5, 1], [0, 1, 7], [0, 7, 10], [0, 10, 11], [1, 5, 9], [5, 11, 4], [11, 10, 2], [10, 7, 6], [7, 1, 8],
+                  [3, 9, 4], [3, 4, 2], [3, 2, 6], [3, 6, 8], [3, 8, 9], [4, 9, 5], [2, 4, 11], [6, 2, 10], [8, 6, 7], [9, 8, 1]], np.int64)
+    for _ in range(subdiv):
+        cache, verts = {}, list(v)
+
+        def mid(a, b):
+            k = (min(a, b), max(a, b))
+            if k not in cache:
+                m = (verts[a] + verts[b]) / 2
+                verts.append(m / np.linalg.norm(m)); cache[k] = len(verts) - 1
+            return cache[k]
+
+        nf = []
+        for a, b, c in f:
+            ab, bc, ca = mid(a, b), mid(b, c), mid(c, a)
+            nf += [[a, ab, ca], [b, bc, ab], [c, ca, bc], [ab, bc, ca]]
+        v, f = np.array(verts), np.array(nf, np.int64)
+    return (v * radius).astype(np.float32), f.astype(np.int32)
+
+
+def perspective_mvp(cam_pos, fovy=0.6911, aspect=1.0, near=0.05, far=10.0):
+    """OpenGL-style projection * view for a camera at cam_pos looking at the origin (y up); returns [4,4] float32"""
+    c = np.asarray(cam_pos, np.float64)
+    fwd = -c / np.linalg.norm(c)
+    up = np.array([0.0, 0.0, 1.0])
+    if abs(np.dot(fwd, up)) > 0.999:
+        up = np.array([0.0, 1.0, 0.0])
+    right = np.cross(fwd, up); right /= np.linalg.norm(right)
+    tup = np.cross(right, fwd)
+    view = np.eye(4)
+    view[0, :3], view[1, :3], view[2, :3] = right, tup, -fwd
+    view[:3, 3] = -view[:3, :3] @ c
+    f = 1.0 / np.tan(fovy / 2)
+    proj = np.array([[f / aspect, 0, 0, 0], [0, f, 0, 0], [0, 0, (far + near) / (near - far), 2 * far * near / (near - far)], [0, 0, -1, 0]])
+    return (proj @ view).astype(np.float32)

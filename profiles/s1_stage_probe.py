@@ -11,7 +11,7 @@ from nerf2mesh_b200 import _lib, synthetic as S                      # noqa: E40
 from nerf2mesh_b200.stage0 import Stage0Config, Stage0Trainer        # noqa: E402
 from nerf2mesh_b200.stage1 import Stage1Trainer                      # noqa: E402
 from nerf2mesh_b200.train_synthetic import full_image_rays           # noqa: E402
-from oracle import raster_oracle as R                                # noqa: E402  (mesh / projection builders only)
+R = S                                                                # mesh / projection builders
 
 h0 = w0 = 800
 t0 = Stage0Trainer(Stage0Config(bound=1.0, num_rays=1024, max_samples=1024 * 128), seed=0)
