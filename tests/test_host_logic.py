@@ -18,6 +18,22 @@ def declared_symbols():
     return sorted(set(names))
 
 
+def test_headers_are_plain_c(tmp_path):
+    """the drop-in boundary is a C ABI: every header under include/ must compile as C99 on its own (no C++ types, no torch types)"""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        import pytest
+        pytest.skip("gcc not available")
+    for h in sorted(f for f in os.listdir(os.path.join(ROOT, "include")) if f.endswith(".h")):
+        r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", os.path.join(ROOT, "include", h)],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, (h, r.stderr[:500])
+        src = open(os.path.join(ROOT, "include", h)).read()
+        assert "at::" not in src and "torch" not in re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+
+
 def test_library_exports_every_declared_symbol():
     from nerf2mesh_b200 import _lib
     syms = declared_symbols()
