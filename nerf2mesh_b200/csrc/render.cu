@@ -101,7 +101,9 @@ k_r_march(n2m_s0_params p, const float* __restrict__ rays_o, const float* __rest
     const float ox = rays_o[3 * ray], oy = rays_o[3 * ray + 1], oz = rays_o[3 * ray + 2];
     const float dx = rays_d[3 * ray], dy = rays_d[3 * ray + 1], dz = rays_d[3 * ray + 2];
     float4* slab = recs + (size_t)i * n_step;
-    const uint32_t got = march_one(c, rays_t[ray], rays_far[ray], n_step, ox, oy, oz, dx, dy, dz, 1 / dx, 1 / dy, 1 / dz, RecSink{slab, ray});
+    // reciprocal directions as the reference's INFERENCE marcher forms them (raymarching.cu:744; its training kernel divides by d itself)
+    const uint32_t got = march_one(c, rays_t[ray], rays_far[ray], n_step, ox, oy, oz, dx, dy, dz, 1 / (dx + 1e-10f), 1 / (dy + 1e-10f), 1 / (dz + 1e-10f),
+                                   RecSink{slab, ray});
     for (uint32_t k = got; k < n_step; ++k) slab[k] = make_float4(0.f, 0.f, 0.f, __int_as_float(ray));     // the ray ran out: zero tail
 }
 
